@@ -1,0 +1,164 @@
+/*
+ * lcn_b200.h -- C ABI of liblcn_b200.so: the B200 (sm_100a) implementation of the adgx/lcn-pose
+ * LCN hot path.  Plain C, plain pointers and sizes; no torch / TF types.
+ *
+ * The reference has no FFI or plugin layer (it is TensorFlow graph code + NumPy); the boundary it
+ * exposes for this path is the Python class API of network/models_att.py (cgcnn: mask construction,
+ * mask_weights, LCN layer stack, loss, Adam, predict batching) and the function API of
+ * tools/tools.py (image_to_camera_frame, procrustes/align_to_gt) consumed by evaluate.py.  Each
+ * entry point below cites the reference code it replaces (paths relative to the reference root).
+ * Host bindings: lcn_pose_b200/_lib.py (ctypes, used here) and the TF custom-op stub shown in
+ * INTEGRATION.md (cannot be built in this image: no TensorFlow headers).
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a host pointer.
+ *  - every launch-type call takes a cudaStream_t (passed as void*) and only enqueues work; the
+ *    library never synchronises the device and never allocates device memory.
+ *  - every function returns 0 (LCN_OK) or a negative LCN_E* code; the message is available from
+ *    lcn_last_error() (thread local).  No C++ exception crosses the boundary.
+ *  - a model handle is immutable after creation (block lists, offsets); concurrent launches on
+ *    distinct streams with distinct workspaces are safe.
+ *  - matrices are row-major; feature index inside a row is joint-major: column j*F + f
+ *    (network/models_att.py:582); mask index is [input joint, output joint] (:583).
+ */
+#ifndef LCN_B200_H_
+#define LCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCN_JOINTS 17
+
+enum {
+  LCN_OK = 0,
+  LCN_EINVAL = -1,   /* bad argument / unsupported shape */
+  LCN_ECUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
+  LCN_ENOMEM = -3,   /* workspace too small */
+  LCN_ESTATE = -4    /* call order violated (e.g. backward before forward) */
+};
+
+/* arithmetic path of the LCN layers */
+enum {
+  LCN_PATH_FP32 = 0, /* fp32 storage + fp32 FFMA accumulate: the 1e-4 parity path          */
+  LCN_PATH_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM (tcgen05): the 1e-2 path     */
+};
+
+enum {
+  LCN_MASK_LOCALLY_CONNECTED = 0, /* trainable softmax(var,axis=0)*support, models_att.py:547-571 */
+  LCN_MASK_CONSTANT = 1           /* constant mask values (exponential), models_att.py:573-574     */
+};
+
+/* Mirrors the cgcnn constructor kwargs that shape the arithmetic (models_att.py:478-506). */
+typedef struct lcn_model_desc {
+  int32_t F;            /* channels per joint ("F"), multiple of 64                               */
+  int32_t in_F;         /* input features per joint ("in_F"), >= 2                                */
+  int32_t num_layers;   /* residual two_linear blocks ("num_layers")                              */
+  int32_t mask_kind;    /* LCN_MASK_*                                                             */
+  int32_t residual;     /* models_att.py:704                                                      */
+  int32_t batch_norm;   /* models_att.py:664 (only 1 is implemented on device)                    */
+  int32_t max_norm;     /* tf.clip_by_norm(w, 1) before masking, models_att.py:659                */
+  int32_t path;         /* LCN_PATH_*                                                             */
+  float support[LCN_JOINTS * LCN_JOINTS];    /* [in_joint, out_joint] != 0 where a block exists    */
+  float const_mask[LCN_JOINTS * LCN_JOINTS]; /* mask values when mask_kind == LCN_MASK_CONSTANT    */
+} lcn_model_desc;
+
+typedef struct lcn_model lcn_model; /* opaque */
+
+/* ---- library ---- */
+const char* lcn_version(void);
+const char* lcn_last_error(void);
+
+/* ---- mask construction on the host, bit exact (tools/params_help.py:8-20, tools/filter_hub.py:4-20,
+ *      network/models_att.py:14-69) ---- */
+int lcn_neighbour_matrix(int knn, float* h_out /* [17*17] float32 0/1 */);
+int lcn_exponential_matrix(float* h_out /* [17*17] float32 */);
+
+/* ---- model handle ---- */
+int lcn_model_create(const lcn_model_desc* desc, lcn_model** out);
+void lcn_model_destroy(lcn_model* m);
+
+/* Flat fp32 parameter vector (also the layout of Adam m, v and of gradients).  Tensor names follow
+ * the reference's TF variable names: "mask", "linear_model/w1", ".../b1",
+ * "linear_model/two_linear_{i}/w2_{i}", ..., "linear_model/w4", ".../b4",
+ * "<bn layer>/gamma", "<bn layer>/beta". */
+int64_t lcn_model_param_count(const lcn_model* m);
+int lcn_model_num_tensors(const lcn_model* m);
+int lcn_model_tensor_info(const lcn_model* m, int index, char* name_buf, int name_buf_len,
+                          int64_t* offset, int32_t* rows, int32_t* cols);
+
+/* Row geometry.  A "group" is one BatchNorm batch: `bn_group` consecutive poses share statistics
+ * (models_att.py:588-612 reduces over batch x joints; predict() zero-pads the last batch,
+ * :92-97, and the zero rows count).  n_rows = number of real poses; the last group is padded with
+ * zero inputs up to bn_group.  Training uses one group (bn_group = batch). */
+size_t lcn_model_workspace_bytes(const lcn_model* m, int64_t n_rows, int32_t bn_group, int training);
+
+/* (a4) clip_by_norm + mask_weights + pack, for every layer; must run after any parameter change
+ * and before forward.  models_att.py:659-660,690-691,726-728,762-764 and :534-586. */
+int lcn_model_prepare_weights(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, void* stream);
+
+/* (a5)-(a8) cgcnn._inference_lcn, models_att.py:707-775.  d_x [n_rows, 17*in_F] fp32,
+ * d_out [n_rows, 51] fp32.  dropout_rate 0 reproduces predict() (:102); the keep decision of
+ * element e of layer l at step `step` is lcn_dropout_mask()'s. */
+int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes,
+                      const float* d_x, int64_t n_rows, int32_t bn_group, int training,
+                      float dropout_rate, uint64_t seed, uint64_t step, float* d_out, void* stream);
+
+/* (a9)+(autodiff) base_model.loss models_att.py:352-380 and optimizer.compute_gradients :408.
+ * Requires a preceding lcn_model_forward(training=1) on the same workspace.  d_labels [n_rows,51].
+ * d_loss: one float (mean squared error).  d_grads_raw: flat, param layout; holds dL/dWm for the
+ * weight tensors (gradient w.r.t. the masked effective weight) and true gradients for biases / BN. */
+int lcn_model_backward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes,
+                       const float* d_x, const float* d_labels, int64_t n_rows,
+                       float dropout_rate, uint64_t seed, uint64_t step,
+                       float* d_loss, float* d_grads_raw, void* stream);
+
+/* Chain rule through mask_weights, clip_by_norm and the mask softmax:
+ * reduces <dWm, W> per joint pair, then either writes the true dense gradients (d_grads_out != NULL;
+ * used by tests and by data-parallel hosts that want to inspect them) ... */
+int lcn_model_finalize_grads(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes,
+                             const float* d_grads_raw, float* d_grads_out, void* stream);
+
+/* (a10) ... or applies TF1 Adam directly from the raw gradients in one fused pass (models_att.py:404-409):
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (host scalar); theta -= lr_t*m/(sqrt(v)+eps).
+ * `regularization` adds reg*theta to the gradient of w* / b* (models_att.py:362-365).  Also re-runs the
+ * weight preparation for the next forward. */
+int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, float* d_v, void* d_ws, size_t ws_bytes,
+                        const float* d_grads_raw, float lr_t, float beta1, float beta2, float eps,
+                        float regularization, void* stream);
+
+/* Debug / parity taps: copy an internal tensor of the last forward/backward to dense fp32.
+ * kind: 0 = Z_l (pre-BN linear output), 1 = A_l (layer output after BN/act/dropout/residual),
+ *       2 = effective masked weight Wm_l (dense [Kin,Kout]), 3 = mask values [17,17],
+ *       4 = BN mean [groups,F], 5 = BN rstd [groups,F], 6 = dZ_l. */
+int lcn_model_read_tensor(lcn_model* m, void* d_ws, size_t ws_bytes, int kind, int layer,
+                          int64_t n_rows, int32_t bn_group, float* d_dst, void* stream);
+
+/* Dropout keep decisions (1 = keep) exactly as the fused kernels draw them: Philox4x32-10 keyed on
+ * seed, counter (element/4, layer, step).  tf.nn.dropout keeps u >= rate (models_att.py:673). */
+int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int32_t cols, float rate,
+                     uint8_t* d_keep, void* stream);
+
+/* ---- (c) evaluation: evaluate.py:53-61 per pose, batched ----
+ * d_pred [n,17,3] image-frame predictions (after DataReader.denormalize), d_gt [n,17,3] camera-frame
+ * ground truth, d_box [n,4], d_cam [n,4] = (fx, fy, cx, cy), d_root_depth [n], d_action [n] int32 or NULL.
+ * tools.image_to_camera_frame (tools/tools.py:183-194) -> optional tools.align_to_gt / procrustes
+ * (:96-181,197-202; reflections allowed) -> per-joint L2 error.
+ * d_err [n,17] per-joint errors in mm, may be NULL.  d_sums: double [n_actions+1][17+1+1]:
+ * per action (row n_actions = all) 17 per-joint error sums, pose count, count(err < 50 mm);
+ * accumulated (caller zeroes).  n_actions may be 0. */
+int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const float* d_box, const float* d_cam,
+                   const float* d_root_depth, const int32_t* d_action, int32_t n_actions, int64_t n,
+                   int protocol2, float* d_err, double* d_sums, void* stream);
+
+/* (f) DataReader.denormalize arithmetic, tools/data.py:471-472, fused in front of the evaluator:
+ * d_pose [n,17,3] in place; d_res [n,2] = (res_w, res_h). */
+int lcn_denormalize(float* d_pose, const float* d_res, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCN_B200_H_ */

@@ -1,0 +1,216 @@
+// Internal definitions shared by the liblcn_b200 translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "lcn_b200.h"
+
+#define LCN_J 17
+#define LCN_TILE 128          // rows per GEMM tile; BN groups are padded to a multiple of this
+#define LCN_CH 64             // channel chunk: joint-pair blocks are handled as 64x64 sub-blocks
+#define LCN_MAX_LIN 18        // 2 + 2*num_layers, num_layers <= 8
+#define LCN_MAX_TENSORS 80
+#define LCN_BN_EPS 1e-3f      // Keras BatchNormalization default epsilon (models_att.py:599)
+#define LCN_LRELU 0.2f        // tf.nn.leaky_relu default alpha (models_att.py:526)
+
+// Neighbour lists passed to kernels BY VALUE (no device-side plan allocation).
+//   by_out: list a = output joint j  -> idx[j][n] = n-th input joint i of j,  blk = pair id of (i,j)
+//   by_in : list a = input joint i   -> idx[i][n] = n-th output joint j of i, blk = pair id of (i,j)
+// pair id enumerates the support in (i major, j ascending) order.
+struct JointLists {
+  uint8_t cnt[LCN_J];
+  uint8_t idx[LCN_J][LCN_J];
+  int16_t blk[LCN_J][LCN_J];
+};
+
+struct SupportBits {            // sup[i] bit j set <=> block (i -> j) exists
+  uint32_t row[LCN_J];          // outputs of input joint i
+  uint32_t col[LCN_J];          // inputs of output joint j
+  int16_t pair[LCN_J][LCN_J];   // pair id or -1
+};
+
+struct LayerInfo {
+  int Fi, Fo, Kin, Kout;
+  int64_t w_off, b_off, gamma_off, beta_off;  // offsets into the flat parameter vector (-1: none)
+  int has_bn;                                 // BN + LeakyReLU + dropout follow the linear op
+  int res_from;                               // activation index added after this layer, or -1
+};
+
+enum { SEG_MASK = 0, SEG_W = 1, SEG_B = 2, SEG_BN = 3 };
+struct SegInfo {                // one parameter tensor, for the multi-tensor Adam kernel
+  int64_t off, size;
+  int32_t kind, layer;
+  int32_t chunk_start;          // first Adam chunk (of LCN_ADAM_CHUNK elements) of this tensor
+};
+#define LCN_ADAM_CHUNK 4096
+struct SegTable {
+  int n;
+  int total_chunks;
+  SegInfo s[LCN_MAX_TENSORS];
+};
+
+struct TensorMeta {
+  std::string name;
+  int64_t off;
+  int rows, cols;
+};
+
+struct lcn_model {
+  lcn_model_desc d;
+  int n_lin, n_bn, P, FC, nnz;
+  JointLists by_out, by_in;
+  SupportBits sup;
+  LayerInfo L[LCN_MAX_LIN];
+  SegTable segs;
+  std::vector<TensorMeta> tensors;
+  int64_t n_params, mask_off;
+  int sm_count;
+};
+
+// Per-layer device scalars (live in the workspace)
+struct LayerScalars {
+  double norm2;      // ||W||_F^2 of the current weights
+  double sdot;       // <dWc, W>
+  float inv_norm;    // 1/max(||W||,1)   (1 if !max_norm)
+  float coef;        // sdot/||W||^3 if ||W|| > 1 else 0
+  float clipped;     // 1 if ||W|| > 1
+  float pad;
+};
+
+// Workspace layout, a pure function of (model, n_rows, bn_group, training).
+struct WsLayout {
+  int64_t n_rows, rows_pad;
+  int bn_group, gstride, n_groups, tiles, tiles_per_group, training;
+  size_t es;                         // activation storage element size
+  size_t off_scalars;                // LayerScalars[LCN_MAX_LIN]
+  size_t off_mask;                   // float[289] mask values
+  size_t off_pairdot;                // float[n_lin][289]  <dWm, W> per support pair
+  size_t off_loss;                   // double[2]
+  size_t off_wm_first, off_wm_last;  // dense masked fp32 effective weights of the edge layers
+  size_t off_wp32;                   // fp32 packed mid-layer blocks  [mid][pair][FC][FC][64][64]
+  size_t off_wp16f, off_wp16b;       // bf16 UMMA-layout packed blocks (forward / transposed)
+  size_t off_part;                   // float[tiles][P][2] BN partials (mean, M2)
+  size_t off_bnstat;                 // float[n_bn][n_groups][F][2]  (mean, rstd)
+  size_t off_bnsum;                  // float[n_bn][F][2]  backward sums (sum dy, sum dy*xhat)
+  size_t off_out;                    // float[rows_pad][51] copy of the prediction (training)
+  size_t off_dout;                   // float[rows_pad][51]
+  size_t off_z, z_stride; int n_z;   // Z buffers
+  size_t off_a, a_stride; int n_a;   // A buffers
+  size_t off_d, d_stride; int n_d;   // gradient ping-pong buffers (training)
+  size_t off_dz;                     // dZ buffer (training)
+  size_t total;
+};
+
+WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int training);
+
+void lcn_set_error(const char* fmt, ...);
+#define LCN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      lcn_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return LCN_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+#define LCN_CHECK_LAUNCH() LCN_CHECK_CUDA(cudaGetLastError())
+#define LCN_REQUIRE(cond, ...)   \
+  do {                           \
+    if (!(cond)) {               \
+      lcn_set_error(__VA_ARGS__); \
+      return LCN_EINVAL;         \
+    }                            \
+  } while (0)
+
+// ---- launch wrappers implemented in the kernel translation units ----
+struct FwdArgs {                 // one call of the forward pass
+  const lcn_model* m;
+  const float* params;
+  char* ws;
+  WsLayout lay;
+  const float* x;
+  float* out;
+  float dropout_rate;
+  uint64_t seed, step;
+  cudaStream_t st;
+};
+
+int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
+                       bool recompute_norm, cudaStream_t st);
+int lcn_launch_forward(const FwdArgs& a);
+int lcn_launch_backward(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
+                        const float* x, const float* labels, float dropout_rate, uint64_t seed,
+                        uint64_t step, float* loss, float* grads_raw, cudaStream_t st);
+int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
+                             const float* grads_raw, float* grads_out, cudaStream_t st);
+int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
+                    const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg,
+                    cudaStream_t st);
+int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,
+                           float* dst, cudaStream_t st);
+
+// tcgen05 (bf16) mid-layer kernels, lcn_gemm_tc.cu.  transposed=0: Y = A*Wm (+bias, BN partials);
+// transposed=1: dA = dZ*Wm^T (+addend).
+int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed,
+                const __nv_bfloat16* A, const char* wpacked, const float* bias, const __nv_bfloat16* addend,
+                __nv_bfloat16* Y, float* part, cudaStream_t st);
+int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ,
+                 float* dW /* dense [P,P] */, cudaStream_t st);
+bool lcn_tc_enabled();
+
+// ---- device helpers ----
+__device__ __forceinline__ float lcn_ld(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float lcn_ld(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void lcn_st(float* p, size_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void lcn_st(__nv_bfloat16* p, size_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// 4-wide vector access (16 B for fp32, 8 B for bf16); i is the element index, multiple of 4
+__device__ __forceinline__ float4 lcn_ld4(const float* p, size_t i) {
+  return *reinterpret_cast<const float4*>(p + i);
+}
+__device__ __forceinline__ float4 lcn_ld4(const __nv_bfloat16* p, size_t i) {
+  uint2 u = *reinterpret_cast<const uint2*>(p + i);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void lcn_st4(float* p, size_t i, float4 v) {
+  *reinterpret_cast<float4*>(p + i) = v;
+}
+__device__ __forceinline__ void lcn_st4(__nv_bfloat16* p, size_t i, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p + i) = u;
+}
+
+// Philox4x32-10 counter-based generator; one call yields the 4 uniforms of elements 4*idx4 .. 4*idx4+3.
+__device__ __host__ __forceinline__ void lcn_philox4(uint64_t seed, uint64_t step, uint32_t layer, uint64_t idx4,
+                                                     uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = layer, c3 = (uint32_t)step;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// keep decision of tf.nn.dropout: u >= rate with u in [0,1) (24-bit)
+__device__ __host__ __forceinline__ bool lcn_keep(uint32_t bits, float rate) {
+  return (float)(bits >> 8) * (1.0f / 16777216.0f) >= rate;
+}

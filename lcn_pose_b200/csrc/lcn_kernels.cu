@@ -1,0 +1,1220 @@
+// CUDA-core kernels of the LCN hot path: weight preparation (clip_by_norm + mask + pack), the edge
+// layers (17*in_F -> 17*F and 17*F -> 51), BatchNorm statistics / apply, the fp32 block-sparse GEMMs
+// of the 1e-4 parity path, the whole backward pass and the fused masked TF1-Adam step.
+// The bf16 tensor-core (tcgen05) mid-layer GEMMs live in lcn_gemm_tc.cu.
+//
+// Reference semantics implemented here (paths relative to the reference root):
+//   network/models_att.py:534-586 (mask, mask_weights), :588-612 (BN), :630-775 (layers, head),
+//   :352-421 (loss, Adam); SURVEY.md section 9 lists the TF behaviours relied on.
+#include <string.h>
+
+#include <algorithm>
+
+#include "lcn_internal.cuh"
+
+struct LinTable {
+  int n;
+  int64_t w_off[LCN_MAX_LIN];
+  int32_t Fi[LCN_MAX_LIN], Fo[LCN_MAX_LIN];
+};
+struct PairTable {
+  uint8_t pi[LCN_J * LCN_J], pj[LCN_J * LCN_J];
+};
+struct ConstMask {
+  float v[LCN_J * LCN_J];
+};
+
+static LinTable make_lin(const lcn_model* m) {
+  LinTable t;
+  t.n = m->n_lin;
+  for (int l = 0; l < m->n_lin; ++l) {
+    t.w_off[l] = m->L[l].w_off;
+    t.Fi[l] = m->L[l].Fi;
+    t.Fo[l] = m->L[l].Fo;
+  }
+  return t;
+}
+static PairTable make_pairs(const lcn_model* m) {
+  PairTable t;
+  for (int i = 0; i < LCN_J; ++i)
+    for (int j = 0; j < LCN_J; ++j)
+      if (m->sup.pair[i][j] >= 0) {
+        t.pi[m->sup.pair[i][j]] = (uint8_t)i;
+        t.pj[m->sup.pair[i][j]] = (uint8_t)j;
+      }
+  return t;
+}
+
+__device__ __forceinline__ double block_reduce_sum_d(double v, double* sh /* >= 32 */) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation
+// ------------------------------------------------------------------------------------------------
+__global__ void k_zero_norm2(LayerScalars* sc, int n) {
+  if (threadIdx.x < n) sc[threadIdx.x].norm2 = 0.0;
+}
+
+// ||W_l||_F^2 of the full, unmasked matrix (tf.clip_by_norm, models_att.py:659)
+__global__ void k_sumsq(const float* __restrict__ params, LinTable lt, LayerScalars* sc) {
+  __shared__ double sh[32];
+  int l = blockIdx.y;
+  int64_t n4 = (int64_t)lt.Fi[l] * lt.Fo[l] * LCN_J * LCN_J / 4;
+  const float4* w = reinterpret_cast<const float4*>(params + lt.w_off[l]);
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = w[i];
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  s = block_reduce_sum_d(s, sh);
+  if (threadIdx.x == 0) atomicAdd(&sc[l].norm2, s);
+}
+
+// mask = softmax(var, axis=0) * support (models_att.py:569-571) or the constant; per-layer clip scale
+__global__ void k_mask_scalars(const float* __restrict__ params, int64_t mask_off, SupportBits sup,
+                               ConstMask cmask, int n_lin, int max_norm,
+                               LayerScalars* sc, float* mask_out) {
+  int t = threadIdx.x;
+  if (t < LCN_J * LCN_J) {
+    int i = t / LCN_J, j = t % LCN_J;
+    float mval;
+    if (mask_off >= 0) {
+      const float* var = params + mask_off;
+      float mx = -INFINITY;
+      for (int k = 0; k < LCN_J; ++k) mx = fmaxf(mx, var[k * LCN_J + j]);
+      float den = 0.f;
+      for (int k = 0; k < LCN_J; ++k) den += expf(var[k * LCN_J + j] - mx);
+      mval = expf(var[t] - mx) / den;
+    } else {
+      mval = cmask.v[t];
+    }
+    mask_out[t] = ((sup.row[i] >> j) & 1u) ? mval : 0.f;
+  }
+  if (t < n_lin) {
+    double nrm = sqrt(sc[t].norm2);
+    bool clip = max_norm && nrm > 1.0;
+    sc[t].inv_norm = clip ? (float)(1.0 / nrm) : 1.0f;
+    sc[t].clipped = clip ? 1.f : 0.f;
+  }
+}
+
+// dense masked effective weight of an edge layer: Wm = W * inv_norm * mask[i,j]
+__global__ void k_pack_edge(const float* __restrict__ w, int Fi, int Fo, const LayerScalars* sc, int l,
+                            const float* __restrict__ mask, float* __restrict__ wm) {
+  int Kout = LCN_J * Fo;
+  int64_t n = (int64_t)LCN_J * Fi * Kout;
+  float inv = sc[l].inv_norm;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(e / Kout), c = (int)(e - (int64_t)r * Kout);
+    wm[e] = w[e] * inv * mask[(r / Fi) * LCN_J + c / Fo];
+  }
+}
+
+// packed 64x64 sub-blocks of the mid layers.  grid (nnz*FC*FC, n_mid), 256 threads.
+//   wp32 : [mid][pair][hi][ho][fi][fo] fp32                (CUDA-core GEMMs)
+//   wp16f: bf16, UMMA K-major SWIZZLE_128B image of B[n=fo][k=fi], input-chunk-major order
+//   wp16b: bf16, same for the transposed operand B[n=fi][k=fo], output-chunk-major order
+__global__ void k_pack_mid(const float* __restrict__ params, LinTable lt, PairTable pt, SupportBits sup,
+                           const LayerScalars* sc, const float* __restrict__ mask, int F, int FC, int nnz,
+                           float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
+                           __nv_bfloat16* __restrict__ wp16b) {
+  int mid = blockIdx.y, l = mid + 1;
+  int sb = blockIdx.x;
+  int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
+  int i = pt.pi[p], j = pt.pj[p];
+  int P = LCN_J * F;
+  float scale = sc[l].inv_norm * mask[i * LCN_J + j];
+  const float* w = params + lt.w_off[l];
+  // destination sub-block slots
+  int base_i = 0, base_j = 0;
+  for (int q = 0; q < i; ++q) base_i += __popc(sup.row[q]);
+  for (int q = 0; q < j; ++q) base_j += __popc(sup.col[q]);
+  int rank_out = __popc(sup.row[i] & ((1u << j) - 1u));   // rank of j among outputs of i
+  int rank_in = __popc(sup.col[j] & ((1u << i) - 1u));    // rank of i among inputs of j
+  int cnt_out = __popc(sup.row[i]), cnt_in = __popc(sup.col[j]);
+  size_t slot_f = (size_t)FC * FC * base_i + (size_t)hi * (cnt_out * FC) + rank_out * FC + ho;
+  size_t slot_b = (size_t)FC * FC * base_j + (size_t)ho * (cnt_in * FC) + rank_in * FC + hi;
+  size_t mid_sb = (size_t)nnz * FC * FC;
+  float* d32 = wp32 + ((size_t)mid * mid_sb + sb) * 4096;
+  __nv_bfloat16* df = wp16f + ((size_t)mid * mid_sb + slot_f) * 4096;
+  __nv_bfloat16* db = wp16b + ((size_t)mid * mid_sb + slot_b) * 4096;
+  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+    int fi = e >> 6, fo = e & 63;
+    float v = w[(size_t)(i * F + hi * 64 + fi) * P + j * F + ho * 64 + fo] * scale;
+    d32[e] = v;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    df[fo * 64 + ((((fi >> 3) ^ (fo & 7)) << 3) | (fi & 7))] = h;   // row n=fo, k=fi
+    db[fi * 64 + ((((fo >> 3) ^ (fi & 7)) << 3) | (fo & 7))] = h;   // row n=fi, k=fo
+  }
+}
+
+int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
+                       bool recompute_norm, cudaStream_t st) {
+  LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
+  float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
+  LinTable lt = make_lin(m);
+  if (recompute_norm) {
+    k_zero_norm2<<<1, 32, 0, st>>>(sc, m->n_lin);
+    k_sumsq<<<dim3(64, m->n_lin), 256, 0, st>>>(params, lt, sc);
+    LCN_CHECK_LAUNCH();
+  }
+  ConstMask cmask;
+  memcpy(cmask.v, m->d.const_mask, sizeof(cmask.v));
+  k_mask_scalars<<<1, 320, 0, st>>>(params, m->mask_off, m->sup, cmask, m->n_lin, m->d.max_norm, sc, mask);
+  LCN_CHECK_LAUNCH();
+  int last = m->n_lin - 1;
+  k_pack_edge<<<64, 256, 0, st>>>(params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
+                                  reinterpret_cast<float*>(ws + lay.off_wm_first));
+  k_pack_edge<<<64, 256, 0, st>>>(params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
+                                  reinterpret_cast<float*>(ws + lay.off_wm_last));
+  int n_mid = m->n_lin - 2;
+  if (n_mid > 0) {
+    k_pack_mid<<<dim3(m->nnz * m->FC * m->FC, n_mid), 256, 0, st>>>(
+        params, lt, make_pairs(m), m->sup, sc, mask, m->d.F, m->FC, m->nnz,
+        reinterpret_cast<float*>(ws + lay.off_wp32), reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f),
+        reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b));
+  }
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row geometry helpers
+// ------------------------------------------------------------------------------------------------
+struct RowGeom {
+  int64_t n_rows;   // real poses
+  int bn_group;     // rows per BN group (logical)
+  int gstride;      // physical rows per group (multiple of 128)
+};
+// physical row -> (valid for BN statistics, source row or -1 when zero padded)
+__device__ __forceinline__ bool row_valid(const RowGeom& g, int64_t pr, int64_t* src) {
+  int64_t grp = pr / g.gstride;
+  int rin = (int)(pr - grp * g.gstride);
+  int64_t s = grp * g.bn_group + rin;
+  *src = (rin < g.bn_group && s < g.n_rows) ? s : -1;
+  return rin < g.bn_group;
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer: Z0 = X * Wm1 + b1  (models_att.py:729), K = 17*in_F, plus BN partials
+// grid (tiles, ceil(P/256)), 256 threads; thread = one output column, 128 rows
+// ------------------------------------------------------------------------------------------------
+template <typename T, int IN_F>
+__global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x, RowGeom g,
+                                                     const float* __restrict__ wm, const float* __restrict__ bias,
+                                                     T* __restrict__ Z, float* __restrict__ part, int P) {
+  constexpr int KIN = LCN_J * IN_F;
+  __shared__ float xs[KIN][LCN_TILE];
+  __shared__ unsigned char valid_s[LCN_TILE];
+  int tile = blockIdx.x;
+  for (int e = threadIdx.x; e < LCN_TILE * KIN; e += blockDim.x) {
+    int r = e / KIN, k = e - r * KIN;
+    int64_t src;
+    bool v = row_valid(g, (int64_t)tile * LCN_TILE + r, &src);
+    xs[k][r] = (src >= 0) ? x[src * KIN + k] : 0.f;
+    if (k == 0) valid_s[r] = v;
+  }
+  __syncthreads();
+  int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= P) return;
+  float w[KIN];
+#pragma unroll
+  for (int k = 0; k < KIN; ++k) w[k] = wm[(size_t)k * P + c];
+  float b = bias[c];
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+  int nv = 0;
+  for (int r4 = 0; r4 < LCN_TILE; r4 += 4) {
+    float acc[4] = {b, b, b, b};
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+      float4 xv = *reinterpret_cast<const float4*>(&xs[k][r4]);
+      acc[0] = fmaf(xv.x, w[k], acc[0]);
+      acc[1] = fmaf(xv.y, w[k], acc[1]);
+      acc[2] = fmaf(xv.z, w[k], acc[2]);
+      acc[3] = fmaf(xv.w, w[k], acc[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int r = r4 + q;
+      bool v = valid_s[r];
+      float val = v ? acc[q] : 0.f;
+      lcn_st(Z, ((size_t)tile * LCN_TILE + r) * P + c, val);
+      if (v) {
+        if (nv == 0) shift = val;
+        float d = val - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+        ++nv;
+      }
+    }
+  }
+  float mean = shift + s1 / (float)nv;
+  float m2 = fmaxf(s2 - s1 * s1 / (float)nv, 0.f);
+  part[((size_t)tile * P + c) * 2 + 0] = mean;
+  part[((size_t)tile * P + c) * 2 + 1] = m2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 block-sparse GEMM of the mid layers (CUDA cores).
+//   TRANSPOSED = false: Z[tile, oc] = sum_{i in N(j)} A[tile, i-chunks] * Wp(i->j) + bias, BN partials
+//   TRANSPOSED = true : dA[tile, ic] = sum_{j in O(i)} dZ[tile, j-chunks] * Wp(i->j)^T (+ addend)
+// grid (tiles, 17*FC), 256 threads, thread = 8 rows x 4 cols of the 128 x 64 output tile.
+// ------------------------------------------------------------------------------------------------
+#define GS_APAD 65
+#define GS_BPAD 68
+template <typename T, bool TRANSPOSED>
+__global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, const float* __restrict__ wp32,
+                                                   const float* __restrict__ bias, const T* __restrict__ addend,
+                                                   T* __restrict__ Y, float* __restrict__ part, JointLists lists,
+                                                   int P, int FC, int bn_group, int gstride) {
+  extern __shared__ float smem[];
+  float* As = smem;                          // [128][65]
+  float* Bs = smem + LCN_TILE * GS_APAD;     // [64][68]
+  __shared__ float red[4][64];
+  int tile = blockIdx.x, oc = blockIdx.y;
+  int a = oc / FC, ha = oc % FC;             // joint / sub-chunk owning the output columns
+  int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  size_t row0 = (size_t)tile * LCN_TILE;
+  float acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+
+  int cnt = lists.cnt[a];
+  for (int n = 0; n < cnt; ++n) {
+    int b = lists.idx[a][n];
+    int p = lists.blk[a][n];
+    for (int h = 0; h < FC; ++h) {
+      int col0 = (b * FC + h) * 64;
+      // sub-block (pair p, hi, ho): forward hi = h (input side), ho = ha; transposed hi = ha, ho = h
+      int hi = TRANSPOSED ? ha : h, ho = TRANSPOSED ? h : ha;
+      const float* blk = wp32 + ((size_t)(p * FC + hi) * FC + ho) * 4096;
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int f = tid + 256 * it;
+        int r = f >> 4, kq = f & 15;
+        float4 v = lcn_ld4(A, (row0 + r) * P + col0 + kq * 4);
+        float* dst = As + r * GS_APAD + kq * 4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        int f = tid + 256 * it;                 // float4 index in the 64x64 block
+        int r = f >> 4, cq = f & 15;
+        float4 v = *reinterpret_cast<const float4*>(blk + r * 64 + cq * 4);
+        if (!TRANSPOSED) {
+          *reinterpret_cast<float4*>(Bs + r * GS_BPAD + cq * 4) = v;   // Bs[k=fi][n=fo]
+        } else {                                                       // Bs[k=fo][n=fi]
+          Bs[(cq * 4 + 0) * GS_BPAD + r] = v.x;
+          Bs[(cq * 4 + 1) * GS_BPAD + r] = v.y;
+          Bs[(cq * 4 + 2) * GS_BPAD + r] = v.z;
+          Bs[(cq * 4 + 3) * GS_BPAD + r] = v.w;
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        float4 bv = *reinterpret_cast<const float4*>(Bs + k * GS_BPAD + tx * 4);
+        float av[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) av[r] = As[(ty * 8 + r) * GS_APAD + k];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          acc[r][0] = fmaf(av[r], bv.x, acc[r][0]);
+          acc[r][1] = fmaf(av[r], bv.y, acc[r][1]);
+          acc[r][2] = fmaf(av[r], bv.z, acc[r][2]);
+          acc[r][3] = fmaf(av[r], bv.w, acc[r][3]);
+        }
+      }
+    }
+  }
+  int ccol = oc * 64 + tx * 4;
+  if (!TRANSPOSED) {
+    float4 bv = *reinterpret_cast<const float4*>(bias + ccol);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float4 v = make_float4(acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w);
+      lcn_st4(Y, (row0 + ty * 8 + r) * P + ccol, v);
+      float* dst = As + (ty * 8 + r) * GS_APAD + tx * 4;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    // exact two-pass column statistics over the valid rows of this tile
+    int tig = tile % (gstride / LCN_TILE);
+    int nvalid = min(LCN_TILE, bn_group - tig * LCN_TILE);
+    int col = tid & 63, prt = tid >> 6;
+    float s = 0.f;
+    for (int r = prt * 32; r < prt * 32 + 32; ++r)
+      if (r < nvalid) s += As[r * GS_APAD + col];
+    red[prt][col] = s;
+    __syncthreads();
+    float mean = (red[0][col] + red[1][col] + red[2][col] + red[3][col]) / (float)nvalid;
+    __syncthreads();
+    float q = 0.f;
+    for (int r = prt * 32; r < prt * 32 + 32; ++r)
+      if (r < nvalid) {
+        float d = As[r * GS_APAD + col] - mean;
+        q = fmaf(d, d, q);
+      }
+    red[prt][col] = q;
+    __syncthreads();
+    if (prt == 0) {
+      float m2 = red[0][col] + red[1][col] + red[2][col] + red[3][col];
+      part[((size_t)tile * P + oc * 64 + col) * 2 + 0] = mean;
+      part[((size_t)tile * P + oc * 64 + col) * 2 + 1] = m2;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (addend != nullptr) {
+        float4 ad = lcn_ld4(addend, (row0 + ty * 8 + r) * P + ccol);
+        v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+      }
+      lcn_st4(Y, (row0 + ty * 8 + r) * P + ccol, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics: merge per-tile (mean, M2) partials over the tiles of a group and the 17
+// joints (Keras BN axis=-1 on [B,17,F]: per channel over batch x joints, biased variance).
+// grid n_groups, 256 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bn_finalize(const float* __restrict__ part, float* __restrict__ stat, int P, int F,
+                              int tiles_per_group, int bn_group) {
+  __shared__ double sn[256], smean[256], sm2[256];
+  int g = blockIdx.x, tid = threadIdx.x;
+  int f = tid % F, slice = tid / F, nsl = 256 / F;
+  double n = 0, mean = 0, m2 = 0;
+  int items = tiles_per_group * LCN_J;
+  for (int it = slice; it < items; it += nsl) {
+    int t = it / LCN_J, j = it - t * LCN_J;
+    double nb = (double)min(LCN_TILE, bn_group - t * LCN_TILE);
+    size_t o = ((size_t)(g * tiles_per_group + t) * P + j * F + f) * 2;
+    double mb = part[o], qb = part[o + 1];
+    double nn = n + nb, delta = mb - mean;
+    mean += delta * nb / nn;
+    m2 += qb + delta * delta * n * nb / nn;
+    n = nn;
+  }
+  sn[tid] = n; smean[tid] = mean; sm2[tid] = m2;
+  __syncthreads();
+  if (slice == 0) {
+    for (int s = 1; s < nsl; ++s) {
+      double nb = sn[s * F + f], mb = smean[s * F + f], qb = sm2[s * F + f];
+      if (nb == 0) continue;
+      double nn = n + nb, delta = mb - mean;
+      mean += delta * nb / nn;
+      m2 += qb + delta * delta * n * nb / nn;
+      n = nn;
+    }
+    double var = m2 / n;
+    stat[((size_t)g * F + f) * 2 + 0] = (float)mean;
+    stat[((size_t)g * F + f) * 2 + 1] = (float)(1.0 / sqrt(var + (double)LCN_BN_EPS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply + LeakyReLU(0.2) + dropout + residual (models_att.py:664-673,704).
+// grid rows_pad/16, block P/4 threads; thread = 4 consecutive columns, 16 rows.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ Aout, int P, int F,
+                         int bn_group, int gstride, float rate, uint64_t seed, uint64_t step, int layer) {
+  int c4 = threadIdx.x * 4;
+  int f0 = c4 % F;
+  int64_t pr0 = (int64_t)blockIdx.x * 16;
+  int g = (int)(pr0 / gstride);
+  float sc[4], sh[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float mean = stat[((size_t)g * F + f0 + q) * 2], rstd = stat[((size_t)g * F + f0 + q) * 2 + 1];
+    sc[q] = gamma[f0 + q] * rstd;
+    sh[q] = beta[f0 + q] - mean * sc[q];
+  }
+  float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  for (int r = 0; r < 16; ++r) {
+    int64_t pr = pr0 + r;
+    size_t o = (size_t)pr * P + c4;
+    if ((int)(pr % gstride) >= bn_group) {
+      lcn_st4(Aout, o, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    float4 z = lcn_ld4(Z, o);
+    float y[4] = {fmaf(z.x, sc[0], sh[0]), fmaf(z.y, sc[1], sh[1]), fmaf(z.z, sc[2], sh[2]), fmaf(z.w, sc[3], sh[3])};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[q] = y[q] > 0.f ? y[q] : LCN_LRELU * y[q];
+    if (rate > 0.f) {
+      uint32_t rb[4];
+      lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(o >> 2), rb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y[q] = lcn_keep(rb[q], rate) ? y[q] * inv_keep : 0.f;
+    }
+    if (res != nullptr) {
+      float4 rv = lcn_ld4(res, o);
+      y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+    }
+    lcn_st4(Aout, o, make_float4(y[0], y[1], y[2], y[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// last layer + output head: out = A * Wm4 + b4, xy residual from the 2D input (models_att.py:750-773)
+// grid tiles, 128 threads (thread = row), input chunks streamed through shared memory.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_last_layer(const T* __restrict__ A, const float* __restrict__ wm,
+                                                    const float* __restrict__ bias, const float* __restrict__ x,
+                                                    int in_F, RowGeom g, float* __restrict__ out_user,
+                                                    float* __restrict__ out_ws, SupportBits sup, int P, int FC) {
+  extern __shared__ float smem[];
+  float* As = smem;                         // [128][65]
+  float* Ws = smem + LCN_TILE * GS_APAD;    // [64][17][4]
+  int tile = blockIdx.x, tid = threadIdx.x;
+  size_t row0 = (size_t)tile * LCN_TILE;
+  float acc[LCN_J][3];
+#pragma unroll
+  for (int j = 0; j < LCN_J; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+  for (int ic = 0; ic < LCN_J * FC; ++ic) {
+    int i = ic / FC;
+    __syncthreads();
+    for (int f = tid; f < LCN_TILE * 16; f += 128) {
+      int r = f >> 4, kq = f & 15;
+      float4 v = lcn_ld4(A, (row0 + r) * P + ic * 64 + kq * 4);
+      float* dst = As + r * GS_APAD + kq * 4;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    for (int e = tid; e < 64 * LCN_J * 3; e += 128) {
+      int k = e / (LCN_J * 3), jc = e - k * (LCN_J * 3);
+      Ws[(k * LCN_J + jc / 3) * 4 + jc % 3] = wm[(size_t)(ic * 64 + k) * (LCN_J * 3) + jc];
+    }
+    __syncthreads();
+    uint32_t outs = sup.row[i];
+    for (int k = 0; k < 64; ++k) {
+      float av = As[tid * GS_APAD + k];
+#pragma unroll
+      for (int j = 0; j < LCN_J; ++j) {
+        if ((outs >> j) & 1u) {
+          float4 wv = *reinterpret_cast<const float4*>(Ws + (k * LCN_J + j) * 4);
+          acc[j][0] = fmaf(av, wv.x, acc[j][0]);
+          acc[j][1] = fmaf(av, wv.y, acc[j][1]);
+          acc[j][2] = fmaf(av, wv.z, acc[j][2]);
+        }
+      }
+    }
+  }
+  int64_t pr = (int64_t)row0 + tid, src;
+  bool valid = row_valid(g, pr, &src);
+  int kin = LCN_J * in_F;
+#pragma unroll
+  for (int j = 0; j < LCN_J; ++j) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = acc[j][c] + bias[j * 3 + c];
+      if (c < 2 && src >= 0) v += x[src * kin + j * in_F + c];
+      if (out_ws != nullptr) out_ws[(size_t)pr * 51 + j * 3 + c] = valid ? v : 0.f;
+      if (src >= 0) out_user[src * 51 + j * 3 + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss and its gradient: mean((out-labels)^2) over B*51 (models_att.py:356); dOut = 2 (out-y)/(B*51)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_loss_dout(const float* __restrict__ out_ws, const float* __restrict__ labels, int64_t n_rows,
+                            int64_t rows_pad, float* __restrict__ dout, double* loss_acc) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  float inv = 2.0f / ((float)n_rows * 51.f);
+  int64_t n = rows_pad * 51;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pr = e / 51;
+    float d = 0.f;
+    if (pr < n_rows) {
+      d = out_ws[e] - labels[e];
+      s += (double)d * d;
+    }
+    dout[e] = d * inv;
+  }
+  s = block_reduce_sum_d(s, sh);
+  if (threadIdx.x == 0) atomicAdd(loss_acc, s);
+}
+__global__ void k_loss_final(const double* loss_acc, int64_t n_rows, float* loss_out) {
+  loss_out[0] = (float)(loss_acc[0] / ((double)n_rows * 51.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// last layer backward: dA = dOut * Wm4^T, dWm4 = A^T dOut, db4 = sum_rows dOut
+// grid (rows_pad/rows_per_block, ceil(P/256)), 256 threads; thread = one input column
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_last_layer_bwd(const T* __restrict__ A, const float* __restrict__ dout,
+                                                        const float* __restrict__ wm, T* __restrict__ dA,
+                                                        float* __restrict__ dwm, float* __restrict__ db, int P,
+                                                        int rows_per_block) {
+  __shared__ float ds[32][52];
+  int c = blockIdx.y * 256 + threadIdx.x;
+  bool act = c < P;
+  float w[51], gw[51];
+#pragma unroll
+  for (int q = 0; q < 51; ++q) {
+    w[q] = act ? wm[(size_t)c * 51 + q] : 0.f;
+    gw[q] = 0.f;
+  }
+  float sdb = 0.f;
+  size_t row0 = (size_t)blockIdx.x * rows_per_block;
+  for (int rc = 0; rc < rows_per_block; rc += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 51; e += 256) ds[e / 51][e % 51] = dout[(row0 + rc) * 51 + e];
+    __syncthreads();
+    if (blockIdx.y == 0 && threadIdx.x < 51)
+      for (int r = 0; r < 32; ++r) sdb += ds[r][threadIdx.x];
+    if (act) {
+      for (int r = 0; r < 32; ++r) {
+        size_t o = (row0 + rc + r) * P + c;
+        float av = lcn_ld(A, o), da = 0.f;
+#pragma unroll
+        for (int q = 0; q < 51; ++q) {
+          float d = ds[r][q];
+          da = fmaf(w[q], d, da);
+          gw[q] = fmaf(av, d, gw[q]);
+        }
+        lcn_st(dA, o, da);
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int q = 0; q < 51; ++q) atomicAdd(&dwm[(size_t)c * 51 + q], gw[q]);
+  }
+  if (blockIdx.y == 0 && threadIdx.x < 51) atomicAdd(&db[threadIdx.x], sdb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN / LeakyReLU / dropout backward (training = one group).
+//   dy   = dOut * keep/(1-rate) * (ybn > 0 ? 1 : 0.2)
+//   sums = (sum dy, sum dy*xhat) per channel        [k_bn_bwd_reduce]
+//   dZ   = gamma*rstd*(dy - s1/n - xhat*s2/n)       [k_bn_bwd_apply], db = sum_rows dZ
+// grid rows_pad/16, block P/4.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void bn_bwd_dy(const T* dOut, const T* Z, size_t o, const float* sc, const float* sh,
+                                          const float* mean, const float* rstd, float rate, float inv_keep,
+                                          uint64_t seed, uint64_t step, int layer, float dy[4], float xh[4]) {
+  float4 z = lcn_ld4(Z, o), d = lcn_ld4(dOut, o);
+  float zz[4] = {z.x, z.y, z.z, z.w}, dd[4] = {d.x, d.y, d.z, d.w};
+  uint32_t rb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  if (rate > 0.f) lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(o >> 2), rb);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float ybn = fmaf(zz[q], sc[q], sh[q]);
+    float v = dd[q];
+    if (rate > 0.f) v = lcn_keep(rb[q], rate) ? v * inv_keep : 0.f;
+    dy[q] = ybn > 0.f ? v : LCN_LRELU * v;
+    xh[q] = (zz[q] - mean[q]) * rstd[q];
+  }
+}
+
+template <typename T>
+__global__ void k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float* __restrict__ sums, int P, int F, int bn_group, float rate, uint64_t seed,
+                                uint64_t step, int layer) {
+  extern __shared__ float red[];   // [P/4][8]
+  int c4 = threadIdx.x * 4, f0 = c4 % F;
+  float sc[4], sh[4], mean[4], rstd[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    mean[q] = stat[(f0 + q) * 2];
+    rstd[q] = stat[(f0 + q) * 2 + 1];
+    sc[q] = gamma[f0 + q] * rstd[q];
+    sh[q] = beta[f0 + q] - mean[q] * sc[q];
+  }
+  float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  int64_t pr0 = (int64_t)blockIdx.x * 16;
+  for (int r = 0; r < 16; ++r) {
+    int64_t pr = pr0 + r;
+    if (pr >= bn_group) break;
+    float dy[4], xh[4];
+    bn_bwd_dy(dOut, Z, (size_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s1[q] += dy[q];
+      s2[q] = fmaf(dy[q], xh[q], s2[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    red[threadIdx.x * 8 + q] = s1[q];
+    red[threadIdx.x * 8 + 4 + q] = s2[q];
+  }
+  __syncthreads();
+  int per = F / 4;
+  if ((int)threadIdx.x < per) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < LCN_J; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] += red[(threadIdx.x + j * per) * 8 + q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(&sums[(f0 + q) * 2 + 0], a[q]);
+      atomicAdd(&sums[(f0 + q) * 2 + 1], a[4 + q]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ sums, T* __restrict__ dZ, float* __restrict__ db,
+                               float* __restrict__ dgamma, float* __restrict__ dbeta, int P, int F, int bn_group,
+                               float rate, uint64_t seed, uint64_t step, int layer) {
+  int c4 = threadIdx.x * 4, f0 = c4 % F;
+  float sc[4], sh[4], mean[4], rstd[4], m1[4], m2[4];
+  float inv_n = 1.f / ((float)bn_group * (float)LCN_J);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    mean[q] = stat[(f0 + q) * 2];
+    rstd[q] = stat[(f0 + q) * 2 + 1];
+    sc[q] = gamma[f0 + q] * rstd[q];
+    sh[q] = beta[f0 + q] - mean[q] * sc[q];
+    m1[q] = sums[(f0 + q) * 2] * inv_n;
+    m2[q] = sums[(f0 + q) * 2 + 1] * inv_n;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < F / 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dbeta[f0 + q] = sums[(f0 + q) * 2];
+      dgamma[f0 + q] = sums[(f0 + q) * 2 + 1];
+    }
+  }
+  float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  float bsum[4] = {0, 0, 0, 0};
+  int64_t pr0 = (int64_t)blockIdx.x * 16;
+  for (int r = 0; r < 16; ++r) {
+    int64_t pr = pr0 + r;
+    size_t o = (size_t)pr * P + c4;
+    if (pr >= bn_group) {
+      lcn_st4(dZ, o, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    float dy[4], xh[4], dz[4];
+    bn_bwd_dy(dOut, Z, o, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dz[q] = sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
+      bsum[q] += dz[q];
+    }
+    lcn_st4(dZ, o, make_float4(dz[0], dz[1], dz[2], dz[3]));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) atomicAdd(&db[c4 + q], bsum[q]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 weight gradient of the mid layers, nonzero 64x64 sub-blocks only: dWm = A^T dZ (K = rows)
+// grid (nnz*FC*FC, row splits), 256 threads, thread = 4x4 outputs; atomics into the dense dW.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_wgrad_simt(const T* __restrict__ A, const T* __restrict__ dZ,
+                                                    float* __restrict__ dW, PairTable pt, int P, int FC,
+                                                    int rows_per_block) {
+  __shared__ __align__(16) float As[32][64];
+  __shared__ __align__(16) float Ds[32][64];
+  int sb = blockIdx.x;
+  int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
+  int ic = pt.pi[p] * FC + hi, oc = pt.pj[p] * FC + ho;
+  int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  size_t row0 = (size_t)blockIdx.y * rows_per_block;
+  for (int rc = 0; rc < rows_per_block; rc += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int f = tid + 256 * it;
+      int r = f >> 4, kq = f & 15;
+      *reinterpret_cast<float4*>(&As[r][kq * 4]) = lcn_ld4(A, (row0 + rc + r) * P + ic * 64 + kq * 4);
+      *reinterpret_cast<float4*>(&Ds[r][kq * 4]) = lcn_ld4(dZ, (row0 + rc + r) * P + oc * 64 + kq * 4);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      float4 av = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
+      float4 dv = *reinterpret_cast<const float4*>(&Ds[r][tx * 4]);
+      float a4[4] = {av.x, av.y, av.z, av.w}, d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], d4[b], acc[a][b]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      atomicAdd(&dW[(size_t)(ic * 64 + ty * 4 + a) * P + oc * 64 + tx * 4 + b], acc[a][b]);
+}
+
+// first layer weight gradient: dWm1[k][c] = sum_rows X[row][k] dZ0[row][c]  (dense 17*in_F x P)
+template <typename T, int IN_F>
+__global__ void __launch_bounds__(256) k_first_wgrad(const float* __restrict__ x, int64_t n_rows,
+                                                     const T* __restrict__ dZ, float* __restrict__ dW, int P,
+                                                     int rows_per_block) {
+  constexpr int KIN = LCN_J * IN_F;
+  __shared__ float xs[32][KIN];
+  int c = blockIdx.y * 256 + threadIdx.x;
+  bool act = c < P;
+  float acc[KIN];
+#pragma unroll
+  for (int k = 0; k < KIN; ++k) acc[k] = 0.f;
+  int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  for (int rc = 0; rc < rows_per_block; rc += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * KIN; e += 256) {
+      int64_t pr = row0 + rc + e / KIN;
+      xs[e / KIN][e % KIN] = pr < n_rows ? x[pr * KIN + e % KIN] : 0.f;
+    }
+    __syncthreads();
+    if (act) {
+      for (int r = 0; r < 32; ++r) {
+        float dz = lcn_ld(dZ, (size_t)(row0 + rc + r) * P + c);
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) acc[k] = fmaf(xs[r][k], dz, acc[k]);
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) atomicAdd(&dW[(size_t)k * P + c], acc[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain rule through mask_weights / clip_by_norm / mask softmax, and the fused masked Adam
+// ------------------------------------------------------------------------------------------------
+// pairdot[l][p] = <dWm_l(block p), W_l(block p)>      grid (nnz, n_lin), 256 threads
+__global__ void k_pairdot(const float* __restrict__ params, const float* __restrict__ graw, LinTable lt,
+                          PairTable pt, float* __restrict__ pairdot) {
+  __shared__ double sh[32];
+  int p = blockIdx.x, l = blockIdx.y;
+  int Fi = lt.Fi[l], Fo = lt.Fo[l], Kout = LCN_J * Fo;
+  int i = pt.pi[p], j = pt.pj[p];
+  const float* w = params + lt.w_off[l];
+  const float* g = graw + lt.w_off[l];
+  double s = 0.0;
+  for (int e = threadIdx.x; e < Fi * Fo; e += blockDim.x) {
+    int fi = e / Fo, fo = e - fi * Fo;
+    size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
+    s += (double)g[o] * (double)w[o];
+  }
+  s = block_reduce_sum_d(s, sh);
+  if (threadIdx.x == 0) pairdot[l * LCN_J * LCN_J + p] = (float)s;
+}
+
+// per-layer <dWc,W> -> clip coefficient; mask gradient through the column softmax
+__global__ void k_maskgrad(const float* __restrict__ params, int64_t mask_off, SupportBits sup, PairTable pt,
+                           int nnz, int n_lin, const float* __restrict__ pairdot, const float* __restrict__ mask,
+                           LayerScalars* sc, float* __restrict__ maskgrad /*[289]*/) {
+  __shared__ float dM[LCN_J * LCN_J];
+  __shared__ float soft[LCN_J * LCN_J];
+  int t = threadIdx.x;
+  if (t < n_lin) {
+    double s = 0.0;
+    for (int p = 0; p < nnz; ++p) s += (double)mask[pt.pi[p] * LCN_J + pt.pj[p]] * (double)pairdot[t * LCN_J * LCN_J + p];
+    sc[t].sdot = s;
+    double inv = sc[t].inv_norm;
+    sc[t].coef = sc[t].clipped > 0.f ? (float)(s * inv * inv * inv) : 0.f;
+  }
+  if (t < LCN_J * LCN_J) {
+    int i = t / LCN_J, j = t % LCN_J;
+    float d = 0.f;
+    int p = sup.pair[i][j];
+    if (p >= 0)
+      for (int l = 0; l < n_lin; ++l) d += pairdot[l * LCN_J * LCN_J + p] * sc[l].inv_norm;
+    dM[t] = d;
+    if (mask_off >= 0) {
+      const float* var = params + mask_off;
+      float mx = -INFINITY;
+      for (int k = 0; k < LCN_J; ++k) mx = fmaxf(mx, var[k * LCN_J + j]);
+      float den = 0.f;
+      for (int k = 0; k < LCN_J; ++k) den += expf(var[k * LCN_J + j] - mx);
+      soft[t] = expf(var[t] - mx) / den;
+    }
+  }
+  __syncthreads();
+  if (t < LCN_J * LCN_J && mask_off >= 0) {
+    int j = t % LCN_J;
+    float dot = 0.f;
+    for (int k = 0; k < LCN_J; ++k) dot += soft[k * LCN_J + j] * dM[k * LCN_J + j];
+    maskgrad[t] = soft[t] * (dM[t] - dot);
+  }
+}
+
+// Fused: true gradient from the raw one, TF1 Adam update, ||W_new||^2 accumulation.
+// WRITE_G: only materialise the true gradients (tests / inspection).
+template <bool WRITE_G>
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float* __restrict__ mm,
+                                              float* __restrict__ vv, const float* __restrict__ graw,
+                                              float* __restrict__ gout, SegTable segs, LinTable lt, SupportBits sup,
+                                              const float* __restrict__ mask, const float* __restrict__ maskgrad,
+                                              LayerScalars* sc, float lr_t, float b1, float b2, float eps, float reg) {
+  __shared__ double sh[32];
+  int chunk = blockIdx.x;
+  int s = 0;
+  while (s + 1 < segs.n && segs.s[s + 1].chunk_start <= chunk) ++s;
+  const SegInfo sg = segs.s[s];
+  int64_t e0 = (int64_t)(chunk - sg.chunk_start) * LCN_ADAM_CHUNK;
+  int64_t e1 = min(e0 + (int64_t)LCN_ADAM_CHUNK, sg.size);
+  int l = sg.layer;
+  int Fi = 1, Fo = 1, Kout = 1;
+  float inv = 1.f, coef = 0.f;
+  if (sg.kind == SEG_W) {
+    Fi = lt.Fi[l]; Fo = lt.Fo[l]; Kout = LCN_J * Fo;
+    inv = sc[l].inv_norm; coef = sc[l].coef;
+  }
+  double nrm = 0.0;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+    int64_t o = sg.off + e;
+    float w = params[o];
+    float g;
+    if (sg.kind == SEG_W) {
+      int r = (int)(e / Kout), c = (int)(e - (int64_t)r * Kout);
+      int i = r / Fi, j = c / Fo;
+      g = -coef * w;
+      if ((sup.row[i] >> j) & 1u) g = fmaf(graw[o], mask[i * LCN_J + j] * inv, g);
+      g = fmaf(reg, w, g);
+    } else if (sg.kind == SEG_B) {
+      g = fmaf(reg, w, graw[o]);
+    } else if (sg.kind == SEG_MASK) {
+      g = maskgrad[e];
+    } else {
+      g = graw[o];
+    }
+    if (WRITE_G) {
+      gout[o] = g;
+    } else {
+      float m = b1 * mm[o] + (1.f - b1) * g;
+      float v = b2 * vv[o] + (1.f - b2) * g * g;
+      mm[o] = m;
+      vv[o] = v;
+      w -= lr_t * m / (sqrtf(v) + eps);
+      params[o] = w;
+      nrm += (double)w * w;
+    }
+  }
+  if (!WRITE_G && sg.kind == SEG_W) {
+    nrm = block_reduce_sum_d(nrm, sh);
+    if (threadIdx.x == 0) atomicAdd(&sc[l].norm2, nrm);
+  }
+}
+
+static int launch_grad_chain(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
+                             const float* graw, cudaStream_t st) {
+  LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
+  float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
+  float* pairdot = reinterpret_cast<float*>(ws + lay.off_pairdot);
+  float* maskgrad = mask + 2 * LCN_J * LCN_J;
+  k_pairdot<<<dim3(m->nnz, m->n_lin), 256, 0, st>>>(params, graw, make_lin(m), make_pairs(m), pairdot);
+  k_maskgrad<<<1, 320, 0, st>>>(params, m->mask_off, m->sup, make_pairs(m), m->nnz, m->n_lin, pairdot, mask, sc,
+                                maskgrad);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
+                             const float* grads_raw, float* grads_out, cudaStream_t st) {
+  int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st);
+  if (rc) return rc;
+  LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
+  float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
+  k_adam<true><<<m->segs.total_chunks, 256, 0, st>>>(const_cast<float*>(params), nullptr, nullptr, grads_raw,
+                                                     grads_out, m->segs, make_lin(m), m->sup, mask,
+                                                     mask + 2 * LCN_J * LCN_J, sc, 0.f, 0.f, 0.f, 0.f, 0.f);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
+                    const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg, cudaStream_t st) {
+  int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st);
+  if (rc) return rc;
+  LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
+  float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
+  k_zero_norm2<<<1, 32, 0, st>>>(sc, m->n_lin);
+  k_adam<false><<<m->segs.total_chunks, 256, 0, st>>>(params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
+                                                      m->sup, mask, mask + 2 * LCN_J * LCN_J, sc, lr_t, b1, b2, eps,
+                                                      reg);
+  LCN_CHECK_LAUNCH();
+  return lcn_launch_prepare(m, params, ws, lay, /*recompute_norm=*/false, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / backward orchestration
+// ------------------------------------------------------------------------------------------------
+static inline char* z_buf(char* ws, const WsLayout& lay, int l) {
+  return ws + lay.off_z + (size_t)(lay.training ? l : 0) * lay.z_stride;
+}
+static inline char* a_buf(char* ws, const WsLayout& lay, int l) {
+  return ws + lay.off_a + (size_t)(lay.training ? l : l % 3) * lay.a_stride;
+}
+static inline float* bn_stat(char* ws, const WsLayout& lay, const lcn_model* m, int l) {
+  return reinterpret_cast<float*>(ws + lay.off_bnstat) + (size_t)l * lay.n_groups * m->d.F * 2;
+}
+
+template <typename T>
+static int forward_impl(const FwdArgs& a) {
+  const lcn_model* m = a.m;
+  const WsLayout& lay = a.lay;
+  char* ws = a.ws;
+  cudaStream_t st = a.st;
+  const int P = m->P, F = m->d.F, FC = m->FC;
+  RowGeom g{lay.n_rows, lay.bn_group, lay.gstride};
+  float* part = reinterpret_cast<float*>(ws + lay.off_part);
+  const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_simt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_simt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_last_layer<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    attr_done = true;
+  }
+  int n_bn = m->n_bn;
+  for (int l = 0; l < n_bn; ++l) {
+    const LayerInfo& L = m->L[l];
+    T* Z = reinterpret_cast<T*>(z_buf(ws, lay, l));
+    T* Aout = reinterpret_cast<T*>(a_buf(ws, lay, l));
+    if (l == 0) {
+      dim3 grid(lay.tiles, (P + 255) / 256);
+      const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
+      switch (m->d.in_F) {
+        case 2: k_first_layer<T, 2><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P); break;
+        case 3: k_first_layer<T, 3><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P); break;
+        default: lcn_set_error("in_F=%d not supported (2 or 3)", m->d.in_F); return LCN_EINVAL;
+      }
+    } else {
+      const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, l - 1));
+      if (tc) {
+        const char* wp = ws + lay.off_wp16f + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+        int rc = lcn_tc_gemm(m, lay, l - 1, 0, reinterpret_cast<const __nv_bfloat16*>(Ain), wp, a.params + L.b_off,
+                             nullptr, reinterpret_cast<__nv_bfloat16*>(Z), part, st);
+        if (rc) return rc;
+      } else {
+        const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
+        k_gemm_simt<T, false><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(
+            Ain, wp, a.params + L.b_off, nullptr, Z, part, m->by_out, P, FC, lay.bn_group, lay.gstride);
+      }
+    }
+    LCN_CHECK_LAUNCH();
+    float* stat = bn_stat(ws, lay, m, l);
+    k_bn_finalize<<<lay.n_groups, 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
+    const T* res = L.res_from >= 0 ? reinterpret_cast<const T*>(a_buf(ws, lay, L.res_from)) : nullptr;
+    k_bn_act<T><<<(unsigned)(lay.rows_pad / 16), P / 4, 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off,
+                                                                 res, Aout, P, F, lay.bn_group, lay.gstride,
+                                                                 a.dropout_rate, a.seed, a.step, l);
+    LCN_CHECK_LAUNCH();
+  }
+  int last = m->n_lin - 1;
+  const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, n_bn - 1));
+  float* out_ws = lay.training ? reinterpret_cast<float*>(ws + lay.off_out) : nullptr;
+  k_last_layer<T><<<lay.tiles, 128, gemm_smem, st>>>(Ain, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+                                                     a.params + m->L[last].b_off, a.x, m->d.in_F, g, a.out, out_ws,
+                                                     m->sup, P, FC);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+int lcn_launch_forward(const FwdArgs& a) {
+  return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<float>(a);
+}
+
+template <typename T>
+static int backward_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, const float* x,
+                         const float* labels, float rate, uint64_t seed, uint64_t step, float* loss,
+                         float* graw, cudaStream_t st) {
+  const int P = m->P, F = m->d.F, FC = m->FC;
+  const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
+  LCN_CHECK_CUDA(cudaMemsetAsync(graw, 0, sizeof(float) * m->n_params, st));
+  LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_loss, 0, 2 * sizeof(double), st));
+  LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_bnsum, 0, sizeof(float) * m->n_bn * F * 2, st));
+  float* dout = reinterpret_cast<float*>(ws + lay.off_dout);
+  double* lacc = reinterpret_cast<double*>(ws + lay.off_loss);
+  k_loss_dout<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_out), labels, lay.n_rows, lay.rows_pad,
+                                   dout, lacc);
+  k_loss_final<<<1, 1, 0, st>>>(lacc, lay.n_rows, loss);
+  LCN_CHECK_LAUNCH();
+
+  auto D = [&](int i) { return reinterpret_cast<T*>(ws + lay.off_d + (size_t)i * lay.d_stride); };
+  T* dZ = reinterpret_cast<T*>(ws + lay.off_dz);
+  int last = m->n_lin - 1;
+  int rows_blk = 512;
+  while (lay.rows_pad % rows_blk) rows_blk >>= 1;   // rows_pad is a multiple of 128
+  int cur = 0;
+  {
+    const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, m->n_bn - 1));
+    k_last_layer_bwd<T><<<dim3((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256), 256, 0, st>>>(
+        Ain, dout, reinterpret_cast<const float*>(ws + lay.off_wm_last), D(cur), graw + m->L[last].w_off,
+        graw + m->L[last].b_off, P, rows_blk);
+    LCN_CHECK_LAUNCH();
+  }
+  unsigned eg = (unsigned)(lay.rows_pad / 16);
+  size_t red_smem = (size_t)(P / 4) * 8 * sizeof(float);
+  PairTable pt = make_pairs(m);
+  for (int l = m->n_bn - 1; l >= 0; --l) {
+    const LayerInfo& L = m->L[l];
+    const T* Z = reinterpret_cast<const T*>(z_buf(ws, lay, l));
+    const float* stat = bn_stat(ws, lay, m, l);
+    float* sums = reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)l * F * 2;
+    k_bn_bwd_reduce<T><<<eg, P / 4, red_smem, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, P,
+                                                    F, lay.bn_group, rate, seed, step, l);
+    k_bn_bwd_apply<T><<<eg, P / 4, 0, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, dZ,
+                                            graw + L.b_off, graw + L.gamma_off, graw + L.beta_off, P, F, lay.bn_group,
+                                            rate, seed, step, l);
+    LCN_CHECK_LAUNCH();
+    if (l == 0) {
+      dim3 grid((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256);
+      if (m->d.in_F == 2) k_first_wgrad<T, 2><<<grid, 256, 0, st>>>(x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
+      else k_first_wgrad<T, 3><<<grid, 256, 0, st>>>(x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
+      LCN_CHECK_LAUNCH();
+      break;
+    }
+    const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, l - 1));
+    // gradient w.r.t. the layer input goes to the next free buffer; the block-output gradient D(cur)
+    // of a residual block stays alive until the first layer of the block has been processed.
+    bool second_of_block = (L.res_from >= 0) || (!m->d.residual && (l % 2 == 0));
+    int nxt = second_of_block ? (cur + 1) % 3 : (cur + 1) % 3;
+    const T* addend = nullptr;
+    int keep = cur;
+    if (!second_of_block && m->d.residual) {
+      // first layer of the block: D(cur) is the mid gradient, D(prev) the block-output gradient
+      addend = D((cur + 2) % 3);
+    }
+    if (tc) {
+      int rc = lcn_tc_wgrad(m, lay, reinterpret_cast<const __nv_bfloat16*>(Ain),
+                            reinterpret_cast<const __nv_bfloat16*>(dZ), graw + L.w_off, st);
+      if (rc) return rc;
+      const char* wp = ws + lay.off_wp16b + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+      rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), wp, nullptr,
+                       reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(D(nxt)),
+                       nullptr, st);
+      if (rc) return rc;
+    } else {
+      k_wgrad_simt<T><<<dim3(m->nnz * FC * FC, (unsigned)(lay.rows_pad / rows_blk)), 256, 0, st>>>(
+          Ain, dZ, graw + L.w_off, pt, P, FC, rows_blk);
+      const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
+      k_gemm_simt<T, true><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(
+          dZ, wp, nullptr, addend, D(nxt), nullptr, m->by_in, P, FC, lay.bn_group, lay.gstride);
+    }
+    LCN_CHECK_LAUNCH();
+    (void)keep;
+    cur = nxt;
+  }
+  return LCN_OK;
+}
+
+int lcn_launch_backward(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, const float* x,
+                        const float* labels, float dropout_rate, uint64_t seed, uint64_t step, float* loss,
+                        float* grads_raw, cudaStream_t st) {
+  return m->d.path == LCN_PATH_BF16
+             ? backward_impl<__nv_bfloat16>(m, params, ws, lay, x, labels, dropout_rate, seed, step, loss, grads_raw, st)
+             : backward_impl<float>(m, params, ws, lay, x, labels, dropout_rate, seed, step, loss, grads_raw, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity taps
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_read_rows(const T* __restrict__ src, float* __restrict__ dst, int64_t n_logical, int P,
+                            int bn_group, int gstride) {
+  int64_t n = n_logical * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lr = e / P;
+    int c = (int)(e - lr * P);
+    int64_t pr = (lr / bn_group) * gstride + lr % bn_group;
+    dst[e] = lcn_ld(src, (size_t)pr * P + c);
+  }
+}
+__global__ void k_unpack_mid(const float* __restrict__ wp32, PairTable pt, int nnz, int F, int FC,
+                             float* __restrict__ dst) {
+  int P = LCN_J * F;
+  int sb = blockIdx.x;
+  int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
+  int i = pt.pi[p], j = pt.pj[p];
+  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+    int fi = e >> 6, fo = e & 63;
+    dst[(size_t)(i * F + hi * 64 + fi) * P + j * F + ho * 64 + fo] = wp32[(size_t)sb * 4096 + e];
+  }
+}
+
+int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer, float* dst,
+                           cudaStream_t st) {
+  const int P = m->P, F = m->d.F;
+  int64_t n_logical = (int64_t)lay.n_groups * lay.bn_group;
+  bool bf = m->d.path == LCN_PATH_BF16;
+  if (kind == 0 || kind == 1 || kind == 6) {
+    LCN_REQUIRE(lay.training, "activation taps need a training-mode workspace layout");
+    LCN_REQUIRE(layer >= 0 && layer < m->n_bn, "layer %d out of range", layer);
+    const char* src = kind == 0 ? z_buf(ws, lay, layer) : kind == 1 ? a_buf(ws, lay, layer) : ws + lay.off_dz;
+    if (bf) k_read_rows<__nv_bfloat16><<<256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
+    else k_read_rows<float><<<256, 256, 0, st>>>(reinterpret_cast<const float*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
+  } else if (kind == 2) {
+    LCN_REQUIRE(layer >= 0 && layer < m->n_lin, "layer %d out of range", layer);
+    const LayerInfo& L = m->L[layer];
+    if (layer == 0 || layer == m->n_lin - 1) {
+      LCN_CHECK_CUDA(cudaMemcpyAsync(dst, ws + (layer == 0 ? lay.off_wm_first : lay.off_wm_last),
+                                     sizeof(float) * L.Kin * L.Kout, cudaMemcpyDeviceToDevice, st));
+    } else {
+      LCN_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * P * P, st));
+      const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(layer - 1) * m->nnz * m->FC * m->FC * 4096;
+      k_unpack_mid<<<m->nnz * m->FC * m->FC, 256, 0, st>>>(wp, make_pairs(m), m->nnz, F, m->FC, dst);
+    }
+  } else if (kind == 3) {
+    LCN_CHECK_CUDA(cudaMemcpyAsync(dst, ws + lay.off_mask, sizeof(float) * LCN_J * LCN_J, cudaMemcpyDeviceToDevice, st));
+  } else if (kind == 4 || kind == 5) {
+    LCN_REQUIRE(layer >= 0 && layer < m->n_bn, "layer %d out of range", layer);
+    const float* stat = bn_stat(ws, lay, m, layer);
+    LCN_CHECK_CUDA(cudaMemcpy2DAsync(dst, sizeof(float), stat + (kind == 5 ? 1 : 0), 2 * sizeof(float), sizeof(float),
+                                     (size_t)lay.n_groups * F, cudaMemcpyDeviceToDevice, st));
+  } else {
+    lcn_set_error("unknown tensor kind %d", kind);
+    return LCN_EINVAL;
+  }
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+// dropout keep decisions, exactly as k_bn_act draws them
+__global__ void k_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t n4, float rate, uint8_t* keep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t rb[4];
+    lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)i, rb);
+    for (int q = 0; q < 4; ++q) keep[i * 4 + q] = lcn_keep(rb[q], rate) ? 1 : 0;
+  }
+}
+extern "C" int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int32_t cols, float rate,
+                                uint8_t* d_keep, void* stream) {
+  LCN_REQUIRE(cols % 4 == 0, "cols must be a multiple of 4");
+  k_dropout_mask<<<256, 256, 0, (cudaStream_t)stream>>>(seed, step, layer, rows * cols / 4, rate, d_keep);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}

@@ -1,0 +1,285 @@
+"""LcnEngine: owns the device buffers (through torch) of one LCN model and drives the C ABI.
+
+torch is plumbing here (device memory, streams, pinned host buffers, torch.distributed); every
+arithmetic step of the hot path is a kernel of liblcn_b200.so.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+J = 17
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class LcnEngine:
+    """One model (mask support + layer stack) on one GPU.
+
+    Mirrors the arithmetic of cgcnn (network/models_att.py:475-775) and base_model's loss / Adam
+    (:352-421).  `path` selects the arithmetic: "bf16" (tcgen05 tensor cores, 1e-2 parity) or
+    "fp32" (CUDA cores, 1e-4 parity)."""
+
+    def __init__(self, F=64, in_F=2, num_layers=3, mask_type="locally_connected", neighbour_matrix=None,
+                 residual=True, batch_norm=True, max_norm=True, path="bf16", device="cuda:0",
+                 learning_rate=1e-3, decay_steps=32000, decay_rate=0.96, regularization=0.0):
+        if not torch.cuda.is_available():
+            raise L.LcnError("LcnEngine needs a CUDA device; there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.F, self.in_F, self.num_layers = int(F), int(in_F), int(num_layers)
+        self.mask_type = mask_type
+        self.path = path
+        desc = L.ModelDesc()
+        desc.F, desc.in_F, desc.num_layers = self.F, self.in_F, self.num_layers
+        desc.residual, desc.batch_norm, desc.max_norm = int(bool(residual)), int(bool(batch_norm)), int(bool(max_norm))
+        desc.path = L.LCN_PATH_BF16 if path == "bf16" else L.LCN_PATH_FP32
+        if "exponential" in mask_type:                      # models_att.py:573-574
+            em = L.exponential_matrix()
+            desc.mask_kind = L.LCN_MASK_CONSTANT
+            sup = (em != 0).astype(np.float32)
+            cm = em
+        else:                                               # models_att.py:547-571
+            assert neighbour_matrix is not None
+            nm = np.asarray(neighbour_matrix, dtype=np.float32)
+            assert nm.shape == (J, J)
+            desc.mask_kind = L.LCN_MASK_LOCALLY_CONNECTED
+            sup = (nm.T != 0).astype(np.float32)
+            cm = np.zeros((J, J), np.float32)
+        self.support = sup.copy()
+        desc.support[:] = sup.reshape(-1).tolist()
+        desc.const_mask[:] = cm.reshape(-1).tolist()
+        h = C.c_void_p()
+        L.check(self.lib.lcn_model_create(C.byref(desc), C.byref(h)))
+        self.h = h
+        self.n_params = int(self.lib.lcn_model_param_count(h))
+        self.tensors = {}
+        name = C.create_string_buffer(256)
+        off, rows, cols = C.c_int64(), C.c_int32(), C.c_int32()
+        for i in range(self.lib.lcn_model_num_tensors(h)):
+            L.check(self.lib.lcn_model_tensor_info(h, i, name, 256, C.byref(off), C.byref(rows), C.byref(cols)))
+            self.tensors[name.value.decode()] = (off.value, rows.value, cols.value)
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self.grads_raw = torch.zeros_like(self.params)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.ws = None
+        self.learning_rate, self.decay_steps, self.decay_rate = learning_rate, decay_steps, decay_rate
+        self.regularization = 0.0 if regularization is None else float(regularization)
+        self.step = 0                      # Adam t / global_step
+        self.seed = 2019
+        self._prepared = False
+        self._fwd_geom = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.lcn_model_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- parameters -------------------------------------------------------------------------
+    def tensor(self, name):
+        off, rows, cols = self.tensors[name]
+        v = self.params[off: off + rows * cols]
+        return v.view(rows, cols) if rows > 1 else v
+
+    def _view(self, flat, name):
+        off, rows, cols = self.tensors[name]
+        v = flat[off: off + rows * cols]
+        return v.view(rows, cols) if rows > 1 else v
+
+    def set_params(self, np_params):
+        """np_params: dict name -> ndarray, names as in the reference's TF variables."""
+        for k, v in np_params.items():
+            t = self.tensor(k)
+            t.copy_(torch.as_tensor(np.asarray(v, dtype=np.float32).reshape(tuple(t.shape))))
+        self._prepared = False
+
+    def get_params(self):
+        p = self.params.detach().cpu().numpy()
+        return {k: p[o: o + r * c].reshape((r, c) if r > 1 else (c,)).copy() for k, (o, r, c) in self.tensors.items()}
+
+    def unflatten(self, flat):
+        f = flat.detach().cpu().numpy()
+        return {k: f[o: o + r * c].reshape((r, c) if r > 1 else (c,)).copy() for k, (o, r, c) in self.tensors.items()}
+
+    def init_params(self, seed=42):
+        """Reference initialisation (models_att.py:614-628 kaiming for w* and b*, BN gamma=1 beta=0,
+        mask var = L, :549-566)."""
+        rng = np.random.default_rng(seed)
+
+        def tn(shape):
+            out = rng.standard_normal(shape)
+            bad = np.abs(out) > 2
+            while bad.any():
+                out[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(out) > 2
+            return out
+        p = {}
+        for k, (o, r, c) in self.tensors.items():
+            base = k.rsplit("/", 1)[-1]
+            if k == "mask":
+                p[k] = self.support.copy()
+            elif base == "gamma":
+                p[k] = np.ones(c)
+            elif base == "beta":
+                p[k] = np.zeros(c)
+            elif base.startswith("w"):
+                p[k] = tn((r, c)) * math.sqrt(2.0 / r)
+            else:
+                p[k] = tn((c,)) * math.sqrt(2.0 / c)
+        self.set_params(p)
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        self.step = 0
+
+    # ---- workspace ----------------------------------------------------------------------------
+    def _ensure_ws(self, n_rows, bn_group, training):
+        need = int(self.lib.lcn_model_workspace_bytes(self.h, n_rows, bn_group, int(training)))
+        if need == 0:
+            raise L.LcnError(self.lib.lcn_last_error().decode())
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._prepared = False
+        return self.ws.numel()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def prepare(self):
+        """clip_by_norm + mask_weights + pack for every layer (models_att.py:576-586,659-660)."""
+        if self.ws is None:
+            self._ensure_ws(128, 128, False)
+        L.check(self.lib.lcn_model_prepare_weights(self.h, _ptr(self.params), _ptr(self.ws), self.ws.numel(), self._stream()))
+        self._prepared = True
+
+    # ---- forward / train ------------------------------------------------------------------------
+    def forward(self, x, bn_group=None, training=False, dropout=0.0, out=None):
+        """x: [n, 17*in_F] float32 CUDA tensor.  Returns [n, 51] float32 (models_att.py:707-775)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        n = x.shape[0]
+        bn_group = n if bn_group is None else int(bn_group)
+        size = self._ensure_ws(n, bn_group, training)
+        if not self._prepared:
+            self.prepare()
+        if out is None:
+            out = torch.empty((n, J * 3), dtype=torch.float32, device=self.device)
+        L.check(self.lib.lcn_model_forward(self.h, _ptr(self.params), _ptr(self.ws), size, _ptr(x), n, bn_group,
+                                           int(training), float(dropout), self.seed, self.step + 1, _ptr(out),
+                                           self._stream()))
+        self._fwd_geom = (n, bn_group, bool(training))
+        return out
+
+    def lr_at(self, step):
+        """exponential_decay with global_step = step-1 (models_att.py:386-399)."""
+        return self.learning_rate * self.decay_rate ** ((step - 1) / self.decay_steps)
+
+    def backward(self, x, labels, dropout=0.0):
+        n = x.shape[0]
+        assert self._fwd_geom == (n, n, True), "backward needs forward(training=True) with one BN group"
+        L.check(self.lib.lcn_model_backward(self.h, _ptr(self.params), _ptr(self.ws), self.ws.numel(), _ptr(x),
+                                            _ptr(labels), n, float(dropout), self.seed, self.step + 1,
+                                            _ptr(self.loss_dev), _ptr(self.grads_raw), self._stream()))
+        return self.loss_dev
+
+    def true_grads(self):
+        g = torch.empty_like(self.params)
+        L.check(self.lib.lcn_model_finalize_grads(self.h, _ptr(self.params), _ptr(self.ws), self.ws.numel(),
+                                                  _ptr(self.grads_raw), _ptr(g), self._stream()))
+        return g
+
+    def adam(self, beta1=0.9, beta2=0.999, eps=1e-8):
+        """TF1 AdamOptimizer.apply_gradients (models_att.py:404-409) + weight re-preparation."""
+        self.step += 1
+        t = self.step
+        lr = self.lr_at(t)
+        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        L.check(self.lib.lcn_model_adam_step(self.h, _ptr(self.params), _ptr(self.adam_m), _ptr(self.adam_v),
+                                             _ptr(self.ws), self.ws.numel(), _ptr(self.grads_raw), lr_t, beta1, beta2,
+                                             eps, self.regularization, self._stream()))
+        self._prepared = True
+        return lr
+
+    def train_step(self, x, labels, dropout=0.0, out=None):
+        """One sess.run([op_train, ...]) of the reference (models_att.py:210-212): fwd, loss, bwd, Adam.
+        Returns (loss device scalar, learning rate used)."""
+        self.forward(x, bn_group=x.shape[0], training=True, dropout=dropout, out=out)
+        loss = self.backward(x, labels, dropout)
+        lr = self.adam()
+        return loss, lr
+
+    def read_tensor(self, kind, layer, n_rows, bn_group):
+        n_groups = (n_rows + bn_group - 1) // bn_group
+        P = J * self.F
+        if kind in (0, 1, 6):
+            shape = (n_groups * bn_group, P)
+        elif kind == 2:
+            n_lin = 2 + 2 * self.num_layers
+            kin = J * (self.in_F if layer == 0 else self.F)
+            kout = J * (3 if layer == n_lin - 1 else self.F)
+            shape = (kin, kout)
+        elif kind == 3:
+            shape = (J, J)
+        else:
+            shape = (n_groups, self.F)
+        dst = torch.empty(shape, dtype=torch.float32, device=self.device)
+        L.check(self.lib.lcn_model_read_tensor(self.h, _ptr(self.ws), self.ws.numel(), kind, layer, n_rows, bn_group,
+                                               _ptr(dst), self._stream()))
+        return dst
+
+    def dropout_keep(self, layer, rows, rate, step=None):
+        P = J * self.F
+        k = torch.empty((rows, P), dtype=torch.uint8, device=self.device)
+        L.check(self.lib.lcn_dropout_mask(self.seed, self.step + 1 if step is None else step, layer, rows, P,
+                                          float(rate), _ptr(k), self._stream()))
+        return k
+
+    # ---- batched predict (base_model.predict, models_att.py:79-132) -------------------------------
+    def predict(self, data, batch_size, chunk_groups=None):
+        """data: [N, 17*in_F] array (host).  Batches of `batch_size` poses are BN groups; the last one is
+        zero padded (the zero rows take part in the statistics) exactly like the reference.  Returns
+        float64 [N, 51]."""
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        n = data.shape[0]
+        if chunk_groups is None:
+            chunk_groups = max(1, 32768 // batch_size)
+        chunk = chunk_groups * batch_size
+        preds = np.empty((n, J * 3), dtype=np.float64)
+        pin_in = torch.empty((min(chunk, n), data.shape[1]), dtype=torch.float32).pin_memory()
+        pin_out = torch.empty((min(chunk, n), J * 3), dtype=torch.float32).pin_memory()
+        for b in range(0, n, chunk):
+            e = min(b + chunk, n)
+            pin_in[: e - b].copy_(torch.from_numpy(data[b:e]))
+            x = pin_in[: e - b].to(self.device, non_blocking=True)
+            out = self.forward(x, bn_group=batch_size, training=False)
+            pin_out[: e - b].copy_(out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            preds[b:e] = pin_out[: e - b].numpy()
+        return preds
+
+
+def eval_mpjpe(pred, gt, box, cam, root_depth, protocol2, action=None, n_actions=0, want_err=True):
+    """Batched evaluate.py:53-61.  All inputs CUDA float32 tensors: pred/gt [n,17,3], box [n,4],
+    cam [n,4]=(fx,fy,cx,cy), root_depth [n]; action int32 [n] or None.
+    Returns (err [n,17] or None, sums float64 [n_actions+1, 19])."""
+    lib = L.load()
+    n = pred.shape[0]
+    dev = pred.device
+    for t in (pred, gt, box, cam, root_depth):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    err = torch.empty((n, J), dtype=torch.float32, device=dev) if want_err else None
+    na = int(n_actions) if action is not None else 0
+    sums = torch.zeros((na + 1, 19), dtype=torch.float64, device=dev)
+    L.check(lib.lcn_eval_mpjpe(_ptr(pred), _ptr(gt), _ptr(box), _ptr(cam), _ptr(root_depth), _ptr(action), na, n,
+                               int(bool(protocol2)), _ptr(err), _ptr(sums),
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return err, sums

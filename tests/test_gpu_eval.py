@@ -1,0 +1,104 @@
+"""GPU parity of the batched evaluator (evaluate.py:53-61) against the reference's own NumPy outputs
+(tests/golden) and the float64 oracle.  Tolerance: 0.1 mm on per-joint errors (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from lcn_pose_b200.engine import eval_mpjpe
+from lcn_pose_b200 import _lib as L
+from oracle import lcn_oracle as O
+from tests.gpu_helpers import dev
+
+pytestmark = pytest.mark.gpu
+TOL_MM = 0.1
+
+
+def _f32(a):
+    return dev(np.asarray(a, dtype=np.float32))
+
+
+def synth(n, seed=7):
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    return mk.synth_eval(np.random.default_rng(seed), n)
+
+
+@pytest.mark.parametrize("protocol2", [False, True])
+def test_eval_matches_reference_goldens(golden, protocol2):
+    g = golden
+    n = len(g["ev_pred"])
+    normal = np.array([i % 16 != 5 for i in range(n)])
+    err, sums = eval_mpjpe(_f32(g["ev_pred"]), _f32(g["ev_gt"]), _f32(g["ev_box"]), _f32(g["ev_cam"]),
+                           _f32(g["ev_root_depth"]), protocol2)
+    err = err.cpu().numpy()
+    ref = g["ev_err_p2"] if protocol2 else g["ev_err_p1"]
+    assert np.abs(err[normal] - ref[normal]).max() < TOL_MM
+    s = sums.cpu().numpy()[0]
+    np.testing.assert_allclose(s[:17], err.astype(np.float64).sum(0), rtol=1e-6)
+    assert s[17] == n and s[18] == (err < 50).sum()
+
+
+def test_procrustes_accepts_reflections_like_reference(golden):
+    """a reflected + scaled copy of gt aligns (almost) exactly, det(R) = -1."""
+    g = golden
+    idx = [i for i in range(len(g["ev_gt"])) if i % 16 == 5]
+    gt = g["ev_gt"][idx]
+    cam_frame = g["ev_camframe"][idx]
+    # feed camera-frame poses through an identity un-projection: box width 1999 -> ratio 1, depth 0,
+    # fx = fy = z... not invertible in general, so test procrustes via a synthetic identity camera:
+    n = len(idx)
+    z = cam_frame[:, :, 2]
+    pred = cam_frame.copy()
+    pred[:, :, 0] = cam_frame[:, :, 0] / z       # (u - 0)/1 * z = x
+    pred[:, :, 1] = cam_frame[:, :, 1] / z
+    box = np.tile(np.array([0, 0, 1999, 1999.0]), (n, 1))
+    cam = np.tile(np.array([1.0, 1.0, 0.0, 0.0]), (n, 1))
+    err, _ = eval_mpjpe(_f32(pred), _f32(gt), _f32(box), _f32(cam), _f32(np.zeros(n)), True)
+    assert err.cpu().numpy().max() < TOL_MM
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 4097])
+def test_eval_matches_oracle_ragged_sizes(n):
+    pred, gt, box, cam, rd = synth(n, seed=n)
+    for protocol2 in (False, True):
+        ref = O.eval_errors(pred, gt, box, cam, rd, protocol2)
+        err, sums = eval_mpjpe(_f32(pred), _f32(gt), _f32(box), _f32(cam), _f32(rd), protocol2)
+        err = err.cpu().numpy()
+        assert np.abs(err - ref).max() < TOL_MM
+        fin_ref, pck_ref = O.eval_summary_joint(ref)
+        s = sums.cpu().numpy()[0]
+        mpjpe = s[:17] / s[17]
+        assert np.abs(mpjpe - np.array(fin_ref[:17])).max() < TOL_MM
+        assert abs(mpjpe.mean() - fin_ref[17]) < TOL_MM
+        assert abs(s[18] / (s[17] * 17) * 100 - pck_ref[0]) < 0.2
+
+
+def test_eval_per_action_sums_and_no_err_output():
+    n, na = 2000, 5
+    pred, gt, box, cam, rd = synth(n, seed=3)
+    rng = np.random.default_rng(0)
+    action = np.sort(rng.integers(0, na, n)).astype(np.int32)
+    action[::7] = rng.integers(0, na, len(action[::7]))          # not warp-uniform everywhere
+    ref = O.eval_errors(pred, gt, box, cam, rd, True)
+    fin_ref, pck_ref = O.eval_summary_action(ref, action, range(na))
+    err, sums = eval_mpjpe(_f32(pred), _f32(gt), _f32(box), _f32(cam), _f32(rd), True, action=dev(action),
+                           n_actions=na, want_err=False)
+    assert err is None
+    s = sums.cpu().numpy()
+    per_action = s[:na, :17].sum(1) / (s[:na, 17] * 17)
+    assert np.abs(per_action - np.array(fin_ref[:na])).max() < TOL_MM
+    assert abs(per_action.mean() - fin_ref[na]) < TOL_MM
+    assert s[na, 17] == n and np.all(s[:na, 17] == np.bincount(action, minlength=na))
+
+
+def test_denormalize_matches_reference_arithmetic():
+    rng = np.random.default_rng(5)
+    n = 777
+    pose = rng.normal(0, 0.3, (n, 17, 3)).astype(np.float32)
+    res = np.stack([rng.choice([1000.0, 2048.0], n), rng.choice([1000.0, 1002.0, 2048.0], n)], 1).astype(np.float32)
+    ref = O.denormalize(pose, res[:, 0], res[:, 1])
+    d = dev(pose.copy())
+    L.check(L.load().lcn_denormalize(d.data_ptr(), dev(res).data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    assert np.abs(d.cpu().numpy() - ref).max() < 1e-3

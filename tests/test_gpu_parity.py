@@ -1,0 +1,188 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the float64 oracle on the
+same seeded inputs.  Tolerances (BASELINE.json north_star): per-layer outputs within 1e-4 relative on
+the fp32 path and 1e-2 on the bf16 path; masks bit exact (tests/test_abi_host.py); MPJPE / P-MPJPE
+within 0.1 mm (tests/test_gpu_eval.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lcn_oracle as O
+from tests.gpu_helpers import dev, make_pair, rel_err, synth_xy
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+@pytest.mark.parametrize("mask_type,knn", [("locally_connected", 3), ("locally_connected", 1), ("exponential", 2)])
+def test_mask_and_effective_weights(mask_type, knn):
+    eng, cfg, p = make_pair(L=1, knn=knn, mask_type=mask_type)
+    eng.prepare()
+    mask = O.mask_values(cfg, p)
+    got = eng.read_tensor(3, 0, 128, 128).cpu().numpy()
+    assert rel_err(got, mask) < 2e-6
+    for l, name in enumerate(O.weight_names(cfg)):
+        wm, _, _ = O.effective_weight(cfg, p[name], mask)
+        got = eng.read_tensor(2, l, 128, 128).cpu().numpy()
+        assert rel_err(got, wm) < 5e-6, name
+        sup = np.kron(cfg.support(), np.ones((wm.shape[0] // 17, wm.shape[1] // 17))) != 0
+        assert np.all(got[~sup] == 0), name
+
+
+def _per_layer_check(eng, cfg, p, x, n, bn_group, rate, tol, keep=None):
+    """Compare every Z_l / A_l with the oracle layer applied to the GPU's own previous activation."""
+    mask = O.mask_values(cfg, p)
+    wn, bn_, bnn = O.weight_names(cfg), O.bias_names(cfg), O.bn_names(cfg)
+    n_bn = 1 + 2 * cfg.num_layers
+    ng = (n + bn_group - 1) // bn_group
+    xpad = np.zeros((ng * bn_group, x.shape[1]))
+    xpad[:n] = x
+    a_prev = xpad
+    worst = 0.0
+    for l in range(n_bn):
+        wm, _, _ = O.effective_weight(cfg, p[wn[l]], mask)
+        z_ref = a_prev @ wm + p[bn_[l]]
+        z = eng.read_tensor(0, l, n, bn_group).cpu().numpy().astype(np.float64)
+        e = rel_err(z, z_ref)
+        worst = max(worst, e)
+        assert e < tol, f"Z[{l}] rel err {e}"
+        # BN per group on the GPU's Z, then act / dropout / residual
+        a_ref = np.empty_like(z)
+        for g in range(ng):
+            sl = slice(g * bn_group, (g + 1) * bn_group)
+            y, _, _, _ = O._bn_forward(z[sl], p[bnn[l] + "/gamma"], p[bnn[l] + "/beta"], cfg.F)
+            a_ref[sl] = y
+        a_ref = np.where(a_ref > 0, a_ref, 0.2 * a_ref)
+        if rate > 0:
+            a_ref = a_ref * keep[l] / (1 - rate)
+        if l >= 2 and l % 2 == 0 and cfg.residual:
+            a_ref = a_ref + eng.read_tensor(1, l - 2, n, bn_group).cpu().numpy()
+        a = eng.read_tensor(1, l, n, bn_group).cpu().numpy().astype(np.float64)
+        e = rel_err(a, a_ref)
+        worst = max(worst, e)
+        assert e < tol, f"A[{l}] rel err {e}"
+        a_prev = a
+    return worst
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16"])
+@pytest.mark.parametrize("L,knn,n,bn_group", [(1, 3, 200, 200), (2, 2, 300, 128), (1, 3, 256, 256)])
+def test_forward_per_layer_and_end_to_end(path, L, knn, n, bn_group):
+    eng, cfg, p = make_pair(L=L, knn=knn, path=path)
+    x, _ = synth_xy(n)
+    out = eng.forward(dev(x), bn_group=bn_group, training=True).cpu().numpy()
+    _per_layer_check(eng, cfg, p, x.astype(np.float64), n, bn_group, 0.0, TOL[path])
+    ref = O.predict(cfg, p, x.astype(np.float64), bn_group)
+    e = rel_err(out, ref)
+    assert e < (5e-4 if path == "fp32" else 5e-2), f"end-to-end rel err {e}"
+    # inference-layout (rotating buffers) result equals the training-layout one
+    out2 = eng.forward(dev(x), bn_group=bn_group, training=False).cpu().numpy()
+    assert np.array_equal(out, out2)
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16"])
+def test_exponential_mask_forward(path):
+    eng, cfg, p = make_pair(L=1, knn=1, mask_type="exponential", path=path)
+    x, _ = synth_xy(128)
+    out = eng.forward(dev(x), bn_group=128, training=True).cpu().numpy()
+    _per_layer_check(eng, cfg, p, x.astype(np.float64), 128, 128, 0.0, TOL[path])
+    assert rel_err(out, O.forward(cfg, p, x.astype(np.float64))[0]) < (5e-4 if path == "fp32" else 5e-2)
+
+
+def test_wide_model_F128_forward():
+    eng, cfg, p = make_pair(F=128, L=1, knn=2, path="fp32")
+    x, _ = synth_xy(128)
+    out = eng.forward(dev(x), bn_group=128, training=True).cpu().numpy()
+    _per_layer_check(eng, cfg, p, x.astype(np.float64), 128, 128, 0.0, 1e-4)
+    assert rel_err(out, O.forward(cfg, p, x.astype(np.float64))[0]) < 5e-4
+
+
+def test_predict_zero_pads_last_batch_like_reference():
+    eng, cfg, p = make_pair(L=1, knn=3, path="fp32")
+    x, _ = synth_xy(300)
+    got = eng.predict(x, batch_size=128)
+    ref = O.predict(cfg, p, x.astype(np.float64), 128)
+    assert got.dtype == np.float64 and got.shape == (300, 51)
+    assert rel_err(got, ref) < 5e-4
+    # sharding the pose batch at BN-group granularity does not change any result
+    got2 = np.concatenate([eng.predict(x[:256], 128), eng.predict(x[256:], 128)])
+    assert np.array_equal(got, got2)
+
+
+def _keep_masks(eng, cfg, n, rate):
+    return [eng.dropout_keep(l, n, rate).cpu().numpy().astype(bool) for l in range(1 + 2 * cfg.num_layers)]
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16"])
+def test_dropout_forward_with_injected_keep_mask(path):
+    eng, cfg, p = make_pair(L=1, knn=3, path=path)
+    n, rate = 200, 0.25
+    x, _ = synth_xy(n)
+    keep = _keep_masks(eng, cfg, n, rate)
+    frac = np.mean([k.mean() for k in keep])
+    assert abs(frac - 0.75) < 0.01
+    out = eng.forward(dev(x), bn_group=n, training=True, dropout=rate).cpu().numpy()
+    _per_layer_check(eng, cfg, p, x.astype(np.float64), n, n, rate, TOL[path], keep)
+    ref, _ = O.forward(cfg, p, x.astype(np.float64), rate, keep)
+    assert rel_err(out, ref) < (5e-4 if path == "fp32" else 5e-2)
+
+
+GRAD_TOL = {"fp32": 2e-3, "bf16": 6e-2}
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16"])
+@pytest.mark.parametrize("L,knn,mask_type,n,rate", [(1, 3, "locally_connected", 200, 0.0),
+                                                     (2, 2, "locally_connected", 256, 0.25),
+                                                     (1, 1, "exponential", 128, 0.0)])
+def test_backward_gradients(path, L, knn, mask_type, n, rate):
+    eng, cfg, p = make_pair(L=L, knn=knn, mask_type=mask_type, path=path)
+    x, y = synth_xy(n)
+    keep = _keep_masks(eng, cfg, n, rate) if rate > 0 else None
+    xd, yd = dev(x), dev(y)
+    eng.forward(xd, bn_group=n, training=True, dropout=rate)
+    loss = eng.backward(xd, yd, rate).item()
+    g = eng.unflatten(eng.true_grads())
+    ref_loss, ref_g = O.loss_and_grads(cfg, p, x.astype(np.float64), y.astype(np.float64), rate, keep)
+    assert abs(loss - ref_loss) < (1e-4 if path == "fp32" else 2e-2) * ref_loss
+    assert set(g) == set(ref_g)
+    for k in sorted(ref_g):
+        e = rel_err(g[k], ref_g[k])
+        assert e < GRAD_TOL[path], f"grad {k}: rel err {e}"
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16"])
+def test_train_steps_match_tf1_adam(path):
+    eng, cfg, p = make_pair(L=1, knn=3, path=path, perturb=True)
+    n = 256
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    st = O.AdamState()
+    p_ref = {k: v.copy() for k, v in p.items()}
+    tol = 5e-3 if path == "fp32" else 1e-1
+    for step in range(3):
+        before = {k: v.copy() for k, v in p_ref.items()}
+        ref_loss, ref_lr, _ = O.train_step(cfg, p_ref, st, x.astype(np.float64), y.astype(np.float64))
+        loss, lr = eng.train_step(xd, yd)
+        assert abs(lr - ref_lr) < 1e-12
+        assert abs(loss.item() - ref_loss) < (2e-4 if path == "fp32" else 3e-2) * ref_loss
+        got = eng.get_params()
+        for k in p_ref:
+            d_ref = p_ref[k] - before[k]
+            d_got = got[k].astype(np.float64) - before[k]
+            scale = np.abs(d_ref).max()
+            if True:
+                assert np.abs(d_got - d_ref).max() < tol * scale + 1e-7 * np.abs(before[k]).max(), k
+        # keep both sides on the same trajectory: fp32 rounding of the parameters differs slightly
+        eng.set_params({k: v.astype(np.float32) for k, v in p_ref.items()})
+        for k, (o, r, c) in eng.tensors.items():
+            eng.adam_m[o:o + r * c].copy_(torch.as_tensor(st.m[k].astype(np.float32).reshape(-1)))
+            eng.adam_v[o:o + r * c].copy_(torch.as_tensor(st.v[k].astype(np.float32).reshape(-1)))
+    assert eng.step == 3
+
+
+def test_library_is_the_loaded_native_code():
+    import lcn_pose_b200._lib as L
+    maps = open("/proc/self/maps").read()
+    assert "liblcn_b200.so" in maps
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    assert L.load().lcn_version()
