@@ -130,6 +130,13 @@ int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, float* d_v, v
                         const float* d_grads_raw, float lr_t, float beta1, float beta2, float eps,
                         float regularization, void* stream);
 
+/* One LCN linear op in isolation, on the buffers of the last forward (tf.matmul(x, w) + b,
+ * models_att.py:662,692): mid layer `layer` (1..2*num_layers) recomputes Z_layer = A_{layer-1} * Wm + b
+ * (+ BN partial statistics); transposed != 0 runs the matching input-gradient GEMM dA = dZ * Wm^T into a
+ * scratch buffer.  Used by bench.py to time the dominant kernel alone, and by the parity tests. */
+int lcn_layer_gemm(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, int64_t n_rows,
+                   int32_t bn_group, int layer, int transposed, void* stream);
+
 /* Debug / parity taps: copy an internal tensor of the last forward/backward to dense fp32.
  * kind: 0 = Z_l (pre-BN linear output), 1 = A_l (layer output after BN/act/dropout/residual),
  *       2 = effective masked weight Wm_l (dense [Kin,Kout]), 3 = mask values [17,17],

@@ -344,14 +344,29 @@ extern "C" int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, fl
                          (cudaStream_t)stream);
 }
 
+extern "C" int lcn_layer_gemm(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, int64_t n_rows,
+                              int32_t bn_group, int layer, int transposed, void* stream) {
+  int rc = check_geom(m, n_rows, bn_group);
+  if (rc) return rc;
+  LCN_REQUIRE(d_params && d_ws, "null argument");
+  LCN_REQUIRE(layer >= 1 && layer <= 2 * m->d.num_layers, "layer %d is not a mid layer", layer);
+  WsLayout lay = lcn_ws_layout(m, n_rows, bn_group, 1);
+  if (ws_bytes < lay.total) {
+    lcn_set_error("workspace too small: %zu < %zu", ws_bytes, lay.total);
+    return LCN_ENOMEM;
+  }
+  return lcn_launch_layer_gemm(m, d_params, (char*)d_ws, lay, layer, transposed, (cudaStream_t)stream);
+}
+
 extern "C" int lcn_model_read_tensor(lcn_model* m, void* d_ws, size_t ws_bytes, int kind, int layer, int64_t n_rows,
                                      int32_t bn_group, float* d_dst, void* stream) {
   int rc = check_geom(m, n_rows, bn_group);
   if (rc) return rc;
   LCN_REQUIRE(d_ws && d_dst, "null argument");
   WsLayout lay = lcn_ws_layout(m, n_rows, bn_group, 1);
-  if (ws_bytes < lay.total) {
-    lcn_set_error("workspace too small: %zu < %zu", ws_bytes, lay.total);
+  size_t need = (kind == 2 || kind == 3) ? lay.off_part : lay.total;   // weights / mask live in the head
+  if (ws_bytes < need) {
+    lcn_set_error("workspace too small: %zu < %zu", ws_bytes, need);
     return LCN_ENOMEM;
   }
   return lcn_launch_read_tensor(m, (char*)d_ws, lay, kind, layer, d_dst, (cudaStream_t)stream);

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
                                                        const int32_t* __restrict__ action, int n_actions, int64_t n,
                                                        int protocol2, float* __restrict__ err_out,
                                                        double* __restrict__ sums) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   // per warp: pred[32*51], gt[32*51]; then per block: action sums (double)
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = smem + warp * (2 * 32 * EV_POSE);

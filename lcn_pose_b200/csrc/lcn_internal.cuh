@@ -151,6 +151,8 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
 int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
                     const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg,
                     cudaStream_t st);
+int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
+                          int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,
                            float* dst, cudaStream_t st);
 
@@ -168,6 +170,26 @@ __device__ __forceinline__ float lcn_ld(const float* p, size_t i) { return p[i];
 __device__ __forceinline__ float lcn_ld(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
 __device__ __forceinline__ void lcn_st(float* p, size_t i, float v) { p[i] = v; }
 __device__ __forceinline__ void lcn_st(__nv_bfloat16* p, size_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// Activation layouts in HBM.
+//  fp32 path: row-major [rows_pad][P].
+//  bf16 path: tile-major, each (128-row tile, 64-channel chunk) is ONE contiguous 16 KB block holding the
+//  UMMA SWIZZLE_128B image of the tile (row r at r*128 B, 16-byte chunk c stored at c ^ (r & 7)).  A tile
+//  therefore moves HBM<->smem with a single 1-D bulk TMA copy and is directly a K-major A operand
+//  (forward / dgrad) or an MN-major operand with K = rows (wgrad) of tcgen05.mma.
+// `col` multiples of 4 keep 4 consecutive elements contiguous in both layouts.
+template <typename T>
+__device__ __forceinline__ size_t lcn_off(int64_t row, int col, int P);
+template <>
+__device__ __forceinline__ size_t lcn_off<float>(int64_t row, int col, int P) {
+  return (size_t)row * P + col;
+}
+template <>
+__device__ __forceinline__ size_t lcn_off<__nv_bfloat16>(int64_t row, int col, int P) {
+  int r = (int)(row & 127), k = col & 63;
+  size_t tile = (size_t)(row >> 7) * (P >> 6) + (col >> 6);
+  return (tile * 128 + r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
+}
 
 // 4-wide vector access (16 B for fp32, 8 B for bf16); i is the element index, multiple of 4
 __device__ __forceinline__ float4 lcn_ld4(const float* p, size_t i) {

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
                                                      const float* __restrict__ wm, const float* __restrict__ bias,
                                                      T* __restrict__ Z, float* __restrict__ part, int P) {
   constexpr int KIN = LCN_J * IN_F;
-  __shared__ float xs[KIN][LCN_TILE];
+  __shared__ __align__(16) float xs[KIN][LCN_TILE];
   __shared__ unsigned char valid_s[LCN_TILE];
   int tile = blockIdx.x;
   for (int e = threadIdx.x; e < LCN_TILE * KIN; e += blockDim.x) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
       int r = r4 + q;
       bool v = valid_s[r];
       float val = v ? acc[q] : 0.f;
-      lcn_st(Z, ((size_t)tile * LCN_TILE + r) * P + c, val);
+      lcn_st(Z, lcn_off<T>((int64_t)tile * LCN_TILE + r, c, P), val);
       if (v) {
         if (nv == 0) shift = val;
         float d = val - shift;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
                                                    const float* __restrict__ bias, const T* __restrict__ addend,
                                                    T* __restrict__ Y, float* __restrict__ part, JointLists lists,
                                                    int P, int FC, int bn_group, int gstride) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* As = smem;                          // [128][65]
   float* Bs = smem + LCN_TILE * GS_APAD;     // [64][68]
   __shared__ float red[4][64];
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
       for (int it = 0; it < 8; ++it) {
         int f = tid + 256 * it;
         int r = f >> 4, kq = f & 15;
-        float4 v = lcn_ld4(A, (row0 + r) * P + col0 + kq * 4);
+        float4 v = lcn_ld4(A, lcn_off<T>(row0 + r, col0 + kq * 4, P));
         float* dst = As + r * GS_APAD + kq * 4;
         dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
       }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       float4 v = make_float4(acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w);
-      lcn_st4(Y, (row0 + ty * 8 + r) * P + ccol, v);
+      lcn_st4(Y, lcn_off<T>(row0 + ty * 8 + r, ccol, P), v);
       float* dst = As + (ty * 8 + r) * GS_APAD + tx * 4;
       dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
@@ -380,10 +380,10 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
     for (int r = 0; r < 8; ++r) {
       float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       if (addend != nullptr) {
-        float4 ad = lcn_ld4(addend, (row0 + ty * 8 + r) * P + ccol);
+        float4 ad = lcn_ld4(addend, lcn_off<T>(row0 + ty * 8 + r, ccol, P));
         v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
       }
-      lcn_st4(Y, (row0 + ty * 8 + r) * P + ccol, v);
+      lcn_st4(Y, lcn_off<T>(row0 + ty * 8 + r, ccol, P), v);
     }
   }
 }
@@ -391,36 +391,39 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics: merge per-tile (mean, M2) partials over the tiles of a group and the 17
 // joints (Keras BN axis=-1 on [B,17,F]: per channel over batch x joints, biased variance).
-// grid n_groups, 256 threads.
+// grid (n_groups, F/8), 256 threads = 8 channels x 32 slices; Chan's parallel-variance merge in fp64.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_bn_finalize(const float* __restrict__ part, float* __restrict__ stat, int P, int F,
-                              int tiles_per_group, int bn_group) {
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double mb, double qb) {
+  if (nb == 0.0) return;
+  double nn = n + nb, delta = mb - mean;
+  mean += delta * nb / nn;
+  m2 += qb + delta * delta * n * nb / nn;
+  n = nn;
+}
+__global__ void __launch_bounds__(256) k_bn_finalize(const float* __restrict__ part, float* __restrict__ stat, int P,
+                                                     int F, int tiles_per_group, int bn_group) {
   __shared__ double sn[256], smean[256], sm2[256];
   int g = blockIdx.x, tid = threadIdx.x;
-  int f = tid % F, slice = tid / F, nsl = 256 / F;
+  int c = tid & 7, slice = tid >> 3;
+  int f = blockIdx.y * 8 + c;
   double n = 0, mean = 0, m2 = 0;
   int items = tiles_per_group * LCN_J;
-  for (int it = slice; it < items; it += nsl) {
+  for (int it = slice; it < items; it += 32) {
     int t = it / LCN_J, j = it - t * LCN_J;
     double nb = (double)min(LCN_TILE, bn_group - t * LCN_TILE);
     size_t o = ((size_t)(g * tiles_per_group + t) * P + j * F + f) * 2;
-    double mb = part[o], qb = part[o + 1];
-    double nn = n + nb, delta = mb - mean;
-    mean += delta * nb / nn;
-    m2 += qb + delta * delta * n * nb / nn;
-    n = nn;
+    chan_merge(n, mean, m2, nb, (double)part[o], (double)part[o + 1]);
   }
   sn[tid] = n; smean[tid] = mean; sm2[tid] = m2;
-  __syncthreads();
-  if (slice == 0) {
-    for (int s = 1; s < nsl; ++s) {
-      double nb = sn[s * F + f], mb = smean[s * F + f], qb = sm2[s * F + f];
-      if (nb == 0) continue;
-      double nn = n + nb, delta = mb - mean;
-      mean += delta * nb / nn;
-      m2 += qb + delta * delta * n * nb / nn;
-      n = nn;
+  for (int off = 16; off > 0; off >>= 1) {
+    __syncthreads();
+    if (slice < off) {
+      int o = tid + off * 8;
+      chan_merge(n, mean, m2, sn[o], smean[o], sm2[o]);
+      sn[tid] = n; smean[tid] = mean; sm2[tid] = m2;
     }
+  }
+  if (slice == 0) {
     double var = m2 / n;
     stat[((size_t)g * F + f) * 2 + 0] = (float)mean;
     stat[((size_t)g * F + f) * 2 + 1] = (float)(1.0 / sqrt(var + (double)LCN_BN_EPS));
@@ -449,7 +452,8 @@ __global__ void k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
   for (int r = 0; r < 16; ++r) {
     int64_t pr = pr0 + r;
-    size_t o = (size_t)pr * P + c4;
+    size_t o = lcn_off<T>(pr, c4, P);
+    size_t olog = (size_t)pr * P + c4;
     if ((int)(pr % gstride) >= bn_group) {
       lcn_st4(Aout, o, make_float4(0.f, 0.f, 0.f, 0.f));
       continue;
@@ -460,7 +464,7 @@ __global__ void k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat
     for (int q = 0; q < 4; ++q) y[q] = y[q] > 0.f ? y[q] : LCN_LRELU * y[q];
     if (rate > 0.f) {
       uint32_t rb[4];
-      lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(o >> 2), rb);
+      lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(olog >> 2), rb);
 #pragma unroll
       for (int q = 0; q < 4; ++q) y[q] = lcn_keep(rb[q], rate) ? y[q] * inv_keep : 0.f;
     }
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(128) k_last_layer(const T* __restrict__ A, con
                                                     const float* __restrict__ bias, const float* __restrict__ x,
                                                     int in_F, RowGeom g, float* __restrict__ out_user,
                                                     float* __restrict__ out_ws, SupportBits sup, int P, int FC) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* As = smem;                         // [128][65]
   float* Ws = smem + LCN_TILE * GS_APAD;    // [64][17][4]
   int tile = blockIdx.x, tid = threadIdx.x;
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(128) k_last_layer(const T* __restrict__ A, con
     __syncthreads();
     for (int f = tid; f < LCN_TILE * 16; f += 128) {
       int r = f >> 4, kq = f & 15;
-      float4 v = lcn_ld4(A, (row0 + r) * P + ic * 64 + kq * 4);
+      float4 v = lcn_ld4(A, lcn_off<T>(row0 + r, ic * 64 + kq * 4, P));
       float* dst = As + r * GS_APAD + kq * 4;
       dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(256) k_last_layer_bwd(const T* __restrict__ A,
       for (int r = 0; r < 32; ++r) sdb += ds[r][threadIdx.x];
     if (act) {
       for (int r = 0; r < 32; ++r) {
-        size_t o = (row0 + rc + r) * P + c;
+        size_t o = lcn_off<T>(row0 + rc + r, c, P);
         float av = lcn_ld(A, o), da = 0.f;
 #pragma unroll
         for (int q = 0; q < 51; ++q) {
@@ -612,13 +616,13 @@ __global__ void __launch_bounds__(256) k_last_layer_bwd(const T* __restrict__ A,
 // grid rows_pad/16, block P/4.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void bn_bwd_dy(const T* dOut, const T* Z, size_t o, const float* sc, const float* sh,
+__device__ __forceinline__ void bn_bwd_dy(const T* dOut, const T* Z, size_t o, size_t olog, const float* sc, const float* sh,
                                           const float* mean, const float* rstd, float rate, float inv_keep,
                                           uint64_t seed, uint64_t step, int layer, float dy[4], float xh[4]) {
   float4 z = lcn_ld4(Z, o), d = lcn_ld4(dOut, o);
   float zz[4] = {z.x, z.y, z.z, z.w}, dd[4] = {d.x, d.y, d.z, d.w};
   uint32_t rb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-  if (rate > 0.f) lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(o >> 2), rb);
+  if (rate > 0.f) lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(olog >> 2), rb);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float ybn = fmaf(zz[q], sc[q], sh[q]);
@@ -634,7 +638,7 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict_
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float* __restrict__ sums, int P, int F, int bn_group, float rate, uint64_t seed,
                                 uint64_t step, int layer) {
-  extern __shared__ float red[];   // [P/4][8]
+  extern __shared__ __align__(16) float red[];   // [P/4][8]
   int c4 = threadIdx.x * 4, f0 = c4 % F;
   float sc[4], sh[4], mean[4], rstd[4];
 #pragma unroll
@@ -651,7 +655,7 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict_
     int64_t pr = pr0 + r;
     if (pr >= bn_group) break;
     float dy[4], xh[4];
-    bn_bwd_dy(dOut, Z, (size_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+    bn_bwd_dy(dOut, Z, lcn_off<T>(pr, c4, P), (size_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       s1[q] += dy[q];
@@ -708,13 +712,13 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__
   int64_t pr0 = (int64_t)blockIdx.x * 16;
   for (int r = 0; r < 16; ++r) {
     int64_t pr = pr0 + r;
-    size_t o = (size_t)pr * P + c4;
+    size_t o = lcn_off<T>(pr, c4, P);
     if (pr >= bn_group) {
       lcn_st4(dZ, o, make_float4(0.f, 0.f, 0.f, 0.f));
       continue;
     }
     float dy[4], xh[4], dz[4];
-    bn_bwd_dy(dOut, Z, o, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+    bn_bwd_dy(dOut, Z, o, (size_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       dz[q] = sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
@@ -752,8 +756,8 @@ __global__ void __launch_bounds__(256) k_wgrad_simt(const T* __restrict__ A, con
     for (int it = 0; it < 2; ++it) {
       int f = tid + 256 * it;
       int r = f >> 4, kq = f & 15;
-      *reinterpret_cast<float4*>(&As[r][kq * 4]) = lcn_ld4(A, (row0 + rc + r) * P + ic * 64 + kq * 4);
-      *reinterpret_cast<float4*>(&Ds[r][kq * 4]) = lcn_ld4(dZ, (row0 + rc + r) * P + oc * 64 + kq * 4);
+      *reinterpret_cast<float4*>(&As[r][kq * 4]) = lcn_ld4(A, lcn_off<T>(row0 + rc + r, ic * 64 + kq * 4, P));
+      *reinterpret_cast<float4*>(&Ds[r][kq * 4]) = lcn_ld4(dZ, lcn_off<T>(row0 + rc + r, oc * 64 + kq * 4, P));
     }
     __syncthreads();
 #pragma unroll 8
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(256) k_first_wgrad(const float* __restrict__ x
     __syncthreads();
     if (act) {
       for (int r = 0; r < 32; ++r) {
-        float dz = lcn_ld(dZ, (size_t)(row0 + rc + r) * P + c);
+        float dz = lcn_ld(dZ, lcn_off<T>(row0 + rc + r, c, P));
 #pragma unroll
         for (int k = 0; k < KIN; ++k) acc[k] = fmaf(xs[r][k], dz, acc[k]);
       }
@@ -1026,7 +1030,7 @@ static int forward_impl(const FwdArgs& a) {
     }
     LCN_CHECK_LAUNCH();
     float* stat = bn_stat(ws, lay, m, l);
-    k_bn_finalize<<<lay.n_groups, 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
+    k_bn_finalize<<<dim3(lay.n_groups, F / 8), 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
     const T* res = L.res_from >= 0 ? reinterpret_cast<const T*>(a_buf(ws, lay, L.res_from)) : nullptr;
     k_bn_act<T><<<(unsigned)(lay.rows_pad / 16), P / 4, 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off,
                                                                  res, Aout, P, F, lay.bn_group, lay.gstride,
@@ -1140,6 +1144,37 @@ int lcn_launch_backward(const lcn_model* m, const float* params, char* ws, const
              : backward_impl<float>(m, params, ws, lay, x, labels, dropout_rate, seed, step, loss, grads_raw, st);
 }
 
+template <typename T>
+static int layer_gemm_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int l,
+                           int transposed, cudaStream_t st) {
+  const int P = m->P, FC = m->FC;
+  const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
+  float* part = reinterpret_cast<float*>(ws + lay.off_part);
+  const T* Ain = reinterpret_cast<const T*>(transposed ? ws + lay.off_dz : a_buf(ws, lay, l - 1));
+  T* Y = reinterpret_cast<T*>(transposed ? ws + lay.off_d + 2 * lay.d_stride : z_buf(ws, lay, l));
+  if (tc) {
+    const char* wp = ws + (transposed ? lay.off_wp16b : lay.off_wp16f) + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+    return lcn_tc_gemm(m, lay, l - 1, transposed, reinterpret_cast<const __nv_bfloat16*>(Ain), wp,
+                       transposed ? nullptr : params + m->L[l].b_off, nullptr, reinterpret_cast<__nv_bfloat16*>(Y),
+                       transposed ? nullptr : part, st);
+  }
+  const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
+  if (transposed)
+    k_gemm_simt<T, true><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(Ain, wp, nullptr, nullptr, Y, nullptr,
+                                                                              m->by_in, P, FC, lay.bn_group, lay.gstride);
+  else
+    k_gemm_simt<T, false><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(
+        Ain, wp, params + m->L[l].b_off, nullptr, Y, part, m->by_out, P, FC, lay.bn_group, lay.gstride);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
+                          int transposed, cudaStream_t st) {
+  return m->d.path == LCN_PATH_BF16 ? layer_gemm_impl<__nv_bfloat16>(m, params, ws, lay, layer, transposed, st)
+                                    : layer_gemm_impl<float>(m, params, ws, lay, layer, transposed, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // parity taps
 // ------------------------------------------------------------------------------------------------
@@ -1151,7 +1186,7 @@ __global__ void k_read_rows(const T* __restrict__ src, float* __restrict__ dst, 
     int64_t lr = e / P;
     int c = (int)(e - lr * P);
     int64_t pr = (lr / bn_group) * gstride + lr % bn_group;
-    dst[e] = lcn_ld(src, (size_t)pr * P + c);
+    dst[e] = lcn_ld(src, lcn_off<T>(pr, c, P));
   }
 }
 __global__ void k_unpack_mid(const float* __restrict__ wp32, PairTable pt, int nnz, int F, int FC,

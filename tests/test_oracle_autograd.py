@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import lcn_oracle as O
-from tests import torch_restatement as T
+from oracle import torch_restatement as T
 
 CASES = [
     dict(mask_type="locally_connected", knn=3, F=8, L=2, B=12, drop=0.0, reg=0.0),
