@@ -237,11 +237,17 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_wp32 = take(sizeof(float) * n_mid * sub);
   w.off_wp16f = take(2 * n_mid * sub);
   w.off_wp16b = take(2 * n_mid * sub);
+  w.off_wl16f = take((size_t)LCN_J * m->FC * 8192);
+  w.off_wl16b = take((size_t)LCN_J * m->FC * 8192);
   w.off_part = take(sizeof(float) * (size_t)w.tiles * P * 2);
   w.off_bnstat = take(sizeof(float) * (size_t)m->n_bn * w.n_groups * F * 2);
   w.off_bnsum = take(sizeof(float) * (size_t)m->n_bn * F * 2);
   w.off_out = take(training ? sizeof(float) * (size_t)w.rows_pad * 51 : 0);
   w.off_dout = take(training ? sizeof(float) * (size_t)w.rows_pad * 51 : 0);
+  w.off_x16 = take(training ? (size_t)w.rows_pad * 64 * 2 : 0);
+  w.off_dout16 = take(training ? (size_t)w.rows_pad * 64 * 2 : 0);
+  w.off_dw_first = take(training ? sizeof(float) * 64 * P : 0);
+  w.off_dw_last = take(training ? sizeof(float) * P * 64 : 0);
   size_t act = ((size_t)w.rows_pad * P * w.es + 255) & ~(size_t)255;
   w.n_z = training ? m->n_bn : 1;
   w.n_a = training ? m->n_bn : 3;

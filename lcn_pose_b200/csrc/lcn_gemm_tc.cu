@@ -19,6 +19,7 @@
 // co-resident per SM (256 TMEM columns and ~97 KB smem each) so one CTA's epilogue overlaps the other's
 // main loop.
 #include <stdlib.h>
+#include <string.h>
 
 #include "lcn_internal.cuh"
 
@@ -29,11 +30,33 @@
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_G * TC_B_BYTES)
 #define TC_THREADS 192
 
+// optional per-CTA timeline (clock64) for block (0,0): enabled with -DLCN_TC_PROFILE
+#ifdef LCN_TC_PROFILE
+__device__ unsigned long long g_tc_prof[512];
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_tc_prof[(i)] = clock64(); } while (0)
+extern "C" int lcn_debug_read_prof(unsigned long long* h_out) {
+  return cudaMemcpyFromSymbol(h_out, g_tc_prof, sizeof(g_tc_prof)) == cudaSuccess ? 0 : -2;
+}
+#else
+#define TC_STAMP(i) do {} while (0)
+#endif
+
+enum { TC_MODE_FWD = 0, TC_MODE_DGRAD = 1, TC_MODE_HEAD = 2 };
+
 struct TcParams {
   uint32_t kmask[LCN_J];            // K-side joint -> bitmask of N-side joints with a block
-  int FC, NC, n_groups, P;
+  int FCK, FCN;                     // 64-chunks per joint on the K side / N side
+  int NCK, NCN;                     // chunk counts
+  int n_groups;                     // N-side chunk groups (grid.x)
+  int P;                            // N-side row width in elements (BN partial indexing)
   int bn_group, gstride;
-  int transposed;
+  int mode;                         // TC_MODE_*
+  // head mode (last layer): fp32 output [n_rows, 51] + xy skip from the 2D input
+  const float* x;
+  int in_F;
+  int64_t n_rows;
+  float* out_user;
+  float* out_ws;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -133,48 +156,39 @@ __device__ __forceinline__ void group_range(int g, int NC, int n_groups, int* oc
   *oc0 = g * base + min(g, extra);
 }
 
-// present N-side chunks of the group for K-side chunk kc: bit q set <=> block (kc -> oc0+q) exists
-__device__ __forceinline__ uint32_t present_bits(const TcParams& p, int kc, int oc0, int G) {
-  uint32_t km = p.kmask[kc / p.FC], bits = 0;
-  for (int q = 0; q < G; ++q)
-    if ((km >> ((oc0 + q) / p.FC)) & 1u) bits |= 1u << q;
-  return bits;
-}
-// index (in 64x64 blocks) of block (kc -> oc) inside the packed weight buffer of one layer
-__device__ __forceinline__ int panel_slot(const TcParams& p, int kc, int oc) {
-  int ka = kc / p.FC, hk = kc % p.FC, nb = oc / p.FC, hn = oc % p.FC;
-  int base = 0;
-  for (int q = 0; q < ka; ++q) base += __popc(p.kmask[q]);
-  uint32_t km = p.kmask[ka];
-  return p.FC * p.FC * base + hk * (__popc(km) * p.FC) + __popc(km & ((1u << nb) - 1u)) * p.FC + hn;
-}
-
 // ---------------------------------------------------------------------------------------------
-// forward / dgrad GEMM
+// forward / dgrad / head GEMM.  GMAX = max N-side chunks per CTA (64*GMAX TMEM columns).
 // ---------------------------------------------------------------------------------------------
+template <int GMAX, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __restrict__ A,
                                                         const __nv_bfloat16* __restrict__ Wp,
                                                         const float* __restrict__ bias,
                                                         const __nv_bfloat16* __restrict__ addend,
                                                         __nv_bfloat16* __restrict__ Y, float* __restrict__ part,
                                                         TcParams p) {
+  constexpr int STAGE_BYTES = TC_A_BYTES + GMAX * TC_B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[TC_G * 64];
+  __shared__ __align__(16) float bias_s[GMAX * 64];
+  // per-CTA schedule, built once in parallel: iteration -> (K chunk, present bits, first block slot)
+  __shared__ int sch_kc[2 * LCN_J], sch_slot[2 * LCN_J];
+  __shared__ uint32_t sch_bits[2 * LCN_J];
+  __shared__ int sch_n;
+  __shared__ uint32_t sch_written;
 
-  // 1024-byte aligned operand area (SWIZZLE_128B atoms are 1024 B)
   uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x, tile = blockIdx.y;
   int oc0, G;
-  group_range(g, p.NC, p.n_groups, &oc0, &G);
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]), tfull = smem_u32(&bars[2 * TC_STAGES]);
+  group_range(g, p.NCN, p.n_groups, &oc0, &G);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
   const uint32_t tmem_cols = G <= 1 ? 64u : (G == 2 ? 128u : 256u);
+  TC_STAMP(0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -182,65 +196,107 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), tmem_cols);
-  if (!p.transposed)
-    for (int c = threadIdx.x; c < G * 64; c += TC_THREADS) bias_s[c] = bias[oc0 * 64 + c];
+  if (warp == 2) {
+    // schedule: lanes cover K chunks kc = lane, lane + 32 (NCK <= 34); compaction by ballot
+    int n = 0;
+    uint32_t written = 0;
+    for (int base_kc = 0; base_kc < p.NCK; base_kc += 32) {
+      int kc = base_kc + lane;
+      uint32_t bits = 0;
+      int slot = 0;
+      if (kc < p.NCK) {
+        int ka = kc / p.FCK, hk = kc - ka * p.FCK;
+        uint32_t km = p.kmask[ka];
+        for (int q = 0; q < G; ++q)
+          if ((km >> ((oc0 + q) / p.FCN)) & 1u) bits |= 1u << q;
+        if (bits) {
+          int oc = oc0 + (__ffs(bits) - 1);
+          int nb = oc / p.FCN, hn = oc - nb * p.FCN;
+          int pb = 0;
+          for (int q = 0; q < ka; ++q) pb += __popc(p.kmask[q]);
+          slot = p.FCK * p.FCN * pb + hk * (__popc(km) * p.FCN) + __popc(km & ((1u << nb) - 1u)) * p.FCN + hn;
+        }
+      }
+      uint32_t bal = __ballot_sync(0xffffffffu, bits != 0);
+      if (bits) {
+        int pos = n + __popc(bal & ((1u << lane) - 1u));
+        sch_kc[pos] = kc;
+        sch_bits[pos] = bits;
+        sch_slot[pos] = slot;
+      }
+      n += __popc(bal);
+      for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+      written |= bits;
+    }
+    if (lane == 0) {
+      sch_n = n;
+      sch_written = written;
+    }
+  }
+  if (p.mode != TC_MODE_DGRAD)
+    for (int c = threadIdx.x; c < G * 64; c += TC_THREADS) {
+      int col = oc0 * 64 + c;
+      bias_s[c] = (p.mode == TC_MODE_HEAD && col >= 51) ? 0.f : bias[col];
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const int n_it = sch_n;
+  TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int it = 0;
-      for (int kc = 0; kc < p.NC; ++kc) {
-        uint32_t bits = present_bits(p, kc, oc0, G);
-        if (!bits) continue;
-        int s = it % TC_STAGES;
-        uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+      const __nv_bfloat16* a_tile = A + (size_t)tile * p.NCK * 8192;
+      for (int it = 0; it < n_it; ++it) {
+        int s = it % STAGES;
+        uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        int kc = sch_kc[it];
+        int cnt = __popc(sch_bits[it]);
+        const __nv_bfloat16* wsrc = Wp + (size_t)sch_slot[it] * 4096;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        int cnt = __popc(bits);
-        int first = oc0 + (__ffs(bits) - 1);
-        uint32_t sa = sbase + s * TC_STAGE_BYTES;
+        TC_STAMP(16 + 4 * it);
+        uint32_t sa = sbase + s * STAGE_BYTES;
         mbar_expect_tx(full0 + 8 * s, TC_A_BYTES + cnt * TC_B_BYTES);
-        bulk_g2s(sa, A + ((size_t)tile * p.NC + kc) * 8192, TC_A_BYTES, full0 + 8 * s);
-        bulk_g2s(sa + TC_A_BYTES, Wp + (size_t)panel_slot(p, kc, first) * 4096, cnt * TC_B_BYTES, full0 + 8 * s);
-        ++it;
+        bulk_g2s(sa, a_tile + (size_t)kc * 8192, TC_A_BYTES, full0 + 8 * s);
+        bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * s);
+        TC_STAMP(17 + 4 * it);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int it = 0;
       uint32_t written = 0;
-      for (int kc = 0; kc < p.NC; ++kc) {
-        uint32_t bits = present_bits(p, kc, oc0, G);
-        if (!bits) continue;
-        int s = it % TC_STAGES;
-        uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+      const uint64_t desc_hi = (uint64_t)((1024u >> 4) & 0x3FFF) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
+      for (int it = 0; it < n_it; ++it) {
+        int s = it % STAGES;
+        uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        uint32_t bits = sch_bits[it];
         mbar_wait(full0 + 8 * s, ph);
+        TC_STAMP(18 + 4 * it);
         tc_fence_after();
-        uint32_t sa = sbase + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+        uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
         int rank = 0, q = 0;
         while (q < G) {
           if (!((bits >> q) & 1u)) { ++q; continue; }
-          // maximal run of present chunks with the same accumulate state
-          uint32_t acc = (written >> q) & 1u;
+          uint32_t acc = (written >> q) & 1u;      // maximal run of present chunks with equal accumulate state
           int len = 1;
           while (q + len < G && ((bits >> (q + len)) & 1u) && (((written >> (q + len)) & 1u) == acc)) ++len;
           uint32_t idesc = umma_idesc(64 * len, 0, 0);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            uint64_t ad = umma_desc_sw128(sa + k4 * 32, 16, 1024);
-            uint64_t bd = umma_desc_sw128(sb + rank * TC_B_BYTES + k4 * 32, 16, 1024);
-            umma_f16(tmem_base + q * 64, ad, bd, idesc, (acc | (uint32_t)(k4 > 0)));
-          }
+          uint64_t bd0 = desc_hi | (uint64_t)(((sb + rank * TC_B_BYTES) >> 4) & 0x3FFF);
+          uint32_t d = tmem_base + q * 64;
+          umma_f16(d, ad0, bd0, idesc, acc);       // K = 64 -> 4 instructions of K = 16 (32 bytes each)
+          umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+          umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
+          umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
           written |= ((1u << len) - 1u) << q;
           rank += len;
           q += len;
         }
         umma_commit(empty0 + 8 * s);     // frees the smem stage when these MMAs have read it
-        ++it;
+        TC_STAMP(19 + 4 * it);
       }
       umma_commit(tfull);                // accumulators complete
     }
@@ -248,91 +304,140 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
     // ===== epilogue: 4 warps, warp's TMEM lane quarter = warp id % 4 =====
     const int lq = warp & 3;
     const int row = lq * 32 + lane;
+    const uint32_t written = sch_written;
     mbar_wait(tfull, 0);
+    if (threadIdx.x == 64) TC_STAMP(2);
     tc_fence_after();
-    uint32_t written = 0;
-    for (int kc = 0; kc < p.NC; ++kc) written |= present_bits(p, kc, oc0, G);
-    for (int q = 0; q < G; ++q) {
-      uint8_t* tile_s = sgen + q * TC_A_BYTES;
+    if (p.mode == TC_MODE_HEAD) {
+      // last layer: 51 valid columns of one chunk -> fp32 prediction rows (models_att.py:765-773)
+      int64_t pr = (int64_t)tile * LCN_TILE + row;
+      int64_t grp = pr / p.gstride;
+      int rin = (int)(pr - grp * p.gstride);
+      int64_t src = grp * p.bn_group + rin;
+      bool valid = rin < p.bn_group;
+      if (!(valid && src < p.n_rows)) src = -1;
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
-        if ((written >> q) & 1u) {
-          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + q * 64 + h * 32, v);
+        if (written & 1u) {
+          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + h * 32, v);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (!p.transposed) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += bias_s[q * 64 + h * 32 + i];
-        } else if (addend != nullptr) {
-          const uint8_t* arow = reinterpret_cast<const uint8_t*>(addend) +
-                                (((size_t)tile * p.NC + oc0 + q) * 128 + row) * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 u = *reinterpret_cast<const uint4*>(arow + (((h * 4 + c) ^ (row & 7)) << 4));
-            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 t = __bfloat1622float2(hp[e]);
-              f[c * 8 + 2 * e] += t.x;
-              f[c * 8 + 2 * e + 1] += t.y;
-            }
+        for (int i = 0; i < 32; ++i) {
+          int c = h * 32 + i;
+          if (c < 51) {
+            float val = __uint_as_float(v[i]) + bias_s[c];
+            int j = c / 3, cc = c - j * 3;
+            if (cc < 2 && src >= 0) val += p.x[src * (LCN_J * p.in_F) + j * p.in_F + cc];
+            if (p.out_ws != nullptr) p.out_ws[(size_t)pr * 51 + c] = valid ? val : 0.f;
+            if (src >= 0) p.out_user[src * 51 + c] = val;
           }
         }
-        // pack to bf16 and store the row's 4 sixteen-byte chunks into the swizzled staging tile
+      }
+    } else {
+      for (int q = 0; q < G; ++q) {
+        uint8_t* tile_s = sgen + q * TC_A_BYTES;
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          if ((written >> q) & 1u) {
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + q * 64 + h * 32, v);
+          } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]);
-          __nv_bfloat162 b1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]);
-          __nv_bfloat162 b3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
-          u.x = *reinterpret_cast<uint32_t*>(&b0);
-          u.y = *reinterpret_cast<uint32_t*>(&b1);
-          u.z = *reinterpret_cast<uint32_t*>(&b2);
-          u.w = *reinterpret_cast<uint32_t*>(&b3);
-          *reinterpret_cast<uint4*>(tile_s + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = u;
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.mode == TC_MODE_FWD) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + q * 64 + h * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 bv = b4[i];
+              f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
+            }
+          } else if (addend != nullptr) {
+            const uint8_t* arow = reinterpret_cast<const uint8_t*>(addend) +
+                                  (((size_t)tile * p.NCN + oc0 + q) * 128 + row) * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 u = *reinterpret_cast<const uint4*>(arow + (((h * 4 + c) ^ (row & 7)) << 4));
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 t = __bfloat1622float2(hp[e]);
+                f[c * 8 + 2 * e] += t.x;
+                f[c * 8 + 2 * e + 1] += t.y;
+              }
+            }
+          }
+          // pack to bf16 and store the row's 4 sixteen-byte chunks into the swizzled staging tile
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&b0);
+            u.y = *reinterpret_cast<uint32_t*>(&b1);
+            u.z = *reinterpret_cast<uint32_t*>(&b2);
+            u.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(tile_s + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = u;
+          }
         }
       }
-    }
-    tc_fence_before();
-    fence_proxy_async();                                   // generic smem writes -> bulk-store (async proxy) reads
-    asm volatile("bar.sync 1, 128;" ::: "memory");         // the 4 epilogue warps
-    if (warp == 2 && lane == 0) {
-      for (int q = 0; q < G; ++q)
-        bulk_s2g(Y + ((size_t)tile * p.NC + oc0 + q) * 8192, sbase + q * TC_A_BYTES, TC_A_BYTES);
-      bulk_commit_wait();
-    }
-    if (!p.transposed && part != nullptr) {
-      // BatchNorm partials of this tile: per column (mean, M2) over the valid rows, from the bf16 values
-      int q = warp - 2;
-      if (q < G) {
+      if (threadIdx.x == 64) TC_STAMP(3);
+      tc_fence_before();
+      fence_proxy_async();                                   // generic smem writes -> bulk-store (async proxy) reads
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // the 4 epilogue warps
+      if (warp == 2 && lane == 0) {
+        for (int q = 0; q < G; ++q)
+          bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * 8192, sbase + q * TC_A_BYTES, TC_A_BYTES);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.mode == TC_MODE_FWD && part != nullptr) {
+        // BatchNorm partials of this tile: per column (mean, M2) over the valid rows, from the bf16 values.
+        // 32 lanes x 4 row-quarters per chunk: warp w handles chunks w, w+4 ...; combine quarters by shuffle-free
+        // exact pairwise merge (equal counts are not guaranteed -> use Chan's formula).
         int tig = tile % (p.gstride / LCN_TILE);
         int nvalid = min(LCN_TILE, p.bn_group - tig * LCN_TILE);
-        const uint8_t* tile_s = sgen + q * TC_A_BYTES;
-        float sh0 = 0.f, sh1 = 0.f, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-        for (int r = 0; r < nvalid; ++r) {
-          uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-          float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-          if (r == 0) { sh0 = t.x; sh1 = t.y; }
-          float d0 = t.x - sh0, d1 = t.y - sh1;
-          s1a += d0; s2a = fmaf(d0, d0, s2a);
-          s1b += d1; s2b = fmaf(d1, d1, s2b);
+        for (int q = warp - 2; q < G; q += 4) {
+          const uint8_t* tile_s = sgen + q * TC_A_BYTES;
+          float sh0 = 0.f, sh1 = 0.f, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+          const uint32_t coff = (uint32_t)(lane & 3) * 4;
+          const int chunk = lane >> 2;
+          {
+            uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + ((chunk ^ 0) << 4) + coff);
+            float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+            sh0 = t.x; sh1 = t.y;
+          }
+#pragma unroll 8
+          for (int r = 0; r < nvalid; ++r) {
+            uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
+            float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+            float d0 = t.x - sh0, d1 = t.y - sh1;
+            s1a += d0; s2a = fmaf(d0, d0, s2a);
+            s1b += d1; s2b = fmaf(d1, d1, s2b);
+          }
+          float n = (float)nvalid;
+          size_t o = ((size_t)tile * p.P + (oc0 + q) * 64 + lane * 2) * 2;
+          float4 out = make_float4(sh0 + s1a / n, fmaxf(s2a - s1a * s1a / n, 0.f), sh1 + s1b / n,
+                                   fmaxf(s2b - s1b * s1b / n, 0.f));
+          *reinterpret_cast<float4*>(part + o) = out;
         }
-        float n = (float)nvalid;
-        size_t o = ((size_t)tile * p.P + (oc0 + q) * 64 + lane * 2) * 2;
-        float4 out = make_float4(sh0 + s1a / n, fmaxf(s2a - s1a * s1a / n, 0.f), sh1 + s1b / n,
-                                 fmaxf(s2b - s1b * s1b / n, 0.f));
-        *reinterpret_cast<float4*>(part + o) = out;
+      }
+      if (warp == 2 && lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        TC_STAMP(4);
       }
     }
+    if (threadIdx.x == 64) TC_STAMP(5);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -348,29 +453,102 @@ bool lcn_tc_enabled() {
   return v == 1;
 }
 
+template <int GMAX, int STAGES>
+static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
+                          const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, const TcParams& p, int tiles,
+                          cudaStream_t st) {
+  size_t smem = (size_t)STAGES * (TC_A_BYTES + GMAX * TC_B_BYTES) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm<GMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  k_tc_gemm<GMAX, STAGES><<<dim3(p.n_groups, tiles), TC_THREADS, smem, st>>>(A, W, bias, addend, Y, part, p);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+// Pick the N-side grouping: both configurations keep 2 CTAs resident per SM (~97 KB smem each);
+// choose the one whose CTA count fills the 2*SM slots best (fewest waves, then least idle).
+static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
+                           const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, TcParams& p, int tiles,
+                           int sm_count, cudaStream_t st) {
+  static int force = -1;
+  if (force < 0) {
+    const char* e = getenv("LCN_TC_G");
+    force = e ? atoi(e) : 0;
+  }
+  int slots = 2 * sm_count;
+  auto cost = [&](int gmax) {
+    long ctas = (long)tiles * ((p.NCN + gmax - 1) / gmax);
+    long waves = (ctas + slots - 1) / slots;
+    return (double)waves * gmax;            // time ~ waves x work per CTA (~ group size)
+  };
+  int g = (cost(2) < cost(4)) ? 2 : 4;
+  if (force == 2 || force == 4) g = force;
+  if (p.NCN == 1) g = 2;
+  p.n_groups = (p.NCN + g - 1) / g;
+  if (g == 2) return launch_tc_gemm<2, 3>(A, W, bias, addend, Y, part, p, tiles, st);
+  return launch_tc_gemm<4, 2>(A, W, bias, addend, Y, part, p, tiles, st);
+}
+
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed, const __nv_bfloat16* A,
                 const char* wpacked, const float* bias, const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part,
                 cudaStream_t st) {
   (void)mid_index;
   TcParams p;
+  memset(&p, 0, sizeof(p));
   for (int a = 0; a < LCN_J; ++a) p.kmask[a] = transposed ? m->sup.col[a] : m->sup.row[a];
-  p.FC = m->FC;
-  p.NC = LCN_J * m->FC;
-  p.n_groups = (p.NC + TC_G - 1) / TC_G;
+  p.FCK = p.FCN = m->FC;
+  p.NCK = p.NCN = LCN_J * m->FC;
   p.P = m->P;
   p.bn_group = lay.bn_group;
   p.gstride = lay.gstride;
-  p.transposed = transposed;
-  size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
-  static bool attr = false;
-  if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  k_tc_gemm<<<dim3(p.n_groups, lay.tiles), TC_THREADS, smem, st>>>(
-      A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, addend, Y, part, p);
-  LCN_CHECK_LAUNCH();
-  return LCN_OK;
+  p.mode = transposed ? TC_MODE_DGRAD : TC_MODE_FWD;
+  return pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, addend, Y, part, p, lay.tiles,
+                         m->sm_count, st);
+}
+
+// last layer (17*F -> 51) + output head on the tensor cores: one N-side chunk (51 columns padded to 64),
+// every K chunk present; weights packed by k_pack_last16 as one 64x64 block per K chunk.
+int lcn_tc_head(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const char* wpacked,
+                const float* bias, const float* x, float* out_user, float* out_ws, cudaStream_t st) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  for (int a = 0; a < LCN_J; ++a) p.kmask[a] = 1u;
+  p.FCK = m->FC;
+  p.FCN = 1;
+  p.NCK = LCN_J * m->FC;
+  p.NCN = 1;
+  p.P = 64;
+  p.bn_group = lay.bn_group;
+  p.gstride = lay.gstride;
+  p.mode = TC_MODE_HEAD;
+  p.x = x;
+  p.in_F = m->d.in_F;
+  p.n_rows = lay.n_rows;
+  p.out_user = out_user;
+  p.out_ws = out_ws;
+  return pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, nullptr, nullptr, nullptr, p,
+                         lay.tiles, m->sm_count, st);
+}
+
+// last layer input gradient dA = dOut * Wm4^T: one K chunk (dOut padded to 64 columns), all N chunks present
+int lcn_tc_head_dgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* dOut16, const char* wpacked,
+                      __nv_bfloat16* dA, cudaStream_t st) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.kmask[0] = (1u << LCN_J) - 1u;
+  p.FCK = 1;
+  p.FCN = m->FC;
+  p.NCK = 1;
+  p.NCN = LCN_J * m->FC;
+  p.P = m->P;
+  p.bn_group = lay.bn_group;
+  p.gstride = lay.gstride;
+  p.mode = TC_MODE_DGRAD;
+  return pick_and_launch(dOut16, reinterpret_cast<const __nv_bfloat16*>(wpacked), nullptr, nullptr, dA, nullptr, p,
+                         lay.tiles, m->sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,8 +562,11 @@ int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int tran
 #define TCW_PITCH 260   // floats per staged output row (1040 B: 16-byte aligned, bank-conflict free)
 
 struct TcwParams {
-  uint32_t row[LCN_J];     // outputs of input joint i
-  int FC, NC, P, tiles, tiles_per_cta;
+  uint32_t row[LCN_J];     // outputs (N-side joints) of input (M-side) joint i
+  int FCK, FCN;            // 64-chunks per joint on the A (M) side / dZ (N) side
+  int NCK, NCN;            // chunks per row tile of A / dZ
+  int ldw;                 // row pitch of dW in floats
+  int tiles, tiles_per_cta;
 };
 
 __device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src, uint32_t bytes) {
@@ -408,8 +589,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
   int ic = 0, gi = 0;
   {
     int u = blockIdx.x;
-    for (ic = 0; ic < p.NC; ++ic) {
-      int cnt = __popc(p.row[ic / p.FC]) * p.FC;
+    for (ic = 0; ic < p.NCK; ++ic) {
+      int cnt = __popc(p.row[ic / p.FCK]) * p.FCN;
       int ng = (cnt + TC_G - 1) / TC_G;
       if (u < ng) { gi = u; break; }
       u -= ng;
@@ -418,12 +599,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
   int ocs[TC_G];
   int len = 0;
   {
-    uint32_t bits = p.row[ic / p.FC];
+    uint32_t bits = p.row[ic / p.FCK];
     int e = 0;
     for (int j = 0; j < LCN_J; ++j) {
       if (!((bits >> j) & 1u)) continue;
-      for (int ho = 0; ho < p.FC; ++ho, ++e)
-        if (e >= gi * TC_G && e < gi * TC_G + TC_G) ocs[len++] = j * p.FC + ho;
+      for (int ho = 0; ho < p.FCN; ++ho, ++e)
+        if (e >= gi * TC_G && e < gi * TC_G + TC_G) ocs[len++] = j * p.FCN + ho;
     }
   }
   const int t0 = blockIdx.y * p.tiles_per_cta;
@@ -453,9 +634,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         uint32_t sa = sbase + s * TCW_STAGE_BYTES;
         mbar_expect_tx(full0 + 8 * s, (1 + len) * TC_A_BYTES);
-        bulk_g2s(sa, A + ((size_t)t * p.NC + ic) * 8192, TC_A_BYTES, full0 + 8 * s);
+        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic) * 8192, TC_A_BYTES, full0 + 8 * s);
         for (int q = 0; q < len; ++q)
-          bulk_g2s(sa + (1 + q) * TC_A_BYTES, dZ + ((size_t)t * p.NC + ocs[q]) * 8192, TC_A_BYTES, full0 + 8 * s);
+          bulk_g2s(sa + (1 + q) * TC_A_BYTES, dZ + ((size_t)t * p.NCN + ocs[q]) * 8192, TC_A_BYTES, full0 + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -501,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (lane < 16) {
       for (int q = 0; q < len; ++q)
-        bulk_reduce_add_f32(dW + (size_t)(ic * 64 + m) * p.P + ocs[q] * 64, smem_u32(out_s + m * TCW_PITCH + q * 64), 256);
+        bulk_reduce_add_f32(dW + (size_t)(ic * 64 + m) * p.ldw + ocs[q] * 64, smem_u32(out_s + m * TCW_PITCH + q * 64), 256);
       bulk_commit_wait();
     }
   }
@@ -510,21 +691,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW,
-                 cudaStream_t st) {
-  TcwParams p;
+static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW, int tiles,
+                           cudaStream_t st) {
   int units = 0;
-  for (int i = 0; i < LCN_J; ++i) {
-    p.row[i] = m->sup.row[i];
-    int cnt = __builtin_popcount(m->sup.row[i]) * m->FC;
-    units += m->FC * ((cnt + TC_G - 1) / TC_G);
+  for (int ic = 0; ic < p.NCK; ++ic) {
+    int cnt = __builtin_popcount(p.row[ic / p.FCK]) * p.FCN;
+    units += (cnt + TC_G - 1) / TC_G;
   }
-  p.FC = m->FC;
-  p.NC = LCN_J * m->FC;
-  p.P = m->P;
-  p.tiles = lay.tiles;
-  p.tiles_per_cta = lay.tiles >= 16 ? 4 : (lay.tiles >= 4 ? 2 : 1);
-  int splits = (lay.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.tiles = tiles;
+  p.tiles_per_cta = tiles >= 16 ? 4 : (tiles >= 4 ? 2 : 1);
+  int splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   size_t smem = (size_t)TC_STAGES * TCW_STAGE_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
@@ -534,4 +710,42 @@ int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A
   k_tc_wgrad<<<dim3(units, splits), TC_THREADS, smem, st>>>(A, dZ, dW, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
+}
+
+// mid layers: dWm (dense [P,P], only the nonzero blocks are touched)
+int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW,
+                 cudaStream_t st) {
+  TcwParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < LCN_J; ++i) p.row[i] = m->sup.row[i];
+  p.FCK = p.FCN = m->FC;
+  p.NCK = p.NCN = LCN_J * m->FC;
+  p.ldw = m->P;
+  return launch_tc_wgrad(p, A, dZ, dW, lay.tiles, st);
+}
+// last layer: dW4pad[P][64] += A_L^T dOut16 (one N chunk: 51 columns padded to 64)
+int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dOut16,
+                      float* dWpad, cudaStream_t st) {
+  TcwParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < LCN_J; ++i) p.row[i] = 1u;
+  p.FCK = m->FC;
+  p.FCN = 1;
+  p.NCK = LCN_J * m->FC;
+  p.NCN = 1;
+  p.ldw = 64;
+  return launch_tc_wgrad(p, A, dOut16, dWpad, lay.tiles, st);
+}
+// first layer: dW1pad[64][P] += X16^T dZ0 (one M chunk: 17*in_F columns padded to 64)
+int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* X16, const __nv_bfloat16* dZ,
+                       float* dWpad, cudaStream_t st) {
+  TcwParams p;
+  memset(&p, 0, sizeof(p));
+  p.row[0] = (1u << LCN_J) - 1u;
+  p.FCK = 1;
+  p.FCN = m->FC;
+  p.NCK = 1;
+  p.NCN = LCN_J * m->FC;
+  p.ldw = m->P;
+  return launch_tc_wgrad(p, X16, dZ, dWpad, lay.tiles, st);
 }

@@ -95,6 +95,9 @@ struct WsLayout {
   size_t off_wm_first, off_wm_last;  // dense masked fp32 effective weights of the edge layers
   size_t off_wp32;                   // fp32 packed mid-layer blocks  [mid][pair][FC][FC][64][64]
   size_t off_wp16f, off_wp16b;       // bf16 UMMA-layout packed blocks (forward / transposed)
+  size_t off_wl16f, off_wl16b;       // bf16 packed last-layer weights: per K chunk [64 n][64 k] / per N chunk
+  size_t off_x16, off_dout16;        // bf16 tiles of the 2D input / of dOut (64-column padded), training
+  size_t off_dw_first, off_dw_last;  // fp32 padded weight-gradient scratch of the edge layers
   size_t off_part;                   // float[tiles][P][2] BN partials (mean, M2)
   size_t off_bnstat;                 // float[n_bn][n_groups][F][2]  (mean, rstd)
   size_t off_bnsum;                  // float[n_bn][F][2]  backward sums (sum dy, sum dy*xhat)
@@ -163,6 +166,14 @@ int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int tran
                 __nv_bfloat16* Y, float* part, cudaStream_t st);
 int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ,
                  float* dW /* dense [P,P] */, cudaStream_t st);
+int lcn_tc_head(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const char* wpacked,
+                const float* bias, const float* x, float* out_user, float* out_ws, cudaStream_t st);
+int lcn_tc_head_dgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* dOut16, const char* wpacked,
+                      __nv_bfloat16* dA, cudaStream_t st);
+int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dOut16,
+                      float* dWpad, cudaStream_t st);
+int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* X16, const __nv_bfloat16* dZ,
+                       float* dWpad, cudaStream_t st);
 bool lcn_tc_enabled();
 
 // ---- device helpers ----
@@ -212,6 +223,46 @@ __device__ __forceinline__ void lcn_st4(__nv_bfloat16* p, size_t i, float4 v) {
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p + i) = u;
+}
+
+// 4-wide access into float arrays
+template <typename T>
+__device__ __forceinline__ void lcn_ldv4(const T* p, size_t i, float v[4]) {
+  float4 a = lcn_ld4(p, i);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <typename T>
+__device__ __forceinline__ void lcn_stv4(T* p, size_t i, const float v[4]) {
+  lcn_st4(p, i, make_float4(v[0], v[1], v[2], v[3]));
+}
+// 8-wide vector access (2 x 16 B for fp32, 16 B for bf16); element offset multiple of 8
+__device__ __forceinline__ void lcn_ld8(const float* p, size_t i, float v[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p + i), b = *reinterpret_cast<const float4*>(p + i + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lcn_ld8(const __nv_bfloat16* p, size_t i, float v[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p + i);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 t = __bfloat1622float2(h[e]);
+    v[2 * e] = t.x;
+    v[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void lcn_st8(float* p, size_t i, const float v[8]) {
+  *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void lcn_st8(__nv_bfloat16* p, size_t i, const float v[8]) {
+  uint4 u;
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&b0);
+  u.y = *reinterpret_cast<uint32_t*>(&b1);
+  u.z = *reinterpret_cast<uint32_t*>(&b2);
+  u.w = *reinterpret_cast<uint32_t*>(&b3);
+  *reinterpret_cast<uint4*>(p + i) = u;
 }
 
 // Philox4x32-10 counter-based generator; one call yields the 4 uniforms of elements 4*idx4 .. 4*idx4+3.

@@ -157,6 +157,21 @@ __global__ void k_pack_mid(const float* __restrict__ params, LinTable lt, PairTa
   }
 }
 
+// bf16 images of the last layer's masked weight for the tensor-core head (one 64x64 block per 64-channel chunk):
+//   wl16f[kc]: B[n = output column (51 padded to 64)][k = channel]   (forward:  out = A * Wm4)
+//   wl16b[kc]: B[n = channel][k = output column]                     (dgrad:    dA = dOut * Wm4^T)
+__global__ void k_pack_last16(const float* __restrict__ wm_last, __nv_bfloat16* __restrict__ wl16f,
+                              __nv_bfloat16* __restrict__ wl16b) {
+  int kc = blockIdx.x;
+  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+    int n = e >> 6, k = e & 63;      // n: output column jc, k: channel within chunk
+    float v = n < 51 ? wm_last[(size_t)(kc * 64 + k) * 51 + n] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    wl16f[(size_t)kc * 4096 + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = h;
+    wl16b[(size_t)kc * 4096 + k * 64 + ((((n >> 3) ^ (k & 7)) << 3) | (n & 7))] = h;
+  }
+}
+
 int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
                        bool recompute_norm, cudaStream_t st) {
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
@@ -176,6 +191,10 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
                                   reinterpret_cast<float*>(ws + lay.off_wm_first));
   k_pack_edge<<<64, 256, 0, st>>>(params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_last));
+  if (m->d.path == LCN_PATH_BF16)
+    k_pack_last16<<<LCN_J * m->FC, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_wm_last),
+                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
+                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
   int n_mid = m->n_lin - 2;
   if (n_mid > 0) {
     k_pack_mid<<<dim3(m->nnz * m->FC * m->FC, n_mid), 256, 0, st>>>(
@@ -211,7 +230,8 @@ __device__ __forceinline__ bool row_valid(const RowGeom& g, int64_t pr, int64_t*
 template <typename T, int IN_F>
 __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x, RowGeom g,
                                                      const float* __restrict__ wm, const float* __restrict__ bias,
-                                                     T* __restrict__ Z, float* __restrict__ part, int P) {
+                                                     T* __restrict__ Z, float* __restrict__ part, int P,
+                                                     __nv_bfloat16* __restrict__ x16) {
   constexpr int KIN = LCN_J * IN_F;
   __shared__ __align__(16) float xs[KIN][LCN_TILE];
   __shared__ unsigned char valid_s[LCN_TILE];
@@ -224,6 +244,12 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
     if (k == 0) valid_s[r] = v;
   }
   __syncthreads();
+  if (x16 != nullptr && blockIdx.y == 0) {   // bf16 tile of the (zero padded) input: operand of the tensor-core wgrad
+    for (int e = threadIdx.x; e < LCN_TILE * 64; e += blockDim.x) {
+      int r = e >> 6, cc = e & 63;
+      x16[lcn_off<__nv_bfloat16>((int64_t)tile * LCN_TILE + r, cc, 64)] = __float2bfloat16_rn(cc < KIN ? xs[cc][r] : 0.f);
+    }
+  }
   int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= P) return;
   float w[KIN];
@@ -391,40 +417,49 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics: merge per-tile (mean, M2) partials over the tiles of a group and the 17
 // joints (Keras BN axis=-1 on [B,17,F]: per channel over batch x joints, biased variance).
-// grid (n_groups, F/8), 256 threads = 8 channels x 32 slices; Chan's parallel-variance merge in fp64.
+// grid (n_groups, F/2), 256 threads = 2 channels x 128 slices.  Two-pass merge in fp64:
+//   mean = sum n_b mean_b / N ;  M2 = sum [ M2_b + n_b (mean_b - mean)^2 ]   (exact, no per-item division)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double mb, double qb) {
-  if (nb == 0.0) return;
-  double nn = n + nb, delta = mb - mean;
-  mean += delta * nb / nn;
-  m2 += qb + delta * delta * n * nb / nn;
-  n = nn;
-}
 __global__ void __launch_bounds__(256) k_bn_finalize(const float* __restrict__ part, float* __restrict__ stat, int P,
                                                      int F, int tiles_per_group, int bn_group) {
-  __shared__ double sn[256], smean[256], sm2[256];
+  __shared__ double sa[256];
+  __shared__ double smean[2];
   int g = blockIdx.x, tid = threadIdx.x;
-  int c = tid & 7, slice = tid >> 3;
-  int f = blockIdx.y * 8 + c;
-  double n = 0, mean = 0, m2 = 0;
+  int c = tid & 1, slice = tid >> 1;
+  int f = blockIdx.y * 2 + c;
   int items = tiles_per_group * LCN_J;
-  for (int it = slice; it < items; it += 32) {
+  double ntot = (double)bn_group * LCN_J;
+  double acc = 0;
+  for (int it = slice; it < items; it += 128) {
+    int t = it / LCN_J, j = it - t * LCN_J;
+    double nb = (double)min(LCN_TILE, bn_group - t * LCN_TILE);
+    acc += nb * (double)part[((size_t)(g * tiles_per_group + t) * P + j * F + f) * 2];
+  }
+  sa[tid] = acc;
+  for (int off = 64; off > 0; off >>= 1) {
+    __syncthreads();
+    if (slice < off) sa[tid] += sa[tid + off * 2];
+  }
+  __syncthreads();
+  if (slice == 0) smean[c] = sa[tid] / ntot;
+  __syncthreads();
+  double mean = smean[c];
+  acc = 0;
+  for (int it = slice; it < items; it += 128) {
     int t = it / LCN_J, j = it - t * LCN_J;
     double nb = (double)min(LCN_TILE, bn_group - t * LCN_TILE);
     size_t o = ((size_t)(g * tiles_per_group + t) * P + j * F + f) * 2;
-    chan_merge(n, mean, m2, nb, (double)part[o], (double)part[o + 1]);
+    double d = (double)part[o] - mean;
+    acc += (double)part[o + 1] + nb * d * d;
   }
-  sn[tid] = n; smean[tid] = mean; sm2[tid] = m2;
-  for (int off = 16; off > 0; off >>= 1) {
+  __syncthreads();
+  sa[tid] = acc;
+  for (int off = 64; off > 0; off >>= 1) {
     __syncthreads();
-    if (slice < off) {
-      int o = tid + off * 8;
-      chan_merge(n, mean, m2, sn[o], smean[o], sm2[o]);
-      sn[tid] = n; smean[tid] = mean; sm2[tid] = m2;
-    }
+    if (slice < off) sa[tid] += sa[tid + off * 2];
   }
   if (slice == 0) {
-    double var = m2 / n;
+    double var = sa[tid] / ntot;
     stat[((size_t)g * F + f) * 2 + 0] = (float)mean;
     stat[((size_t)g * F + f) * 2 + 1] = (float)(1.0 / sqrt(var + (double)LCN_BN_EPS));
   }
@@ -432,15 +467,17 @@ __global__ void __launch_bounds__(256) k_bn_finalize(const float* __restrict__ p
 
 // ------------------------------------------------------------------------------------------------
 // BN apply + LeakyReLU(0.2) + dropout + residual (models_att.py:664-673,704).
-// grid rows_pad/16, block P/4 threads; thread = 4 consecutive columns, 16 rows.
+// grid rows_pad/16, block (P/8, 4): thread = 8 consecutive columns (one 16-byte bf16 chunk), 4 rows with
+// all loads in flight before the first use (HBM/L2-bound elementwise pass).
 // ------------------------------------------------------------------------------------------------
+#define EW_MAXT 544   // (P/4) x EW_Y threads: (272,2) for F=64, (544,1) for F=128
 template <typename T>
-__global__ void k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(EW_MAXT) k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ Aout, int P, int F,
                          int bn_group, int gstride, float rate, uint64_t seed, uint64_t step, int layer) {
   int c4 = threadIdx.x * 4;
   int f0 = c4 % F;
-  int64_t pr0 = (int64_t)blockIdx.x * 16;
+  int64_t pr0 = (int64_t)blockIdx.x * (4 * blockDim.y);
   int g = (int)(pr0 / gstride);
   float sc[4], sh[4];
 #pragma unroll
@@ -450,29 +487,42 @@ __global__ void k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat
     sh[q] = beta[f0 + q] - mean * sc[q];
   }
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  for (int r = 0; r < 16; ++r) {
-    int64_t pr = pr0 + r;
-    size_t o = lcn_off<T>(pr, c4, P);
-    size_t olog = (size_t)pr * P + c4;
-    if ((int)(pr % gstride) >= bn_group) {
-      lcn_st4(Aout, o, make_float4(0.f, 0.f, 0.f, 0.f));
-      continue;
-    }
-    float4 z = lcn_ld4(Z, o);
-    float y[4] = {fmaf(z.x, sc[0], sh[0]), fmaf(z.y, sc[1], sh[1]), fmaf(z.z, sc[2], sh[2]), fmaf(z.w, sc[3], sh[3])};
+  float z[4][4], rv[4][4];
+  size_t o[4];
+  bool valid[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) y[q] = y[q] > 0.f ? y[q] : LCN_LRELU * y[q];
-    if (rate > 0.f) {
+  for (int u = 0; u < 4; ++u) {
+    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
+    o[u] = lcn_off<T>(pr, c4, P);
+    valid[u] = (int)(pr % gstride) < bn_group;
+    if (valid[u]) {
+      lcn_ldv4(Z, o[u], z[u]);
+      if (res != nullptr) lcn_ldv4(res, o[u], rv[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float y[4];
+    if (!valid[u]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y[q] = 0.f;
+    } else {
+      int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
       uint32_t rb[4];
-      lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(olog >> 2), rb);
+      if (rate > 0.f) {
+        uint64_t i4 = ((uint64_t)pr * P + c4) >> 2;
+        lcn_philox4(seed, step, (uint32_t)layer, i4, rb);
+      }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) y[q] = lcn_keep(rb[q], rate) ? y[q] * inv_keep : 0.f;
+      for (int q = 0; q < 4; ++q) {
+        float v = fmaf(z[u][q], sc[q], sh[q]);
+        v = v > 0.f ? v : LCN_LRELU * v;
+        if (rate > 0.f) v = lcn_keep(rb[q], rate) ? v * inv_keep : 0.f;
+        if (res != nullptr) v += rv[u][q];
+        y[q] = v;
+      }
     }
-    if (res != nullptr) {
-      float4 rv = lcn_ld4(res, o);
-      y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-    }
-    lcn_st4(Aout, o, make_float4(y[0], y[1], y[2], y[3]));
+    lcn_stv4(Aout, o[u], y);
   }
 }
 
@@ -539,23 +589,39 @@ __global__ void __launch_bounds__(128) k_last_layer(const T* __restrict__ A, con
 // ------------------------------------------------------------------------------------------------
 // loss and its gradient: mean((out-labels)^2) over B*51 (models_att.py:356); dOut = 2 (out-y)/(B*51)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_loss_dout(const float* __restrict__ out_ws, const float* __restrict__ labels, int64_t n_rows,
-                            int64_t rows_pad, float* __restrict__ dout, double* loss_acc) {
+// grid rows_pad/64, 256 threads: thread = (column c = tid%64, row slice tid/64)
+__global__ void __launch_bounds__(256) k_loss_dout(const float* __restrict__ out_ws, const float* __restrict__ labels,
+                                                   int64_t n_rows, float* __restrict__ dout,
+                                                   __nv_bfloat16* __restrict__ dout16, float* __restrict__ db,
+                                                   double* loss_acc) {
   __shared__ double sh[32];
-  double s = 0.0;
+  __shared__ float csum[4][64];
+  int c = threadIdx.x & 63, rs = threadIdx.x >> 6;
   float inv = 2.0f / ((float)n_rows * 51.f);
-  int64_t n = rows_pad * 51;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t pr = e / 51;
-    float d = 0.f;
-    if (pr < n_rows) {
-      d = out_ws[e] - labels[e];
-      s += (double)d * d;
+  double s = 0.0;
+  float cs = 0.f;
+  int64_t pr0 = (int64_t)blockIdx.x * 64;
+  for (int r = rs; r < 64; r += 4) {
+    int64_t pr = pr0 + r;
+    float gsc = 0.f;
+    if (c < 51) {
+      float d = 0.f;
+      if (pr < n_rows) {
+        d = out_ws[pr * 51 + c] - labels[pr * 51 + c];
+        s += (double)d * d;
+      }
+      gsc = d * inv;
+      dout[pr * 51 + c] = gsc;
+      cs += gsc;
     }
-    dout[e] = d * inv;
+    if (dout16 != nullptr) dout16[lcn_off<__nv_bfloat16>(pr, c, 64)] = __float2bfloat16_rn(gsc);
   }
+  csum[rs][c] = cs;
   s = block_reduce_sum_d(s, sh);
   if (threadIdx.x == 0) atomicAdd(loss_acc, s);
+  __syncthreads();
+  if (db != nullptr && threadIdx.x < 51)
+    atomicAdd(&db[threadIdx.x], csum[0][threadIdx.x] + csum[1][threadIdx.x] + csum[2][threadIdx.x] + csum[3][threadIdx.x]);
 }
 __global__ void k_loss_final(const double* loss_acc, int64_t n_rows, float* loss_out) {
   loss_out[0] = (float)(loss_acc[0] / ((double)n_rows * 51.0));
@@ -613,32 +679,33 @@ __global__ void __launch_bounds__(256) k_last_layer_bwd(const T* __restrict__ A,
 //   dy   = dOut * keep/(1-rate) * (ybn > 0 ? 1 : 0.2)
 //   sums = (sum dy, sum dy*xhat) per channel        [k_bn_bwd_reduce]
 //   dZ   = gamma*rstd*(dy - s1/n - xhat*s2/n)       [k_bn_bwd_apply], db = sum_rows dZ
-// grid rows_pad/16, block P/4.
+// grid rows_pad/16, block (P/8, 4); thread = 8 columns x 4 rows, loads issued up front.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void bn_bwd_dy(const T* dOut, const T* Z, size_t o, size_t olog, const float* sc, const float* sh,
-                                          const float* mean, const float* rstd, float rate, float inv_keep,
-                                          uint64_t seed, uint64_t step, int layer, float dy[4], float xh[4]) {
-  float4 z = lcn_ld4(Z, o), d = lcn_ld4(dOut, o);
-  float zz[4] = {z.x, z.y, z.z, z.w}, dd[4] = {d.x, d.y, d.z, d.w};
-  uint32_t rb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-  if (rate > 0.f) lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)(olog >> 2), rb);
+__device__ __forceinline__ void bn_bwd_dy4(const float z[4], const float d[4], uint64_t olog, const float* sc,
+                                           const float* sh, const float* mean, const float* rstd, float rate,
+                                           float inv_keep, uint64_t seed, uint64_t step, int layer, float dy[4],
+                                           float xh[4]) {
+  uint32_t rb[4];
+  if (rate > 0.f) {
+    lcn_philox4(seed, step, (uint32_t)layer, olog >> 2, rb);
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float ybn = fmaf(zz[q], sc[q], sh[q]);
-    float v = dd[q];
+    float ybn = fmaf(z[q], sc[q], sh[q]);
+    float v = d[q];
     if (rate > 0.f) v = lcn_keep(rb[q], rate) ? v * inv_keep : 0.f;
     dy[q] = ybn > 0.f ? v : LCN_LRELU * v;
-    xh[q] = (zz[q] - mean[q]) * rstd[q];
+    xh[q] = (z[q] - mean[q]) * rstd[q];
   }
 }
 
 template <typename T>
-__global__ void k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
+__global__ void __launch_bounds__(EW_MAXT) k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float* __restrict__ sums, int P, int F, int bn_group, float rate, uint64_t seed,
                                 uint64_t step, int layer) {
-  extern __shared__ __align__(16) float red[];   // [P/4][8]
+  extern __shared__ __align__(16) float red[];   // [blockDim.y][P/4][8]
   int c4 = threadIdx.x * 4, f0 = c4 % F;
   float sc[4], sh[4], mean[4], rstd[4];
 #pragma unroll
@@ -649,41 +716,56 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict_
     sh[q] = beta[f0 + q] - mean[q] * sc[q];
   }
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  int64_t pr0 = (int64_t)blockIdx.x * 16;
-  for (int r = 0; r < 16; ++r) {
-    int64_t pr = pr0 + r;
-    if (pr >= bn_group) break;
+  float s1[4], s2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s1[q] = s2[q] = 0.f;
+  int64_t pr0 = (int64_t)blockIdx.x * (4 * blockDim.y);
+  float z[4][4], d[4][4];
+  bool valid[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
+    valid[u] = pr < bn_group;
+    if (valid[u]) {
+      size_t o = lcn_off<T>(pr, c4, P);
+      lcn_ldv4(Z, o, z[u]);
+      lcn_ldv4(dOut, o, d[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (!valid[u]) continue;
+    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
     float dy[4], xh[4];
-    bn_bwd_dy(dOut, Z, lcn_off<T>(pr, c4, P), (size_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+    bn_bwd_dy4<T>(z[u], d[u], (uint64_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       s1[q] += dy[q];
       s2[q] = fmaf(dy[q], xh[q], s2[q]);
     }
   }
+  int nt = blockDim.x;
+  float* mine = red + ((size_t)threadIdx.y * nt + threadIdx.x) * 8;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    red[threadIdx.x * 8 + q] = s1[q];
-    red[threadIdx.x * 8 + 4 + q] = s2[q];
+    mine[q] = s1[q];
+    mine[4 + q] = s2[q];
   }
   __syncthreads();
-  int per = F / 4;
-  if ((int)threadIdx.x < per) {
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j = 0; j < LCN_J; ++j)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] += red[(threadIdx.x + j * per) * 8 + q];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      atomicAdd(&sums[(f0 + q) * 2 + 0], a[q]);
-      atomicAdd(&sums[(f0 + q) * 2 + 1], a[4 + q]);
-    }
+  int per = F / 4;                               // threads (x) per joint
+  int t = threadIdx.y * nt + threadIdx.x;
+  if (t < per * 8) {                             // one thread per (channel-quad, value)
+    int oct = t / 8, v = t % 8;
+    float a = 0.f;
+    for (int y = 0; y < (int)blockDim.y; ++y)
+      for (int j = 0; j < LCN_J; ++j) a += red[((size_t)y * nt + oct + j * per) * 8 + v];
+    int f = oct * 4 + (v & 3);
+    atomicAdd(&sums[f * 2 + (v >> 2)], a);
   }
 }
 
 template <typename T>
-__global__ void k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
+__global__ void __launch_bounds__(EW_MAXT) k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ sums, T* __restrict__ dZ, float* __restrict__ db,
                                float* __restrict__ dgamma, float* __restrict__ dbeta, int P, int F, int bn_group,
@@ -700,7 +782,7 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__
     m1[q] = sums[(f0 + q) * 2] * inv_n;
     m2[q] = sums[(f0 + q) * 2 + 1] * inv_n;
   }
-  if (blockIdx.x == 0 && (int)threadIdx.x < F / 4) {
+  if (blockIdx.x == 0 && threadIdx.y == 0 && (int)threadIdx.x < F / 4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       dbeta[f0 + q] = sums[(f0 + q) * 2];
@@ -708,23 +790,40 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__
     }
   }
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  float bsum[4] = {0, 0, 0, 0};
-  int64_t pr0 = (int64_t)blockIdx.x * 16;
-  for (int r = 0; r < 16; ++r) {
-    int64_t pr = pr0 + r;
-    size_t o = lcn_off<T>(pr, c4, P);
-    if (pr >= bn_group) {
-      lcn_st4(dZ, o, make_float4(0.f, 0.f, 0.f, 0.f));
-      continue;
-    }
-    float dy[4], xh[4], dz[4];
-    bn_bwd_dy(dOut, Z, o, (size_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+  float bsum[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      dz[q] = sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
-      bsum[q] += dz[q];
+  for (int q = 0; q < 4; ++q) bsum[q] = 0.f;
+  int64_t pr0 = (int64_t)blockIdx.x * (4 * blockDim.y);
+  float z[4][4], d[4][4];
+  size_t o[4];
+  bool valid[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
+    o[u] = lcn_off<T>(pr, c4, P);
+    valid[u] = pr < bn_group;
+    if (valid[u]) {
+      lcn_ldv4(Z, o[u], z[u]);
+      lcn_ldv4(dOut, o[u], d[u]);
     }
-    lcn_st4(dZ, o, make_float4(dz[0], dz[1], dz[2], dz[3]));
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float dz[4];
+    if (!valid[u]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dz[q] = 0.f;
+    } else {
+      int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
+      float dy[4], xh[4];
+      bn_bwd_dy4<T>(z[u], d[u], (uint64_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dz[q] = sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
+        bsum[q] += dz[q];
+      }
+    }
+    lcn_stv4(dZ, o[u], dz);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) atomicAdd(&db[c4 + q], bsum[q]);
@@ -1010,9 +1109,10 @@ static int forward_impl(const FwdArgs& a) {
     if (l == 0) {
       dim3 grid(lay.tiles, (P + 255) / 256);
       const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
+      __nv_bfloat16* x16 = (tc && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
       switch (m->d.in_F) {
-        case 2: k_first_layer<T, 2><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P); break;
-        case 3: k_first_layer<T, 3><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P); break;
+        case 2: k_first_layer<T, 2><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
+        case 3: k_first_layer<T, 3><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
         default: lcn_set_error("in_F=%d not supported (2 or 3)", m->d.in_F); return LCN_EINVAL;
       }
     } else {
@@ -1030,9 +1130,10 @@ static int forward_impl(const FwdArgs& a) {
     }
     LCN_CHECK_LAUNCH();
     float* stat = bn_stat(ws, lay, m, l);
-    k_bn_finalize<<<dim3(lay.n_groups, F / 8), 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
+    k_bn_finalize<<<dim3(lay.n_groups, F / 2), 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
     const T* res = L.res_from >= 0 ? reinterpret_cast<const T*>(a_buf(ws, lay, L.res_from)) : nullptr;
-    k_bn_act<T><<<(unsigned)(lay.rows_pad / 16), P / 4, 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off,
+    const int ewy = (P / 4) * 2 <= EW_MAXT ? 2 : 1;
+    k_bn_act<T><<<(unsigned)(lay.rows_pad / (4 * ewy)), dim3(P / 4, ewy), 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off,
                                                                  res, Aout, P, F, lay.bn_group, lay.gstride,
                                                                  a.dropout_rate, a.seed, a.step, l);
     LCN_CHECK_LAUNCH();
@@ -1040,9 +1141,15 @@ static int forward_impl(const FwdArgs& a) {
   int last = m->n_lin - 1;
   const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, n_bn - 1));
   float* out_ws = lay.training ? reinterpret_cast<float*>(ws + lay.off_out) : nullptr;
-  k_last_layer<T><<<lay.tiles, 128, gemm_smem, st>>>(Ain, reinterpret_cast<const float*>(ws + lay.off_wm_last),
-                                                     a.params + m->L[last].b_off, a.x, m->d.in_F, g, a.out, out_ws,
-                                                     m->sup, P, FC);
+  if (tc) {
+    int rc = lcn_tc_head(m, lay, reinterpret_cast<const __nv_bfloat16*>(Ain), ws + lay.off_wl16f,
+                         a.params + m->L[last].b_off, a.x, a.out, out_ws, st);
+    if (rc) return rc;
+  } else {
+    k_last_layer<T><<<lay.tiles, 128, gemm_smem, st>>>(Ain, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+                                                       a.params + m->L[last].b_off, a.x, m->d.in_F, g, a.out, out_ws,
+                                                       m->sup, P, FC);
+  }
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
@@ -1063,8 +1170,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_bnsum, 0, sizeof(float) * m->n_bn * F * 2, st));
   float* dout = reinterpret_cast<float*>(ws + lay.off_dout);
   double* lacc = reinterpret_cast<double*>(ws + lay.off_loss);
-  k_loss_dout<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_out), labels, lay.n_rows, lay.rows_pad,
-                                   dout, lacc);
+  __nv_bfloat16* dout16 = tc ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dout16) : nullptr;
+  k_loss_dout<<<(unsigned)(lay.rows_pad / 64), 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_out), labels,
+                                                             lay.n_rows, dout, dout16,
+                                                             tc ? graw + m->L[m->n_lin - 1].b_off : nullptr, lacc);
   k_loss_final<<<1, 1, 0, st>>>(lacc, lay.n_rows, loss);
   LCN_CHECK_LAUNCH();
 
@@ -1074,27 +1183,47 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   int rows_blk = 512;
   while (lay.rows_pad % rows_blk) rows_blk >>= 1;   // rows_pad is a multiple of 128
   int cur = 0;
-  {
+  if (tc) {
+    const __nv_bfloat16* Ain = reinterpret_cast<const __nv_bfloat16*>(a_buf(ws, lay, m->n_bn - 1));
+    float* dwl = reinterpret_cast<float*>(ws + lay.off_dw_last);
+    LCN_CHECK_CUDA(cudaMemsetAsync(dwl, 0, sizeof(float) * P * 64, st));
+    LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_dw_first, 0, sizeof(float) * 64 * P, st));
+    int rc = lcn_tc_head_dgrad(m, lay, dout16, ws + lay.off_wl16b, reinterpret_cast<__nv_bfloat16*>(D(cur)), st);
+    if (rc) return rc;
+    rc = lcn_tc_wgrad_last(m, lay, Ain, dout16, dwl, st);
+    if (rc) return rc;
+    LCN_CHECK_CUDA(cudaMemcpy2DAsync(graw + m->L[last].w_off, 51 * sizeof(float), dwl, 64 * sizeof(float),
+                                     51 * sizeof(float), P, cudaMemcpyDeviceToDevice, st));
+  } else {
     const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, m->n_bn - 1));
     k_last_layer_bwd<T><<<dim3((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256), 256, 0, st>>>(
         Ain, dout, reinterpret_cast<const float*>(ws + lay.off_wm_last), D(cur), graw + m->L[last].w_off,
         graw + m->L[last].b_off, P, rows_blk);
     LCN_CHECK_LAUNCH();
   }
-  unsigned eg = (unsigned)(lay.rows_pad / 16);
-  size_t red_smem = (size_t)(P / 4) * 8 * sizeof(float);
+  const int ewy = (P / 4) * 2 <= EW_MAXT ? 2 : 1;
+  unsigned eg = (unsigned)(lay.rows_pad / (4 * ewy));
+  size_t red_smem = (size_t)ewy * (P / 4) * 8 * sizeof(float);
   PairTable pt = make_pairs(m);
   for (int l = m->n_bn - 1; l >= 0; --l) {
     const LayerInfo& L = m->L[l];
     const T* Z = reinterpret_cast<const T*>(z_buf(ws, lay, l));
     const float* stat = bn_stat(ws, lay, m, l);
     float* sums = reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)l * F * 2;
-    k_bn_bwd_reduce<T><<<eg, P / 4, red_smem, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, P,
+    k_bn_bwd_reduce<T><<<eg, dim3(P / 4, ewy), red_smem, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, P,
                                                     F, lay.bn_group, rate, seed, step, l);
-    k_bn_bwd_apply<T><<<eg, P / 4, 0, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, dZ,
+    k_bn_bwd_apply<T><<<eg, dim3(P / 4, ewy), 0, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, dZ,
                                             graw + L.b_off, graw + L.gamma_off, graw + L.beta_off, P, F, lay.bn_group,
                                             rate, seed, step, l);
     LCN_CHECK_LAUNCH();
+    if (l == 0 && tc) {
+      float* dwf = reinterpret_cast<float*>(ws + lay.off_dw_first);
+      int rc = lcn_tc_wgrad_first(m, lay, reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_x16),
+                                  reinterpret_cast<const __nv_bfloat16*>(dZ), dwf, st);
+      if (rc) return rc;
+      LCN_CHECK_CUDA(cudaMemcpyAsync(graw + L.w_off, dwf, sizeof(float) * L.Kin * P, cudaMemcpyDeviceToDevice, st));
+      break;
+    }
     if (l == 0) {
       dim3 grid((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256);
       if (m->d.in_F == 2) k_first_wgrad<T, 2><<<grid, 256, 0, st>>>(x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
