@@ -154,12 +154,18 @@ int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int3
  * ground truth, d_box [n,4], d_cam [n,4] = (fx, fy, cx, cy), d_root_depth [n], d_action [n] int32 or NULL.
  * tools.image_to_camera_frame (tools/tools.py:183-194) -> optional tools.align_to_gt / procrustes
  * (:96-181,197-202; reflections allowed) -> per-joint L2 error.
- * d_err [n,17] per-joint errors in mm, may be NULL.  d_sums: double [n_actions+1][17+1+1]:
+ * flags: LCN_EVAL_PROTOCOL2 = Procrustes-align before measuring; LCN_EVAL_CAMERA_FRAME = d_pred is already
+ * in the camera frame (skips the un-projection; box / cam / root_depth may be NULL) -- this is what
+ * tools.align_to_gt(pose, pose_gt) needs when called on its own.
+ * d_err [n,17] per-joint errors in mm, may be NULL.  d_pose_out [n,17,3], may be NULL: the transformed
+ * prediction (camera frame; Procrustes-aligned when PROTOCOL2).  d_sums: double [n_actions+1][17+1+1]:
  * per action (row n_actions = all) 17 per-joint error sums, pose count, count(err < 50 mm);
  * accumulated (caller zeroes).  n_actions may be 0. */
+#define LCN_EVAL_PROTOCOL2 1
+#define LCN_EVAL_CAMERA_FRAME 2
 int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const float* d_box, const float* d_cam,
                    const float* d_root_depth, const int32_t* d_action, int32_t n_actions, int64_t n,
-                   int protocol2, float* d_err, double* d_sums, void* stream);
+                   int flags, float* d_err, float* d_pose_out, double* d_sums, void* stream);
 
 /* (f) DataReader.denormalize arithmetic, tools/data.py:471-472, fused in front of the evaluator:
  * d_pose [n,17,3] in place; d_res [n,2] = (res_w, res_h). */

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "liblcn_b200.so")
 J = 17
 LCN_PATH_FP32, LCN_PATH_BF16 = 0, 1
 LCN_MASK_LOCALLY_CONNECTED, LCN_MASK_CONSTANT = 0, 1
+LCN_EVAL_PROTOCOL2, LCN_EVAL_CAMERA_FRAME = 1, 2
 
 
 class LcnError(RuntimeError):
@@ -41,7 +42,7 @@ PROTOTYPES = {
     "lcn_layer_gemm": (C.c_int, [_vp, _vp, _vp, _sz, _i64, _i32, C.c_int, C.c_int, _vp]),
     "lcn_model_read_tensor": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _i64, _i32, _vp, _vp]),
     "lcn_dropout_mask": (C.c_int, [_u64, _u64, C.c_int, _i64, _i32, _f, _vp, _vp]),
-    "lcn_eval_mpjpe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp]),
+    "lcn_eval_mpjpe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp, _vp]),
     "lcn_denormalize": (C.c_int, [_vp, _vp, _i64, _vp]),
 }
 

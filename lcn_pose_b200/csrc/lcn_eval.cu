@@ -47,8 +47,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
                                                        const float* __restrict__ box, const float* __restrict__ cam,
                                                        const float* __restrict__ root_depth,
                                                        const int32_t* __restrict__ action, int n_actions, int64_t n,
-                                                       int protocol2, float* __restrict__ err_out,
-                                                       double* __restrict__ sums) {
+                                                       int flags, float* __restrict__ err_out,
+                                                       float* __restrict__ pose_out, double* __restrict__ sums) {
+  const int protocol2 = flags & 1, camera_frame = flags & 2;
   extern __shared__ __align__(16) float smem[];
   // per warp: pred[32*51], gt[32*51]; then per block: action sums (double)
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,9 +92,13 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
     int act = -1;
     if (active) {
       int64_t ip = p0 + lane;
-      float4 bx = *reinterpret_cast<const float4*>(box + ip * 4);
-      float4 cm = *reinterpret_cast<const float4*>(cam + ip * 4);   // fx, fy, cx, cy
-      float rd = root_depth[ip];
+      float4 bx = make_float4(0.f, 0.f, 1999.f, 0.f), cm = make_float4(1.f, 1.f, 0.f, 0.f);
+      float rd = 0.f;
+      if (!camera_frame) {
+        bx = *reinterpret_cast<const float4*>(box + ip * 4);
+        cm = *reinterpret_cast<const float4*>(cam + ip * 4);   // fx, fy, cx, cy
+        rd = root_depth[ip];
+      }
       if (action != nullptr) act = action[ip];
       float inv_ratio = 2000.0f / (bx.z - bx.x + 1.0f);
       float ifx = 1.0f / cm.x, ify = 1.0f / cm.y;
@@ -103,10 +108,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
       float pb[3] = {0, 0, 0}, gb[3] = {0, 0, 0};
 #pragma unroll
       for (int j = 0; j < LCN_J; ++j) {
-        float z = mp[j * 3 + 2] * inv_ratio + rd;          // tools.py:187
-        P[j][0] = (mp[j * 3 + 0] - cm.z) * ifx * z;        // tools.py:190,192
-        P[j][1] = (mp[j * 3 + 1] - cm.w) * ify * z;        // tools.py:191,193
-        P[j][2] = z;
+        if (camera_frame) {
+          P[j][0] = mp[j * 3 + 0]; P[j][1] = mp[j * 3 + 1]; P[j][2] = mp[j * 3 + 2];
+        } else {
+          float z = mp[j * 3 + 2] * inv_ratio + rd;          // tools.py:187
+          P[j][0] = (mp[j * 3 + 0] - cm.z) * ifx * z;        // tools.py:190,192
+          P[j][1] = (mp[j * 3 + 1] - cm.w) * ify * z;        // tools.py:191,193
+          P[j][2] = z;
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           G[j][c] = mg[j * 3 + c];
@@ -168,19 +177,28 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
         float sc = nA * tr / nB;
 #pragma unroll
         for (int j = 0; j < LCN_J; ++j) {
-          float d2 = 0.f;
+          float d2 = 0.f, zc[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            float zc = sc * (P[j][0] * R[0][c] + P[j][1] * R[1][c] + P[j][2] * R[2][c]) - G[j][c];
-            d2 = fmaf(zc, zc, d2);
+            zc[c] = sc * (P[j][0] * R[0][c] + P[j][1] * R[1][c] + P[j][2] * R[2][c]) - G[j][c];
+            d2 = fmaf(zc[c], zc[c], d2);
           }
           e[j] = sqrtf(d2);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) P[j][c] = zc[c] + G[j][c] + gb[c];   // aligned pose Z (tools.py:168)
         }
       } else {
 #pragma unroll
         for (int j = 0; j < LCN_J; ++j) {
           float dx = P[j][0] - G[j][0], dy = P[j][1] - G[j][1], dz = P[j][2] - G[j][2];
           e[j] = sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+      }
+      if (pose_out != nullptr) {   // every lane only rewrites its own 51 words of the staging area
+        float* mo = sp + lane * EV_POSE;
+#pragma unroll
+        for (int j = 0; j < LCN_J; ++j) {
+          mo[j * 3 + 0] = P[j][0]; mo[j * 3 + 1] = P[j][1]; mo[j * 3 + 2] = P[j][2];
         }
       }
       int pck = 0;
@@ -198,6 +216,11 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
         atomicAdd(&row[17], 1.0);
         atomicAdd(&row[18], (double)pck);
       }
+    }
+    if (pose_out != nullptr) {
+      __syncwarp();
+      float* dstp = pose_out + p0 * EV_POSE;
+      for (int v = lane; v < cnt * EV_POSE; v += 32) dstp[v] = sp[v];
     }
     if (err_out != nullptr) {
       __syncwarp();
@@ -240,8 +263,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
 
 extern "C" int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const float* d_box, const float* d_cam,
                               const float* d_root_depth, const int32_t* d_action, int32_t n_actions, int64_t n,
-                              int protocol2, float* d_err, double* d_sums, void* stream) {
-  LCN_REQUIRE(d_pred && d_gt && d_box && d_cam && d_root_depth && d_sums, "null argument");
+                              int flags, float* d_err, float* d_pose_out, double* d_sums, void* stream) {
+  LCN_REQUIRE(d_pred && d_gt && d_sums, "null argument");
+  LCN_REQUIRE((flags & 2) || (d_box && d_cam && d_root_depth), "box / cam / root_depth are required unless LCN_EVAL_CAMERA_FRAME");
   LCN_REQUIRE(n > 0, "n must be positive");
   LCN_REQUIRE(n_actions >= 0 && n_actions <= 64, "n_actions=%d outside 0..64", n_actions);
   LCN_REQUIRE((((uintptr_t)d_pred | (uintptr_t)d_gt | (uintptr_t)d_box | (uintptr_t)d_cam) & 15) == 0,
@@ -259,7 +283,7 @@ extern "C" int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const floa
   int64_t blocks = (chunks + EV_WARPS - 1) / EV_WARPS;
   int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * 4);
   k_eval<<<grid, EV_WARPS * 32, smem, (cudaStream_t)stream>>>(d_pred, d_gt, d_box, d_cam, d_root_depth, d_action,
-                                                            n_actions, n, protocol2, d_err, d_sums);
+                                                            n_actions, n, flags, d_err, d_pose_out, d_sums);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }

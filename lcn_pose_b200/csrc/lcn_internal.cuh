@@ -107,6 +107,8 @@ struct WsLayout {
   size_t off_a, a_stride; int n_a;   // A buffers
   size_t off_d, d_stride; int n_d;   // gradient ping-pong buffers (training)
   size_t off_dz;                     // dZ buffer (training)
+  size_t off_dbpart;                 // float[n_bn][2*SMs][P] per-block bias-gradient partial rows (training)
+  size_t off_keep;                   // uint8[n_bn][rows_pad][P/8] dropout keep bits (training)
   size_t total;
 };
 

@@ -6,6 +6,7 @@
 // Reference semantics implemented here (paths relative to the reference root):
 //   network/models_att.py:534-586 (mask, mask_weights), :588-612 (BN), :630-775 (layers, head),
 //   :352-421 (loss, Adam); SURVEY.md section 9 lists the TF behaviours relied on.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -126,7 +127,7 @@ __global__ void k_pack_edge(const float* __restrict__ w, int Fi, int Fo, const L
 __global__ void k_pack_mid(const float* __restrict__ params, LinTable lt, PairTable pt, SupportBits sup,
                            const LayerScalars* sc, const float* __restrict__ mask, int F, int FC, int nnz,
                            float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
-                           __nv_bfloat16* __restrict__ wp16b) {
+                           __nv_bfloat16* __restrict__ wp16b, int write32, int write16) {
   int mid = blockIdx.y, l = mid + 1;
   int sb = blockIdx.x;
   int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
@@ -150,10 +151,12 @@ __global__ void k_pack_mid(const float* __restrict__ params, LinTable lt, PairTa
   for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
     int fi = e >> 6, fo = e & 63;
     float v = w[(size_t)(i * F + hi * 64 + fi) * P + j * F + ho * 64 + fo] * scale;
-    d32[e] = v;
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    df[fo * 64 + ((((fi >> 3) ^ (fo & 7)) << 3) | (fi & 7))] = h;   // row n=fo, k=fi
-    db[fi * 64 + ((((fo >> 3) ^ (fi & 7)) << 3) | (fo & 7))] = h;   // row n=fi, k=fo
+    if (write32) d32[e] = v;
+    if (write16) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      df[fo * 64 + ((((fi >> 3) ^ (fo & 7)) << 3) | (fi & 7))] = h;   // row n=fo, k=fi
+      db[fi * 64 + ((((fo >> 3) ^ (fi & 7)) << 3) | (fo & 7))] = h;   // row n=fi, k=fo
+    }
   }
 }
 
@@ -196,11 +199,12 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
   int n_mid = m->n_lin - 2;
+  const bool use_tc = m->d.path == LCN_PATH_BF16 && lcn_tc_enabled();
   if (n_mid > 0) {
     k_pack_mid<<<dim3(m->nnz * m->FC * m->FC, n_mid), 256, 0, st>>>(
         params, lt, make_pairs(m), m->sup, sc, mask, m->d.F, m->FC, m->nnz,
         reinterpret_cast<float*>(ws + lay.off_wp32), reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f),
-        reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b));
+        reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b), use_tc ? 0 : 1, use_tc ? 1 : 0);
   }
   LCN_CHECK_LAUNCH();
   return LCN_OK;
@@ -466,63 +470,107 @@ __global__ void __launch_bounds__(256) k_bn_finalize(const float* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
-// BN apply + LeakyReLU(0.2) + dropout + residual (models_att.py:664-673,704).
-// grid rows_pad/16, block (P/8, 4): thread = 8 consecutive columns (one 16-byte bf16 chunk), 4 rows with
-// all loads in flight before the first use (HBM/L2-bound elementwise pass).
+// BN apply + LeakyReLU(0.2) + dropout + residual (models_att.py:664-673,704).  HBM/L2-bound elementwise pass.
+// Persistent: grid = 2 x SMs blocks of (P/8, Y) threads, each block owns a contiguous range of rows; a thread
+// owns 8 consecutive columns (16 B of bf16) and walks the rows with a register double buffer (the loads of
+// row r+Y are in flight while row r is processed).  Per-channel scale/shift live in shared memory and are
+// reloaded when the row range crosses into the next BatchNorm group.  When dropout is active the keep
+// decisions are also written as one byte per (row, 8 columns) so that backward does not redraw Philox.
 // ------------------------------------------------------------------------------------------------
-#define EW_MAXT 544   // (P/4) x EW_Y threads: (272,2) for F=64, (544,1) for F=128
+#define EW_MAXT 288   // (P/8) x Y threads: (136,2) for F=64, (272,1) for F=128
 template <typename T>
-__global__ void __launch_bounds__(EW_MAXT) k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat, const float* __restrict__ gamma,
-                         const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ Aout, int P, int F,
-                         int bn_group, int gstride, float rate, uint64_t seed, uint64_t step, int layer) {
-  int c4 = threadIdx.x * 4;
-  int f0 = c4 % F;
-  int64_t pr0 = (int64_t)blockIdx.x * (4 * blockDim.y);
-  int g = (int)(pr0 / gstride);
-  float sc[4], sh[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float mean = stat[((size_t)g * F + f0 + q) * 2], rstd = stat[((size_t)g * F + f0 + q) * 2 + 1];
-    sc[q] = gamma[f0 + q] * rstd;
-    sh[q] = beta[f0 + q] - mean * sc[q];
-  }
+__global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act(const T* __restrict__ Z, const float* __restrict__ stat,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const T* __restrict__ res, T* __restrict__ Aout,
+                                                       uint8_t* __restrict__ keepbits, int P, int F, int rows_pad,
+                                                       int bn_group, int gstride, float rate, uint64_t seed,
+                                                       uint64_t step, int layer) {
+  __shared__ __align__(16) float s_sc[256], s_sh[256];
+  const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  // contiguous row range of this block (multiple of Y rows)
+  int per = ((rows_pad / Y + gridDim.x - 1) / gridDim.x) * Y;
+  int r_begin = blockIdx.x * per, r_end = min(r_begin + per, rows_pad);
+  if (r_begin >= r_end) return;
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  float z[4][4], rv[4][4];
-  size_t o[4];
-  bool valid[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
-    o[u] = lcn_off<T>(pr, c4, P);
-    valid[u] = (int)(pr % gstride) < bn_group;
-    if (valid[u]) {
-      lcn_ldv4(Z, o[u], z[u]);
-      if (res != nullptr) lcn_ldv4(res, o[u], rv[u]);
+  float sc[8], sh[8];
+  int cur_g = -1;
+  float zc[8], rc[8], zn[8], rn[8];
+  int r = r_begin + threadIdx.y;
+  bool vc = false, vn = false;
+  size_t oc = 0, on = 0;
+  if (r < r_end) {
+    oc = lcn_off<T>(r, c8, P);
+    vc = (r % gstride) < bn_group;
+    if (vc) {
+      lcn_ld8(Z, oc, zc);
+      if (res != nullptr) lcn_ld8(res, oc, rc);
     }
   }
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    float y[4];
-    if (!valid[u]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) y[q] = 0.f;
-    } else {
-      int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
-      uint32_t rb[4];
-      if (rate > 0.f) {
-        uint64_t i4 = ((uint64_t)pr * P + c4) >> 2;
-        lcn_philox4(seed, step, (uint32_t)layer, i4, rb);
+  // r_end - r_begin is a multiple of Y, so every thread of the block runs the same number of iterations
+  for (; r < r_end; r += Y) {
+    int g = (r - (int)threadIdx.y) / gstride;     // block-uniform (Y divides gstride)
+    if (g != cur_g) {
+      __syncthreads();
+      if (tid < F) {
+        float mean = stat[((size_t)g * F + tid) * 2], rstd = stat[((size_t)g * F + tid) * 2 + 1];
+        float a = gamma[tid] * rstd;
+        s_sc[tid] = a;
+        s_sh[tid] = beta[tid] - mean * a;
       }
+      __syncthreads();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v = fmaf(z[u][q], sc[q], sh[q]);
-        v = v > 0.f ? v : LCN_LRELU * v;
-        if (rate > 0.f) v = lcn_keep(rb[q], rate) ? v * inv_keep : 0.f;
-        if (res != nullptr) v += rv[u][q];
-        y[q] = v;
+      for (int q = 0; q < 8; ++q) {
+        sc[q] = s_sc[f0 + q];
+        sh[q] = s_sh[f0 + q];
+      }
+      cur_g = g;
+    }
+    int rn_row = r + Y;
+    vn = false;
+    if (rn_row < r_end) {                          // prefetch the next row of this thread
+      on = lcn_off<T>(rn_row, c8, P);
+      vn = (rn_row % gstride) < bn_group;
+      if (vn) {
+        lcn_ld8(Z, on, zn);
+        if (res != nullptr) lcn_ld8(res, on, rn);
       }
     }
-    lcn_stv4(Aout, o[u], y);
+    if (r < r_end) {
+      float y[8];
+      uint32_t kb = 0xffu;
+      if (!vc) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[q] = 0.f;
+      } else {
+        if (rate > 0.f) {
+          uint32_t rb[8];
+          uint64_t i4 = ((uint64_t)r * P + c8) >> 2;
+          lcn_philox4(seed, step, (uint32_t)layer, i4, rb);
+          lcn_philox4(seed, step, (uint32_t)layer, i4 + 1, rb + 4);
+          kb = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) kb |= (lcn_keep(rb[q], rate) ? 1u : 0u) << q;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v = fmaf(zc[q], sc[q], sh[q]);
+          v = v > 0.f ? v : LCN_LRELU * v;
+          v = ((kb >> q) & 1u) ? v * inv_keep : 0.f;
+          if (res != nullptr) v += rc[q];
+          y[q] = v;
+        }
+      }
+      lcn_st8(Aout, oc, y);
+      if (keepbits != nullptr && rate > 0.f) keepbits[(size_t)r * (P >> 3) + threadIdx.x] = (uint8_t)kb;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      zc[q] = zn[q];
+      rc[q] = rn[q];
+    }
+    vc = vn;
+    oc = on;
   }
 }
 
@@ -679,154 +727,211 @@ __global__ void __launch_bounds__(256) k_last_layer_bwd(const T* __restrict__ A,
 //   dy   = dOut * keep/(1-rate) * (ybn > 0 ? 1 : 0.2)
 //   sums = (sum dy, sum dy*xhat) per channel        [k_bn_bwd_reduce]
 //   dZ   = gamma*rstd*(dy - s1/n - xhat*s2/n)       [k_bn_bwd_apply], db = sum_rows dZ
-// grid rows_pad/16, block (P/8, 4); thread = 8 columns x 4 rows, loads issued up front.
+// Persistent like k_bn_act: grid = 2 x SMs blocks of (P/8, Y) threads, strided rows, register double buffer;
+// keep decisions come from the bits written by k_bn_act; one block-level reduction, then one atomic per
+// channel (reduce) / per column (apply) per block.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void bn_bwd_dy4(const float z[4], const float d[4], uint64_t olog, const float* sc,
-                                           const float* sh, const float* mean, const float* rstd, float rate,
-                                           float inv_keep, uint64_t seed, uint64_t step, int layer, float dy[4],
-                                           float xh[4]) {
-  uint32_t rb[4];
-  if (rate > 0.f) {
-    lcn_philox4(seed, step, (uint32_t)layer, olog >> 2, rb);
-  }
+struct BnConsts {
+  float sc[8], sh[8], rstd[8], mr[8];   // scale, shift, rstd, mean*rstd for the thread's 8 channels
+};
+__device__ __forceinline__ void bn_bwd_dy8(const float z[8], const float d[8], uint32_t kb, const BnConsts& k,
+                                           float inv_keep, float dy[8], float xh[8]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float ybn = fmaf(z[q], sc[q], sh[q]);
-    float v = d[q];
-    if (rate > 0.f) v = lcn_keep(rb[q], rate) ? v * inv_keep : 0.f;
+  for (int q = 0; q < 8; ++q) {
+    float ybn = fmaf(z[q], k.sc[q], k.sh[q]);
+    float v = ((kb >> q) & 1u) ? d[q] * inv_keep : 0.f;
     dy[q] = ybn > 0.f ? v : LCN_LRELU * v;
-    xh[q] = (z[q] - mean[q]) * rstd[q];
+    xh[q] = fmaf(z[q], k.rstd[q], -k.mr[q]);
   }
 }
-
-template <typename T>
-__global__ void __launch_bounds__(EW_MAXT) k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                float* __restrict__ sums, int P, int F, int bn_group, float rate, uint64_t seed,
-                                uint64_t step, int layer) {
-  extern __shared__ __align__(16) float red[];   // [blockDim.y][P/4][8]
-  int c4 = threadIdx.x * 4, f0 = c4 % F;
-  float sc[4], sh[4], mean[4], rstd[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    mean[q] = stat[(f0 + q) * 2];
-    rstd[q] = stat[(f0 + q) * 2 + 1];
-    sc[q] = gamma[f0 + q] * rstd[q];
-    sh[q] = beta[f0 + q] - mean[q] * sc[q];
-  }
-  float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  float s1[4], s2[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) s1[q] = s2[q] = 0.f;
-  int64_t pr0 = (int64_t)blockIdx.x * (4 * blockDim.y);
-  float z[4][4], d[4][4];
-  bool valid[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
-    valid[u] = pr < bn_group;
-    if (valid[u]) {
-      size_t o = lcn_off<T>(pr, c4, P);
-      lcn_ldv4(Z, o, z[u]);
-      lcn_ldv4(dOut, o, d[u]);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (!valid[u]) continue;
-    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
-    float dy[4], xh[4];
-    bn_bwd_dy4<T>(z[u], d[u], (uint64_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      s1[q] += dy[q];
-      s2[q] = fmaf(dy[q], xh[q], s2[q]);
-    }
-  }
-  int nt = blockDim.x;
-  float* mine = red + ((size_t)threadIdx.y * nt + threadIdx.x) * 8;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    mine[q] = s1[q];
-    mine[4 + q] = s2[q];
+__device__ __forceinline__ void bn_load_consts(const float* stat, const float* gamma, const float* beta, int F,
+                                               int f0, float* s_a, float* s_b, float* s_c, float* s_d, BnConsts& k) {
+  int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < F) {
+    float mean = stat[tid * 2], rstd = stat[tid * 2 + 1];
+    float sc = gamma[tid] * rstd;
+    s_a[tid] = sc;
+    s_b[tid] = beta[tid] - mean * sc;
+    s_c[tid] = rstd;
+    s_d[tid] = mean * rstd;
   }
   __syncthreads();
-  int per = F / 4;                               // threads (x) per joint
-  int t = threadIdx.y * nt + threadIdx.x;
-  if (t < per * 8) {                             // one thread per (channel-quad, value)
-    int oct = t / 8, v = t % 8;
-    float a = 0.f;
-    for (int y = 0; y < (int)blockDim.y; ++y)
-      for (int j = 0; j < LCN_J; ++j) a += red[((size_t)y * nt + oct + j * per) * 8 + v];
-    int f = oct * 4 + (v & 3);
-    atomicAdd(&sums[f * 2 + (v >> 2)], a);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    k.sc[q] = s_a[f0 + q];
+    k.sh[q] = s_b[f0 + q];
+    k.rstd[q] = s_c[f0 + q];
+    k.mr[q] = s_d[f0 + q];
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(EW_MAXT) k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__ Z, const float* __restrict__ stat,
-                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                               const float* __restrict__ sums, T* __restrict__ dZ, float* __restrict__ db,
-                               float* __restrict__ dgamma, float* __restrict__ dbeta, int P, int F, int bn_group,
-                               float rate, uint64_t seed, uint64_t step, int layer) {
-  int c4 = threadIdx.x * 4, f0 = c4 % F;
-  float sc[4], sh[4], mean[4], rstd[4], m1[4], m2[4];
+__global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_reduce(const T* __restrict__ dOut, const T* __restrict__ Z,
+                                                              const uint8_t* __restrict__ keepbits,
+                                                              const float* __restrict__ stat,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ sums,
+                                                              int P, int F, int bn_group, float rate) {
+  extern __shared__ __align__(16) float red[];   // [Y][P/8][16]
+  __shared__ __align__(16) float s_a[256], s_b[256], s_c[256], s_d[256];
+  const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
+  BnConsts k;
+  bn_load_consts(stat, gamma, beta, F, f0, s_a, s_b, s_c, s_d, k);
+  float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s1[q] = s2[q] = 0.f;
+  const int stride = gridDim.x * Y;
+  int r = blockIdx.x * Y + threadIdx.y;
+  float zc[8], dc[8], zn[8], dn[8];
+  uint32_t kc = 0xffu, kn = 0xffu;
+  if (r < bn_group) {
+    size_t o = lcn_off<T>(r, c8, P);
+    lcn_ld8(Z, o, zc);
+    lcn_ld8(dOut, o, dc);
+    if (rate > 0.f) kc = keepbits[(size_t)r * (P >> 3) + threadIdx.x];
+  }
+  for (; r < bn_group; r += stride) {
+    int rn = r + stride;
+    if (rn < bn_group) {
+      size_t o = lcn_off<T>(rn, c8, P);
+      lcn_ld8(Z, o, zn);
+      lcn_ld8(dOut, o, dn);
+      if (rate > 0.f) kn = keepbits[(size_t)rn * (P >> 3) + threadIdx.x];
+    }
+    float dy[8], xh[8];
+    bn_bwd_dy8(zc, dc, kc, k, inv_keep, dy, xh);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s1[q] += dy[q];
+      s2[q] = fmaf(dy[q], xh[q], s2[q]);
+      zc[q] = zn[q];
+      dc[q] = dn[q];
+    }
+    kc = kn;
+  }
+  int nt = blockDim.x;
+  float* mine = red + ((size_t)threadIdx.y * nt + threadIdx.x) * 16;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    mine[q] = s1[q];
+    mine[8 + q] = s2[q];
+  }
+  __syncthreads();
+  int per = F / 8;                               // threads (x) per joint
+  int t = threadIdx.y * nt + threadIdx.x;
+  if (t < per * 16) {                            // one thread per (channel octet, value)
+    int oct = t / 16, v = t % 16;
+    float a = 0.f;
+    for (int y = 0; y < Y; ++y)
+      for (int j = 0; j < LCN_J; ++j) a += red[((size_t)y * nt + oct + j * per) * 16 + v];
+    int f = oct * 8 + (v & 7);
+    atomicAdd(&sums[f * 2 + (v >> 3)], a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_apply(const T* __restrict__ dOut, const T* __restrict__ Z,
+                                                             const uint8_t* __restrict__ keepbits,
+                                                             const float* __restrict__ stat,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ sums, T* __restrict__ dZ,
+                                                             float* __restrict__ dbpart, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int P, int F, int rows_pad,
+                                                             int bn_group, float rate) {
+  extern __shared__ __align__(16) float red[];   // [Y-1][P] column sums of the other row-threads
+  __shared__ __align__(16) float s_a[256], s_b[256], s_c[256], s_d[256];
+  const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
+  BnConsts k;
+  bn_load_consts(stat, gamma, beta, F, f0, s_a, s_b, s_c, s_d, k);
+  float m1[8], m2[8];
   float inv_n = 1.f / ((float)bn_group * (float)LCN_J);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    mean[q] = stat[(f0 + q) * 2];
-    rstd[q] = stat[(f0 + q) * 2 + 1];
-    sc[q] = gamma[f0 + q] * rstd[q];
-    sh[q] = beta[f0 + q] - mean[q] * sc[q];
+  for (int q = 0; q < 8; ++q) {
     m1[q] = sums[(f0 + q) * 2] * inv_n;
     m2[q] = sums[(f0 + q) * 2 + 1] * inv_n;
   }
-  if (blockIdx.x == 0 && threadIdx.y == 0 && (int)threadIdx.x < F / 4) {
+  if (blockIdx.x == 0 && threadIdx.y == 0 && (int)threadIdx.x < F / 8) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       dbeta[f0 + q] = sums[(f0 + q) * 2];
       dgamma[f0 + q] = sums[(f0 + q) * 2 + 1];
     }
   }
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  float bsum[4];
+  float bsum[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) bsum[q] = 0.f;
-  int64_t pr0 = (int64_t)blockIdx.x * (4 * blockDim.y);
-  float z[4][4], d[4][4];
-  size_t o[4];
-  bool valid[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
-    o[u] = lcn_off<T>(pr, c4, P);
-    valid[u] = pr < bn_group;
-    if (valid[u]) {
-      lcn_ldv4(Z, o[u], z[u]);
-      lcn_ldv4(dOut, o[u], d[u]);
-    }
+  for (int q = 0; q < 8; ++q) bsum[q] = 0.f;
+  const int stride = gridDim.x * Y;
+  int r = blockIdx.x * Y + threadIdx.y;
+  float zc[8], dc[8], zn[8], dn[8];
+  uint32_t kc = 0xffu, kn = 0xffu;
+  if (r < bn_group) {
+    size_t o = lcn_off<T>(r, c8, P);
+    lcn_ld8(Z, o, zc);
+    lcn_ld8(dOut, o, dc);
+    if (rate > 0.f) kc = keepbits[(size_t)r * (P >> 3) + threadIdx.x];
   }
+  for (; r < rows_pad; r += stride) {
+    int rn = r + stride;
+    if (rn < bn_group) {
+      size_t o = lcn_off<T>(rn, c8, P);
+      lcn_ld8(Z, o, zn);
+      lcn_ld8(dOut, o, dn);
+      if (rate > 0.f) kn = keepbits[(size_t)rn * (P >> 3) + threadIdx.x];
+    }
+    float dz[8];
+    if (r >= bn_group) {                          // tile padding rows: dZ must be zero (wgrad reduces over rows)
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    float dz[4];
-    if (!valid[u]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dz[q] = 0.f;
+      for (int q = 0; q < 8; ++q) dz[q] = 0.f;
     } else {
-      int64_t pr = pr0 + threadIdx.y + blockDim.y * u;
-      float dy[4], xh[4];
-      bn_bwd_dy4<T>(z[u], d[u], (uint64_t)pr * P + c4, sc, sh, mean, rstd, rate, inv_keep, seed, step, layer, dy, xh);
+      float dy[8], xh[8];
+      bn_bwd_dy8(zc, dc, kc, k, inv_keep, dy, xh);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dz[q] = sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
+      for (int q = 0; q < 8; ++q) {
+        dz[q] = k.sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
         bsum[q] += dz[q];
       }
     }
-    lcn_stv4(dZ, o[u], dz);
-  }
+    lcn_st8(dZ, lcn_off<T>(r, c8, P), dz);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) atomicAdd(&db[c4 + q], bsum[q]);
+    for (int q = 0; q < 8; ++q) {
+      zc[q] = zn[q];
+      dc[q] = dn[q];
+    }
+    kc = kn;
+  }
+  // db: combine the row-threads of a column octet in shared memory; one partial row per block (no atomics:
+  // 2*SMs blocks adding into the same 17F addresses serialise in L2 -- measured 19 us per layer)
+  if (threadIdx.y > 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[(size_t)(threadIdx.y - 1) * P + c8 + q] = bsum[q];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float a = bsum[q];
+      for (int y = 1; y < Y; ++y) a += red[(size_t)(y - 1) * P + c8 + q];
+      dbpart[(size_t)blockIdx.x * P + c8 + q] = a;
+    }
+  }
+}
+
+// db[l][col] = sum over the per-block partial rows written by k_bn_bwd_apply.  grid (ceil(P/64), n_bn), 256 threads
+__global__ void __launch_bounds__(256) k_db_reduce(const float* __restrict__ dbpart, int nblocks, int P,
+                                                   float* __restrict__ graw, LinTable lt_b /* w_off holds b_off */) {
+  __shared__ float sh[4][64];
+  int l = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
+  float a = 0.f;
+  if (c < P) {
+    const float* src = dbpart + (size_t)l * nblocks * P + c;
+    for (int b = sl; b < nblocks; b += 4) a += src[(size_t)b * P];
+  }
+  sh[sl][threadIdx.x & 63] = a;
+  __syncthreads();
+  if (sl == 0 && c < P) graw[lt_b.w_off[l] + c] = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1132,10 +1237,14 @@ static int forward_impl(const FwdArgs& a) {
     float* stat = bn_stat(ws, lay, m, l);
     k_bn_finalize<<<dim3(lay.n_groups, F / 2), 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
     const T* res = L.res_from >= 0 ? reinterpret_cast<const T*>(a_buf(ws, lay, L.res_from)) : nullptr;
-    const int ewy = (P / 4) * 2 <= EW_MAXT ? 2 : 1;
-    k_bn_act<T><<<(unsigned)(lay.rows_pad / (4 * ewy)), dim3(P / 4, ewy), 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off,
-                                                                 res, Aout, P, F, lay.bn_group, lay.gstride,
-                                                                 a.dropout_rate, a.seed, a.step, l);
+    const int ewy = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
+    uint8_t* keepbits = (lay.training && a.dropout_rate > 0.f)
+                            ? reinterpret_cast<uint8_t*>(ws + lay.off_keep) + (size_t)l * lay.rows_pad * (P / 8)
+                            : nullptr;
+    int ew_grid = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
+    k_bn_act<T><<<ew_grid, dim3(P / 8, ewy), 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
+                                                      keepbits, P, F, (int)lay.rows_pad, lay.bn_group, lay.gstride,
+                                                      a.dropout_rate, a.seed, a.step, l);
     LCN_CHECK_LAUNCH();
   }
   int last = m->n_lin - 1;
@@ -1201,20 +1310,21 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
         graw + m->L[last].b_off, P, rows_blk);
     LCN_CHECK_LAUNCH();
   }
-  const int ewy = (P / 4) * 2 <= EW_MAXT ? 2 : 1;
-  unsigned eg = (unsigned)(lay.rows_pad / (4 * ewy));
-  size_t red_smem = (size_t)ewy * (P / 4) * 8 * sizeof(float);
+  const int ewy = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
+  unsigned eg = (unsigned)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
+  size_t red_smem = (size_t)ewy * (P / 8) * 16 * sizeof(float);
   PairTable pt = make_pairs(m);
   for (int l = m->n_bn - 1; l >= 0; --l) {
     const LayerInfo& L = m->L[l];
     const T* Z = reinterpret_cast<const T*>(z_buf(ws, lay, l));
     const float* stat = bn_stat(ws, lay, m, l);
     float* sums = reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)l * F * 2;
-    k_bn_bwd_reduce<T><<<eg, dim3(P / 4, ewy), red_smem, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, P,
-                                                    F, lay.bn_group, rate, seed, step, l);
-    k_bn_bwd_apply<T><<<eg, dim3(P / 4, ewy), 0, st>>>(D(cur), Z, stat, params + L.gamma_off, params + L.beta_off, sums, dZ,
-                                            graw + L.b_off, graw + L.gamma_off, graw + L.beta_off, P, F, lay.bn_group,
-                                            rate, seed, step, l);
+    const uint8_t* keepbits = reinterpret_cast<const uint8_t*>(ws + lay.off_keep) + (size_t)l * lay.rows_pad * (P / 8);
+    k_bn_bwd_reduce<T><<<eg, dim3(P / 8, ewy), red_smem, st>>>(D(cur), Z, keepbits, stat, params + L.gamma_off,
+                                                             params + L.beta_off, sums, P, F, lay.bn_group, rate);
+    k_bn_bwd_apply<T><<<eg, dim3(P / 8, ewy), (size_t)ewy * P * sizeof(float), st>>>(
+        D(cur), Z, keepbits, stat, params + L.gamma_off, params + L.beta_off, sums, dZ,
+        reinterpret_cast<float*>(ws + lay.off_dbpart) + (size_t)l * eg * P, graw + L.gamma_off, graw + L.beta_off, P, F, (int)lay.rows_pad, lay.bn_group, rate);
     LCN_CHECK_LAUNCH();
     if (l == 0 && tc) {
       float* dwf = reinterpret_cast<float*>(ws + lay.off_dw_first);
@@ -1261,6 +1371,14 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LCN_CHECK_LAUNCH();
     (void)keep;
     cur = nxt;
+  }
+  {
+    LinTable lb;
+    lb.n = m->n_bn;
+    for (int l = 0; l < m->n_bn; ++l) lb.w_off[l] = m->L[l].b_off;
+    k_db_reduce<<<dim3((P + 63) / 64, m->n_bn), 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_dbpart),
+                                                              (int)eg, P, graw, lb);
+    LCN_CHECK_LAUNCH();
   }
   return LCN_OK;
 }
@@ -1348,6 +1466,7 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
       LCN_CHECK_CUDA(cudaMemcpyAsync(dst, ws + (layer == 0 ? lay.off_wm_first : lay.off_wm_last),
                                      sizeof(float) * L.Kin * L.Kout, cudaMemcpyDeviceToDevice, st));
     } else {
+      LCN_REQUIRE(!(bf && lcn_tc_enabled()), "the mid-layer weight tap needs the fp32 path (or LCN_DISABLE_TC=1)");
       LCN_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * P * P, st));
       const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(layer - 1) * m->nnz * m->FC * m->FC * 4096;
       k_unpack_mid<<<m->nnz * m->FC * m->FC, 256, 0, st>>>(wp, make_pairs(m), m->nnz, F, m->FC, dst);

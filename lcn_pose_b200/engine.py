@@ -267,19 +267,24 @@ class LcnEngine:
         return preds
 
 
-def eval_mpjpe(pred, gt, box, cam, root_depth, protocol2, action=None, n_actions=0, want_err=True):
-    """Batched evaluate.py:53-61.  All inputs CUDA float32 tensors: pred/gt [n,17,3], box [n,4],
-    cam [n,4]=(fx,fy,cx,cy), root_depth [n]; action int32 [n] or None.
-    Returns (err [n,17] or None, sums float64 [n_actions+1, 19])."""
+def eval_mpjpe(pred, gt, box=None, cam=None, root_depth=None, protocol2=False, action=None, n_actions=0,
+               want_err=True, want_pose=False, camera_frame=False):
+    """Batched evaluate.py:53-61.  CUDA float32 tensors: pred/gt [n,17,3], box [n,4], cam [n,4]=(fx,fy,cx,cy),
+    root_depth [n]; action int32 [n] or None.  camera_frame=True: pred is already in the camera frame.
+    Returns (err [n,17] or None, sums float64 [n_actions+1, 19]) and the transformed poses when want_pose."""
     lib = L.load()
     n = pred.shape[0]
     dev = pred.device
     for t in (pred, gt, box, cam, root_depth):
-        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
     err = torch.empty((n, J), dtype=torch.float32, device=dev) if want_err else None
+    pose = torch.empty((n, J, 3), dtype=torch.float32, device=dev) if want_pose else None
     na = int(n_actions) if action is not None else 0
     sums = torch.zeros((na + 1, 19), dtype=torch.float64, device=dev)
+    flags = (L.LCN_EVAL_PROTOCOL2 if protocol2 else 0) | (L.LCN_EVAL_CAMERA_FRAME if camera_frame else 0)
     L.check(lib.lcn_eval_mpjpe(_ptr(pred), _ptr(gt), _ptr(box), _ptr(cam), _ptr(root_depth), _ptr(action), na, n,
-                               int(bool(protocol2)), _ptr(err), _ptr(sums),
+                               flags, _ptr(err), _ptr(pose), _ptr(sums),
                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    if want_pose:
+        return err, sums, pose
     return err, sums

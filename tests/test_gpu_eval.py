@@ -102,3 +102,32 @@ def test_denormalize_matches_reference_arithmetic():
     d = dev(pose.copy())
     L.check(L.load().lcn_denormalize(d.data_ptr(), dev(res).data_ptr(), n, torch.cuda.current_stream().cuda_stream))
     assert np.abs(d.cpu().numpy() - ref).max() < 1e-3
+
+
+def test_per_pose_api_matches_reference_known_answers(golden):
+    """The reference's per-pose entry points (evaluate.py:54-59) served by the batched kernel with n = 1."""
+    from lcn_pose_b200.tools import tools as T
+    got = T.image_to_camera_frame(np.arange(51, dtype=np.float64).reshape(17, 3) * 3 + 100, box=[200, 150, 800, 750],
+                                  camera={"cx": 512, "cy": 515, "fx": 1145, "fy": 1144}, rootIdx=0, root_depth=5000)
+    assert got.dtype == np.float64 and np.abs(got - golden["ka_i2c"]).max() < 2e-2     # values ~5e3 mm in fp32
+    gt = np.arange(51, dtype=np.float64).reshape(17, 3) ** 1.5
+    pred = gt[:, ::-1] * 0.9 + np.sin(np.arange(51)).reshape(17, 3) * 7
+    z = T.align_to_gt(pose=pred, pose_gt=gt)
+    assert np.abs(z - golden["ka_proc_Z"]).max() < 1e-2
+    assert abs(np.sqrt(((z - gt) ** 2).sum(1)).mean() - 9.424886756111) < 1e-2      # SURVEY section 4
+    g = golden
+    for i in (0, 5, 17):
+        al = T.align_to_gt(g["ev_camframe"][i], g["ev_gt"][i])
+        assert np.abs(al - g["ev_aligned"][i]).max() < 0.05
+
+
+def test_evaluate_batch_summary(golden):
+    from lcn_pose_b200.tools import tools as T
+    g = golden
+    n = len(g["ev_pred"])
+    normal = np.array([i % 16 != 5 for i in range(n)])
+    r = T.evaluate_batch(g["ev_pred"][normal], g["ev_gt"][normal], g["ev_box"][normal], g["ev_cam"][normal],
+                         g["ev_root_depth"][normal], protocol2=True)
+    fin, pck = O.eval_summary_joint(g["ev_err_p2"][normal])
+    assert np.abs(r["per_joint"] - np.array(fin[:17])).max() < TOL_MM
+    assert abs(r["mpjpe"] - fin[17]) < TOL_MM and abs(r["pck"] - pck[0]) < 0.5
