@@ -124,17 +124,30 @@ __global__ void k_pack_edge(const float* __restrict__ w, int Fi, int Fo, const L
 //   wp32 : [mid][pair][hi][ho][fi][fo] fp32                (CUDA-core GEMMs)
 //   wp16f: bf16, UMMA K-major SWIZZLE_128B image of B[n=fo][k=fi], input-chunk-major order
 //   wp16b: bf16, same for the transposed operand B[n=fi][k=fo], output-chunk-major order
-__global__ void k_pack_mid(const float* __restrict__ params, LinTable lt, PairTable pt, SupportBits sup,
-                           const LayerScalars* sc, const float* __restrict__ mask, int F, int FC, int nnz,
-                           float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
-                           __nv_bfloat16* __restrict__ wp16b, int write32, int write16) {
+__global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ params, LinTable lt, PairTable pt,
+                                                  SupportBits sup, const LayerScalars* sc,
+                                                  const float* __restrict__ mask, int F, int FC, int nnz,
+                                                  float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
+                                                  __nv_bfloat16* __restrict__ wp16b, int write32, int write16) {
+  __shared__ float tile[64][65];     // tile[fi][fo], scaled
   int mid = blockIdx.y, l = mid + 1;
   int sb = blockIdx.x;
   int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
   int i = pt.pi[p], j = pt.pj[p];
   int P = LCN_J * F;
   float scale = sc[l].inv_norm * mask[i * LCN_J + j];
-  const float* w = params + lt.w_off[l];
+  const float* w = params + lt.w_off[l] + (size_t)(i * F + hi * 64) * P + j * F + ho * 64;
+  size_t mid_sb = (size_t)nnz * FC * FC;
+  float* d32 = wp32 + ((size_t)mid * mid_sb + sb) * 4096;
+  for (int f4 = threadIdx.x; f4 < 1024; f4 += 256) {     // coalesced 16-byte loads of the 64x64 block
+    int fi = f4 >> 4, c4 = (f4 & 15) * 4;
+    float4 v = *reinterpret_cast<const float4*>(w + (size_t)fi * P + c4);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    tile[fi][c4] = v.x; tile[fi][c4 + 1] = v.y; tile[fi][c4 + 2] = v.z; tile[fi][c4 + 3] = v.w;
+    if (write32) *reinterpret_cast<float4*>(d32 + fi * 64 + c4) = v;
+  }
+  if (!write16) return;
+  __syncthreads();
   // destination sub-block slots
   int base_i = 0, base_j = 0;
   for (int q = 0; q < i; ++q) base_i += __popc(sup.row[q]);
@@ -144,19 +157,18 @@ __global__ void k_pack_mid(const float* __restrict__ params, LinTable lt, PairTa
   int cnt_out = __popc(sup.row[i]), cnt_in = __popc(sup.col[j]);
   size_t slot_f = (size_t)FC * FC * base_i + (size_t)hi * (cnt_out * FC) + rank_out * FC + ho;
   size_t slot_b = (size_t)FC * FC * base_j + (size_t)ho * (cnt_in * FC) + rank_in * FC + hi;
-  size_t mid_sb = (size_t)nnz * FC * FC;
-  float* d32 = wp32 + ((size_t)mid * mid_sb + sb) * 4096;
-  __nv_bfloat16* df = wp16f + ((size_t)mid * mid_sb + slot_f) * 4096;
-  __nv_bfloat16* db = wp16b + ((size_t)mid * mid_sb + slot_b) * 4096;
-  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
-    int fi = e >> 6, fo = e & 63;
-    float v = w[(size_t)(i * F + hi * 64 + fi) * P + j * F + ho * 64 + fo] * scale;
-    if (write32) d32[e] = v;
-    if (write16) {
-      __nv_bfloat16 h = __float2bfloat16_rn(v);
-      df[fo * 64 + ((((fi >> 3) ^ (fo & 7)) << 3) | (fi & 7))] = h;   // row n=fo, k=fi
-      db[fi * 64 + ((((fo >> 3) ^ (fi & 7)) << 3) | (fo & 7))] = h;   // row n=fi, k=fo
+  uint4* df = reinterpret_cast<uint4*>(wp16f + ((size_t)mid * mid_sb + slot_f) * 4096);
+  uint4* db = reinterpret_cast<uint4*>(wp16b + ((size_t)mid * mid_sb + slot_b) * 4096);
+  for (int e = threadIdx.x; e < 512; e += 256) {          // one 16-byte chunk (8 bf16) per store
+    int n = e >> 3, kc = e & 7;
+    __nv_bfloat162 hf[4], hb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hf[q] = __floats2bfloat162_rn(tile[kc * 8 + 2 * q][n], tile[kc * 8 + 2 * q + 1][n]);   // row n=fo, k=fi
+      hb[q] = __floats2bfloat162_rn(tile[n][kc * 8 + 2 * q], tile[n][kc * 8 + 2 * q + 1]);   // row n=fi, k=fo
     }
+    df[n * 8 + (kc ^ (n & 7))] = *reinterpret_cast<uint4*>(hf);
+    db[n * 8 + (kc ^ (n & 7))] = *reinterpret_cast<uint4*>(hb);
   }
 }
 
@@ -1100,33 +1112,67 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
     inv = sc[l].inv_norm; coef = sc[l].coef;
   }
   double nrm = 0.0;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
-    int64_t o = sg.off + e;
-    float w = params[o];
-    float g;
-    if (sg.kind == SEG_W) {
-      int r = (int)(e / Kout), c = (int)(e - (int64_t)r * Kout);
-      int i = r / Fi, j = c / Fo;
-      g = -coef * w;
-      if ((sup.row[i] >> j) & 1u) g = fmaf(graw[o], mask[i * LCN_J + j] * inv, g);
-      g = fmaf(reg, w, g);
-    } else if (sg.kind == SEG_B) {
-      g = fmaf(reg, w, graw[o]);
-    } else if (sg.kind == SEG_MASK) {
-      g = maskgrad[e];
-    } else {
-      g = graw[o];
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  if (sg.kind == SEG_W && (Fo & 3) == 0) {
+    // fast path: 4 consecutive elements share the row and the joint pair; 28 B/parameter of HBM traffic
+    for (int64_t e = e0 + 4 * threadIdx.x; e < e1; e += 1024) {
+      int64_t o = sg.off + e;
+      uint32_t r = (uint32_t)e / (uint32_t)Kout, c = (uint32_t)e - r * (uint32_t)Kout;
+      uint32_t i = r / (uint32_t)Fi, j = c / (uint32_t)Fo;
+      float4 w4 = *reinterpret_cast<const float4*>(params + o);
+      float w[4] = {w4.x, w4.y, w4.z, w4.w}, g[4];
+      bool on = (sup.row[i] >> j) & 1u;
+      float ms = on ? mask[i * LCN_J + j] * inv : 0.f;
+      float4 gr = on ? *reinterpret_cast<const float4*>(graw + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float grr[4] = {gr.x, gr.y, gr.z, gr.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] = fmaf(reg, w[q], fmaf(grr[q], ms, -coef * w[q]));
+      if (WRITE_G) {
+        *reinterpret_cast<float4*>(gout + o) = make_float4(g[0], g[1], g[2], g[3]);
+      } else {
+        float4 m4 = *reinterpret_cast<const float4*>(mm + o), v4 = *reinterpret_cast<const float4*>(vv + o);
+        float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          m[q] = b1 * m[q] + omb1 * g[q];
+          v[q] = b2 * v[q] + omb2 * g[q] * g[q];
+          w[q] -= lr_t * m[q] / (sqrtf(v[q]) + eps);
+          nrm += (double)w[q] * w[q];
+        }
+        *reinterpret_cast<float4*>(mm + o) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(vv + o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(params + o) = make_float4(w[0], w[1], w[2], w[3]);
+      }
     }
-    if (WRITE_G) {
-      gout[o] = g;
-    } else {
-      float m = b1 * mm[o] + (1.f - b1) * g;
-      float v = b2 * vv[o] + (1.f - b2) * g * g;
-      mm[o] = m;
-      vv[o] = v;
-      w -= lr_t * m / (sqrtf(v) + eps);
-      params[o] = w;
-      nrm += (double)w * w;
+  } else {
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+      int64_t o = sg.off + e;
+      float w = params[o];
+      float g;
+      if (sg.kind == SEG_W) {
+        int r = (int)(e / Kout), c = (int)(e - (int64_t)r * Kout);
+        int i = r / Fi, j = c / Fo;
+        g = -coef * w;
+        if ((sup.row[i] >> j) & 1u) g = fmaf(graw[o], mask[i * LCN_J + j] * inv, g);
+        g = fmaf(reg, w, g);
+      } else if (sg.kind == SEG_B) {
+        g = fmaf(reg, w, graw[o]);
+      } else if (sg.kind == SEG_MASK) {
+        g = maskgrad[e];
+      } else {
+        g = graw[o];
+      }
+      if (WRITE_G) {
+        gout[o] = g;
+      } else {
+        float m = b1 * mm[o] + omb1 * g;
+        float v = b2 * vv[o] + omb2 * g * g;
+        mm[o] = m;
+        vv[o] = v;
+        w -= lr_t * m / (sqrtf(v) + eps);
+        params[o] = w;
+        nrm += (double)w * w;
+      }
     }
   }
   if (!WRITE_G && sg.kind == SEG_W) {
