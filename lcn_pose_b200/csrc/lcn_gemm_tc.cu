@@ -558,7 +558,9 @@ int lcn_tc_head_dgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat
 //   unit = (input chunk, group of <=4 of its present output chunks); grid.y splits the batch rows.
 //   M=64 accumulators use the half-subpartition TMEM layout: row m -> lane 32*(m/16) + m%16.
 // ---------------------------------------------------------------------------------------------
-#define TCW_STAGE_BYTES ((1 + TC_G) * TC_A_BYTES)
+#define TCW_HALF_BYTES 8192                       // 64 rows x 64 bf16: half of an activation tile
+#define TCW_STAGE_BYTES ((1 + TC_G) * TCW_HALF_BYTES)
+#define TCW_STAGES 2
 #define TCW_PITCH 260   // floats per staged output row (1040 B: 16-byte aligned, bank-conflict free)
 
 struct TcwParams {
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ dZ,
                                                          float* __restrict__ dW, TcwParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * TCW_STAGES + 1];
   __shared__ uint32_t tmem_base_s;
   uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -609,11 +611,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
   }
   const int t0 = blockIdx.y * p.tiles_per_cta;
   const int t1 = min(t0 + p.tiles_per_cta, p.tiles);
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]), tfull = smem_u32(&bars[2 * TC_STAGES]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TCW_STAGES]), tfull = smem_u32(&bars[2 * TCW_STAGES]);
   const uint32_t tmem_cols = len <= 1 ? 64u : (len == 2 ? 128u : 256u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < TCW_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -626,17 +628,20 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  const int n_it = 2 * (t1 - t0);                  // two 64-row half tiles per 128-row tile
   if (warp == 0) {
     if (lane == 0) {
-      for (int t = t0, it = 0; t < t1; ++t, ++it) {
-        int s = it % TC_STAGES;
-        uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+      for (int it = 0; it < n_it; ++it) {
+        int s = it % TCW_STAGES;
+        uint32_t ph = (uint32_t)(it / TCW_STAGES) & 1u;
+        int t = t0 + (it >> 1), half = it & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         uint32_t sa = sbase + s * TCW_STAGE_BYTES;
-        mbar_expect_tx(full0 + 8 * s, (1 + len) * TC_A_BYTES);
-        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic) * 8192, TC_A_BYTES, full0 + 8 * s);
+        mbar_expect_tx(full0 + 8 * s, (1 + len) * TCW_HALF_BYTES);
+        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic) * 8192 + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
         for (int q = 0; q < len; ++q)
-          bulk_g2s(sa + (1 + q) * TC_A_BYTES, dZ + ((size_t)t * p.NCN + ocs[q]) * 8192, TC_A_BYTES, full0 + 8 * s);
+          bulk_g2s(sa + (1 + q) * TCW_HALF_BYTES, dZ + ((size_t)t * p.NCN + ocs[q]) * 8192 + half * 4096,
+                   TCW_HALF_BYTES, full0 + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -644,16 +649,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
       // M = 64, N = 64*len, both operands MN-major
       uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((64 * len) >> 3) << 17) |
                        ((uint32_t)(64 >> 4) << 24);
-      for (int t = t0, it = 0; t < t1; ++t, ++it) {
-        int s = it % TC_STAGES;
-        uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+      for (int it = 0; it < n_it; ++it) {
+        int s = it % TCW_STAGES;
+        uint32_t ph = (uint32_t)(it / TCW_STAGES) & 1u;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
-        uint32_t sa = sbase + s * TCW_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        uint32_t sa = sbase + s * TCW_STAGE_BYTES, sb = sa + TCW_HALF_BYTES;
 #pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16) {
-          uint64_t ad = umma_desc_sw128(sa + k16 * 2048, TC_A_BYTES, 1024);
-          uint64_t bd = umma_desc_sw128(sb + k16 * 2048, TC_A_BYTES, 1024);
+        for (int k16 = 0; k16 < 4; ++k16) {          // 64 rows = 4 MMAs of K = 16
+          uint64_t ad = umma_desc_sw128(sa + k16 * 2048, TCW_HALF_BYTES, 1024);
+          uint64_t bd = umma_desc_sw128(sb + k16 * 2048, TCW_HALF_BYTES, 1024);
           umma_f16(tmem_base, ad, bd, idesc, (uint32_t)(it > 0 || k16 > 0));
         }
         umma_commit(empty0 + 8 * s);
@@ -692,16 +697,21 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
 }
 
 static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW, int tiles,
-                           cudaStream_t st) {
+                           int sm_count, cudaStream_t st) {
   int units = 0;
   for (int ic = 0; ic < p.NCK; ++ic) {
     int cnt = __builtin_popcount(p.row[ic / p.FCK]) * p.FCN;
     units += (cnt + TC_G - 1) / TC_G;
   }
   p.tiles = tiles;
-  p.tiles_per_cta = tiles >= 16 ? 4 : (tiles >= 4 ? 2 : 1);
-  int splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  size_t smem = (size_t)TC_STAGES * TCW_STAGE_BYTES + 1024;
+  // two CTAs are resident per SM (~82 KB smem, <=256 TMEM columns each): give every CTA the smallest row
+  // range for which the whole grid is a single wave of 2*SMs slots
+  int slots = 2 * sm_count;
+  int tpc = 1;
+  while (tpc < tiles && (long)units * ((tiles + tpc - 1) / tpc) > slots) ++tpc;
+  p.tiles_per_cta = tpc;
+  int splits = (tiles + tpc - 1) / tpc;
+  size_t smem = (size_t)TCW_STAGES * TCW_STAGE_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
     LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -721,7 +731,7 @@ int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A
   p.FCK = p.FCN = m->FC;
   p.NCK = p.NCN = LCN_J * m->FC;
   p.ldw = m->P;
-  return launch_tc_wgrad(p, A, dZ, dW, lay.tiles, st);
+  return launch_tc_wgrad(p, A, dZ, dW, lay.tiles, m->sm_count, st);
 }
 // last layer: dW4pad[P][64] += A_L^T dOut16 (one N chunk: 51 columns padded to 64)
 int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dOut16,
@@ -734,7 +744,7 @@ int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat
   p.NCK = LCN_J * m->FC;
   p.NCN = 1;
   p.ldw = 64;
-  return launch_tc_wgrad(p, A, dOut16, dWpad, lay.tiles, st);
+  return launch_tc_wgrad(p, A, dOut16, dWpad, lay.tiles, m->sm_count, st);
 }
 // first layer: dW1pad[64][P] += X16^T dZ0 (one M chunk: 17*in_F columns padded to 64)
 int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* X16, const __nv_bfloat16* dZ,
@@ -747,5 +757,5 @@ int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloa
   p.NCK = 1;
   p.NCN = LCN_J * m->FC;
   p.ldw = m->P;
-  return launch_tc_wgrad(p, X16, dZ, dWpad, lay.tiles, st);
+  return launch_tc_wgrad(p, X16, dZ, dWpad, lay.tiles, m->sm_count, st);
 }
