@@ -107,6 +107,14 @@ int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws
                       const float* d_x, int64_t n_rows, int32_t bn_group, int training,
                       float dropout_rate, uint64_t seed, uint64_t step, float* d_out, void* stream);
 
+/* Same arithmetic, with a parity tap: valid only where inference runs as the fused cluster kernel (bf16 path,
+ * F = 64, bn_group <= 256; LCN_EINVAL otherwise).  d_taps receives every layer output A_l (after
+ * BN / LeakyReLU / residual) as bf16 in the kernel's tile-major layout: [n_bn][tile][17 chunks][128 rows][64]
+ * with the 16-byte chunk c of row r stored at c ^ (r & 7); tile = group * ceil(bn_group/128) + row tile. */
+int lcn_model_forward_taps(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes,
+                           const float* d_x, int64_t n_rows, int32_t bn_group, float* d_out,
+                           void* d_taps, size_t taps_bytes, void* stream);
+
 /* (a9)+(autodiff) base_model.loss models_att.py:352-380 and optimizer.compute_gradients :408.
  * Requires a preceding lcn_model_forward(training=1) on the same workspace.  d_labels [n_rows,51].
  * d_loss: one float (mean squared error).  d_grads_raw: flat, param layout; holds dL/dWm for the

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "lcn_model_workspace_bytes": (_sz, [_vp, _i64, _i32, C.c_int]),
     "lcn_model_prepare_weights": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "lcn_model_forward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, C.c_int, _f, _u64, _u64, _vp, _vp]),
+    "lcn_model_forward_taps": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "lcn_model_backward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _i64, _f, _u64, _u64, _vp, _vp, _vp]),
     "lcn_model_finalize_grads": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "lcn_model_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _vp]),

@@ -239,8 +239,10 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_wp16b = take(2 * n_mid * sub);
   w.off_wl16f = take((size_t)LCN_J * m->FC * 8192);
   w.off_wl16b = take((size_t)LCN_J * m->FC * 8192);
-  w.off_part = take(sizeof(float) * (size_t)w.tiles * P * 2);
-  w.off_bnstat = take(sizeof(float) * (size_t)m->n_bn * w.n_groups * F * 2);
+  w.off_wf16 = take((size_t)LCN_J * m->FC * 8192);
+  w.fused = lcn_stack_eligible(m, bn_group, training) ? 1 : 0;
+  w.off_part = take(w.fused ? 0 : sizeof(float) * (size_t)w.tiles * P * 2);
+  w.off_bnstat = take(w.fused ? 0 : sizeof(float) * (size_t)m->n_bn * w.n_groups * F * 2);
   w.off_bnsum = take(sizeof(float) * (size_t)m->n_bn * F * 2);
   w.off_out = take(training ? sizeof(float) * (size_t)w.rows_pad * 51 : 0);
   w.off_dout = take(training ? sizeof(float) * (size_t)w.rows_pad * 51 : 0);
@@ -249,8 +251,8 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_dw_first = take(training ? sizeof(float) * 64 * P : 0);
   w.off_dw_last = take(training ? sizeof(float) * P * 64 : 0);
   size_t act = ((size_t)w.rows_pad * P * w.es + 255) & ~(size_t)255;
-  w.n_z = training ? m->n_bn : 1;
-  w.n_a = training ? m->n_bn : 3;
+  w.n_z = training ? m->n_bn : (w.fused ? 0 : 1);
+  w.n_a = training ? m->n_bn : (w.fused ? 0 : 3);
   w.n_d = training ? 3 : 0;
   w.z_stride = w.a_stride = w.d_stride = act;
   w.off_z = take(act * w.n_z);
@@ -259,6 +261,7 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_dz = take(training ? act : 0);
   w.off_dbpart = take(training ? sizeof(float) * (size_t)m->n_bn * 2 * m->sm_count * P : 0);
   w.off_keep = take(training ? (size_t)m->n_bn * w.rows_pad * (P / 8) : 0);
+  w.off_stack = take(w.fused ? lcn_stack_scratch_bytes(m, bn_group) : 0);
   w.total = off;
   return w;
 }
@@ -310,6 +313,23 @@ extern "C" int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws
   a.step = step;
   a.st = (cudaStream_t)stream;
   return lcn_launch_forward(a);
+}
+
+extern "C" int lcn_model_forward_taps(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,
+                                      int64_t n_rows, int32_t bn_group, float* d_out, void* d_taps, size_t taps_bytes,
+                                      void* stream) {
+  int rc = check_geom(m, n_rows, bn_group);
+  if (rc) return rc;
+  LCN_REQUIRE(d_params && d_ws && d_x && d_out && d_taps, "null argument");
+  WsLayout lay = lcn_ws_layout(m, n_rows, bn_group, 0);
+  LCN_REQUIRE(lay.fused, "forward_taps: the fused inference kernel does not cover this model / bn_group");
+  if (ws_bytes < lay.total) {
+    lcn_set_error("workspace too small: %zu < %zu", ws_bytes, lay.total);
+    return LCN_ENOMEM;
+  }
+  size_t need = (size_t)m->n_bn * lay.tiles * LCN_J * 8192 * 2;
+  LCN_REQUIRE(taps_bytes >= need, "taps buffer too small: %zu < %zu", taps_bytes, need);
+  return lcn_stack_forward(m, lay, d_params, (char*)d_ws, d_x, d_out, d_taps, (cudaStream_t)stream);
 }
 
 extern "C" int lcn_model_backward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,

@@ -96,6 +96,7 @@ struct WsLayout {
   size_t off_wp32;                   // fp32 packed mid-layer blocks  [mid][pair][FC][FC][64][64]
   size_t off_wp16f, off_wp16b;       // bf16 UMMA-layout packed blocks (forward / transposed)
   size_t off_wl16f, off_wl16b;       // bf16 packed last-layer weights: per K chunk [64 n][64 k] / per N chunk
+  size_t off_wf16;                   // bf16 packed first-layer weights: per N chunk [64 n][64 k (17*in_F used)]
   size_t off_x16, off_dout16;        // bf16 tiles of the 2D input / of dOut (64-column padded), training
   size_t off_dw_first, off_dw_last;  // fp32 padded weight-gradient scratch of the edge layers
   size_t off_part;                   // float[tiles][P][2] BN partials (mean, M2)
@@ -109,6 +110,8 @@ struct WsLayout {
   size_t off_dz;                     // dZ buffer (training)
   size_t off_dbpart;                 // float[n_bn][2*SMs][P] per-block bias-gradient partial rows (training)
   size_t off_keep;                   // uint8[n_bn][rows_pad][P/8] dropout keep bits (training)
+  int fused;                         // inference runs as the fused cluster kernel (lcn_stack_tc.cu)
+  size_t off_stack;                  // its per-cluster L2-resident activation scratch
   size_t total;
 };
 
@@ -177,6 +180,12 @@ int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat
 int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* X16, const __nv_bfloat16* dZ,
                        float* dWpad, cudaStream_t st);
 bool lcn_tc_enabled();
+
+// fused whole-stack inference kernel (lcn_stack_tc.cu): one thread-block cluster per BatchNorm group
+bool lcn_stack_eligible(const lcn_model* m, int bn_group, int training);
+size_t lcn_stack_scratch_bytes(const lcn_model* m, int bn_group);
+int lcn_stack_forward(const lcn_model* m, const WsLayout& lay, const float* params, char* ws, const float* x,
+                      float* out, void* taps /* nullable */, cudaStream_t st);
 
 // ---- device helpers ----
 __device__ __forceinline__ float lcn_ld(const float* p, size_t i) { return p[i]; }

@@ -187,6 +187,17 @@ __global__ void k_pack_last16(const float* __restrict__ wm_last, __nv_bfloat16* 
   }
 }
 
+// bf16 image of the first layer's masked weight for the fused inference kernel: one 64x64 block per output
+// chunk, B[n = output column of the chunk][k = input feature (17*in_F used, zero padded to 64)]
+__global__ void k_pack_first16(const float* __restrict__ wm_first, int Kin, int P, __nv_bfloat16* __restrict__ wf16) {
+  int oc = blockIdx.x;
+  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+    int n = e >> 6, k = e & 63;
+    float v = k < Kin ? wm_first[(size_t)k * P + oc * 64 + n] : 0.f;
+    wf16[(size_t)oc * 4096 + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
+  }
+}
+
 int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
                        bool recompute_norm, cudaStream_t st) {
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
@@ -206,10 +217,14 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
                                   reinterpret_cast<float*>(ws + lay.off_wm_first));
   k_pack_edge<<<64, 256, 0, st>>>(params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_last));
-  if (m->d.path == LCN_PATH_BF16)
+  if (m->d.path == LCN_PATH_BF16) {
     k_pack_last16<<<LCN_J * m->FC, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_wm_last),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
+    if (m->L[0].Kin <= 64)
+      k_pack_first16<<<LCN_J * m->FC, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
+                                                    m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
+  }
   int n_mid = m->n_lin - 2;
   const bool use_tc = m->d.path == LCN_PATH_BF16 && lcn_tc_enabled();
   if (n_mid > 0) {
@@ -1310,6 +1325,7 @@ static int forward_impl(const FwdArgs& a) {
 }
 
 int lcn_launch_forward(const FwdArgs& a) {
+  if (a.lay.fused) return lcn_stack_forward(a.m, a.lay, a.params, a.ws, a.x, a.out, nullptr, a.st);
   return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<float>(a);
 }
 

@@ -179,6 +179,29 @@ class LcnEngine:
         self._fwd_geom = (n, bn_group, bool(training))
         return out
 
+    def forward_taps(self, x, bn_group):
+        """Inference through the fused cluster kernel with the parity tap: returns (out [n,51] float32,
+        taps float32 [n_bn, groups*bn_group, 17*F]) -- every layer output A_l decoded from the kernel's tile layout."""
+        n = x.shape[0]
+        size = self._ensure_ws(n, bn_group, False)
+        if not self._prepared:
+            self.prepare()
+        n_bn = 1 + 2 * self.num_layers
+        tpg = (bn_group + 127) // 128
+        groups = (n + bn_group - 1) // bn_group
+        tiles = groups * tpg
+        taps = torch.zeros((n_bn, tiles, J, 128, 8, 8), dtype=torch.bfloat16, device=self.device)
+        out = torch.empty((n, J * 3), dtype=torch.float32, device=self.device)
+        L.check(self.lib.lcn_model_forward_taps(self.h, _ptr(self.params), _ptr(self.ws), size, _ptr(x), n, bn_group,
+                                                _ptr(out), _ptr(taps), taps.numel() * 2, self._stream()))
+        # undo the 128-byte swizzle: stored chunk index = c ^ (r & 7)
+        r = torch.arange(128, device=self.device).view(128, 1)
+        c = torch.arange(8, device=self.device).view(1, 8)
+        src = (c ^ (r & 7)).view(1, 1, 1, 128, 8, 1).expand(n_bn, tiles, J, 128, 8, 8)
+        dec = torch.gather(taps, 4, src).float()                       # [n_bn, tiles, 17, 128, 8, 8] logical chunk order
+        dec = dec.view(n_bn, groups, tpg, J, 128, 64).permute(0, 1, 2, 4, 3, 5).reshape(n_bn, groups, tpg * 128, J * 64)
+        return out, dec[:, :, :bn_group, :].reshape(n_bn, groups * bn_group, J * 64)
+
     def lr_at(self, step):
         """exponential_decay with global_step = step-1 (models_att.py:386-399)."""
         return self.learning_rate * self.decay_rate ** ((step - 1) / self.decay_steps)

@@ -77,7 +77,10 @@ def test_forward_per_layer_and_end_to_end(path, L, knn, n, bn_group):
     assert e < (5e-4 if path == "fp32" else 5e-2), f"end-to-end rel err {e}"
     # inference-layout (rotating buffers) result equals the training-layout one
     out2 = eng.forward(dev(x), bn_group=bn_group, training=False).cpu().numpy()
-    assert np.array_equal(out, out2)
+    if path == "fp32":
+        assert np.array_equal(out, out2)
+    else:   # bf16 inference at bn_group <= 256 runs as the fused cluster kernel (tests/test_gpu_fused.py)
+        assert rel_err(out2, out) < 3e-2
 
 
 @pytest.mark.parametrize("path", ["fp32", "bf16"])
