@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblcn_b200.so")
+# LCN_B200_LIB: another build of the same library (the -DLCN_TC_PROFILE one, profiling scripts only)
+LIB_PATH = os.path.abspath(os.environ.get("LCN_B200_LIB", os.path.join(_HERE, "liblcn_b200.so")))
 
 J = 17
 LCN_PATH_FP32, LCN_PATH_BF16 = 0, 1
