@@ -163,13 +163,20 @@ def run_gpu(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     n_bn = 1 + 2 * LAYERS
 
+    def allreduce(bucket):
+        dist.all_reduce(bucket)                     # one bucket: raw gradient of every tensor
+        bucket.div_(world)
+
     def step(xx, yy):
-        eng.forward(xx, bn_group=BATCH, training=True, dropout=args.dropout)
-        eng.backward(xx, yy, args.dropout)
-        if world > 1:
-            dist.all_reduce(eng.grads_raw)          # one bucket: packed gradient of every tensor
-            eng.grads_raw.div_(world)
-        eng.adam()
+        if args.no_graph:
+            eng.forward(xx, bn_group=BATCH, training=True, dropout=args.dropout)
+            eng.backward(xx, yy, args.dropout)
+            if world > 1:
+                allreduce(eng.grads_raw)
+            eng.adam()
+        else:
+            # the same launches, replayed from a CUDA graph (LcnEngine.train_step_graph)
+            eng.train_step_graph(xx, yy, args.dropout, allreduce if world > 1 else None)
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,7 +246,7 @@ def run_gpu(args, rank, world, local_rank):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.path == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "flushed between steps (256 MiB memset)",
-                           "dropout": args.dropout, "path": args.path,
+                           "dropout": args.dropout, "path": args.path, "launch": "eager" if args.no_graph else "cuda-graph replay",
                            "parallelism": f"dp{world}: per-GPU BatchNorm statistics, NCCL allreduce of the gradient bucket"},
                 "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "poses/s",
                         "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4},
@@ -270,6 +277,7 @@ def main():
     ap.add_argument("--path", default=os.environ.get("LCN_BENCH_PATH", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--dropout", type=float, default=0.25)     # params_help.py:166 training default
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -100,12 +100,24 @@ size_t lcn_model_workspace_bytes(const lcn_model* m, int64_t n_rows, int32_t bn_
  * and before forward.  models_att.py:659-660,690-691,726-728,762-764 and :534-586. */
 int lcn_model_prepare_weights(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Per-step scalars resident in DEVICE memory.  When the d_dyn argument of lcn_model_forward / lcn_model_adam_step is
+ * not NULL, the kernels read `step` (dropout Philox offset) / `lr_t` from it at execution time and ignore the
+ * by-value arguments of the same name: a CUDA graph captured around one train step (all calls only enqueue work on
+ * the caller's stream, so they are capturable) can then be replayed every step after rewriting these 16 bytes.
+ * The reference pays a sess.run feed/launch sequence per step (models_att.py:204-212). */
+typedef struct lcn_step_scalars {
+  uint64_t step;
+  float lr_t;
+  float reserved;
+} lcn_step_scalars;
+
 /* (a5)-(a8) cgcnn._inference_lcn, models_att.py:707-775.  d_x [n_rows, 17*in_F] fp32,
  * d_out [n_rows, 51] fp32.  dropout_rate 0 reproduces predict() (:102); the keep decision of
  * element e of layer l at step `step` is lcn_dropout_mask()'s. */
 int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes,
                       const float* d_x, int64_t n_rows, int32_t bn_group, int training,
-                      float dropout_rate, uint64_t seed, uint64_t step, float* d_out, void* stream);
+                      float dropout_rate, uint64_t seed, uint64_t step, float* d_out,
+                      const lcn_step_scalars* d_dyn, void* stream);
 
 /* Same arithmetic, with a parity tap: valid only where inference runs as the fused cluster kernel (bf16 path,
  * F = 64, bn_group <= 256; LCN_EINVAL otherwise).  d_taps receives every layer output A_l (after
@@ -136,7 +148,7 @@ int lcn_model_finalize_grads(lcn_model* m, const float* d_params, void* d_ws, si
  * weight preparation for the next forward. */
 int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, float* d_v, void* d_ws, size_t ws_bytes,
                         const float* d_grads_raw, float lr_t, float beta1, float beta2, float eps,
-                        float regularization, void* stream);
+                        float regularization, const lcn_step_scalars* d_dyn, void* stream);
 
 /* One LCN linear op in isolation, on the buffers of the last forward (tf.matmul(x, w) + b,
  * models_att.py:662,692): mid layer `layer` (1..2*num_layers) recomputes Z_layer = A_{layer-1} * Wm + b

@@ -36,11 +36,11 @@ PROTOTYPES = {
     "lcn_model_tensor_info": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32)]),
     "lcn_model_workspace_bytes": (_sz, [_vp, _i64, _i32, C.c_int]),
     "lcn_model_prepare_weights": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
-    "lcn_model_forward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, C.c_int, _f, _u64, _u64, _vp, _vp]),
+    "lcn_model_forward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, C.c_int, _f, _u64, _u64, _vp, _vp, _vp]),
     "lcn_model_forward_taps": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "lcn_model_backward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _i64, _f, _u64, _u64, _vp, _vp, _vp]),
     "lcn_model_finalize_grads": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
-    "lcn_model_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _vp]),
+    "lcn_model_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _vp, _vp]),
     "lcn_layer_gemm": (C.c_int, [_vp, _vp, _vp, _sz, _i64, _i32, C.c_int, C.c_int, _vp]),
     "lcn_model_read_tensor": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _i64, _i32, _vp, _vp]),
     "lcn_dropout_mask": (C.c_int, [_u64, _u64, C.c_int, _i64, _i32, _f, _vp, _vp]),

@@ -292,7 +292,7 @@ extern "C" int lcn_model_prepare_weights(lcn_model* m, const float* d_params, vo
 
 extern "C" int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,
                                  int64_t n_rows, int32_t bn_group, int training, float dropout_rate, uint64_t seed,
-                                 uint64_t step, float* d_out, void* stream) {
+                                 uint64_t step, float* d_out, const lcn_step_scalars* d_dyn, void* stream) {
   int rc = check_geom(m, n_rows, bn_group);
   if (rc) return rc;
   LCN_REQUIRE(d_params && d_ws && d_x && d_out, "null argument");
@@ -311,6 +311,7 @@ extern "C" int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws
   a.dropout_rate = dropout_rate;
   a.seed = seed;
   a.step = step;
+  a.dyn = d_dyn;
   a.st = (cudaStream_t)stream;
   return lcn_launch_forward(a);
 }
@@ -361,7 +362,7 @@ extern "C" int lcn_model_finalize_grads(lcn_model* m, const float* d_params, voi
 
 extern "C" int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, float* d_v, void* d_ws, size_t ws_bytes,
                                    const float* d_grads_raw, float lr_t, float beta1, float beta2, float eps,
-                                   float regularization, void* stream) {
+                                   float regularization, const lcn_step_scalars* d_dyn, void* stream) {
   LCN_REQUIRE(m && d_params && d_m && d_v && d_ws && d_grads_raw, "null argument");
   WsLayout lay = lcn_ws_layout(m, 128, 128, 0);
   if (ws_bytes < lay.off_part) {
@@ -369,7 +370,7 @@ extern "C" int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, fl
     return LCN_ENOMEM;
   }
   return lcn_launch_adam(m, d_params, d_m, d_v, (char*)d_ws, lay, d_grads_raw, lr_t, beta1, beta2, eps, regularization,
-                         (cudaStream_t)stream);
+                         d_dyn, (cudaStream_t)stream);
 }
 
 extern "C" int lcn_layer_gemm(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, int64_t n_rows,

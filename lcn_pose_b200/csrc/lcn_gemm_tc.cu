@@ -15,11 +15,15 @@
 // the panels are consumed, so every operand is one contiguous bulk copy -- no tensor maps needed.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem tile -> bulk store).  Two CTAs are
-// co-resident per SM (256 TMEM columns and ~97 KB smem each) so one CTA's epilogue overlaps the other's
-// main loop.
+// lane), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem tile -> bulk store); all six warps compute the
+// BatchNorm partials.  A kernel that allocates TMEM gets ONE resident CTA per SM (cudaOccupancyMaxActiveBlocksPer-
+// Multiprocessor reports 1 for any kernel containing tcgen05.alloc, profiles/micro/occ.cu), so grids are sized as
+// single waves of <= SM-count CTAs and a CTA may use the whole shared memory and all 512 TMEM columns.
 #include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
+#include <vector>
 
 #include "lcn_internal.cuh"
 
@@ -29,6 +33,7 @@
 #define TC_B_BYTES 8192             // one 64x64 bf16 block
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_G * TC_B_BYTES)
 #define TC_THREADS 192
+#define TC_MAX_CHUNKS 34            // 17 joints x (F/64 <= 2) chunks on either side
 
 // optional per-CTA timeline (clock64) for block (0,0): enabled with -DLCN_TC_PROFILE
 #ifdef LCN_TC_PROFILE
@@ -57,15 +62,17 @@ struct TcParams {
   int64_t n_rows;
   float* out_user;
   float* out_ws;
+  // per (N-side chunk group, K chunk) schedule, filled by the host (tc_fill_schedule): which chunks of the group have
+  // a block under this K chunk, and the slot of the first one in the packed panel.  Lives in the kernel parameters
+  // (constant bank) so that the producer / MMA warps index it with uniform loads and keep descriptors in uniform
+  // registers (a schedule in shared memory forces an R2UR per tcgen05.mma operand: measured 80-100 cycles per MMA).
+  uint8_t gbits[TC_MAX_CHUNKS][TC_MAX_CHUNKS];
+  uint16_t gslot[TC_MAX_CHUNKS][TC_MAX_CHUNKS];
+  uint8_t gwritten[TC_MAX_CHUNKS];
+  uint8_t goc0[TC_MAX_CHUNKS + 1];  // group g owns N-side chunks [goc0[g], goc0[g+1]): contiguous, balanced by block count
 };
 
 #include "lcn_tc_ptx.cuh"
-
-__device__ __forceinline__ void group_range(int g, int NC, int n_groups, int* oc0, int* G) {
-  int base = NC / n_groups, extra = NC % n_groups;
-  *G = base + (g < extra ? 1 : 0);
-  *oc0 = g * base + min(g, extra);
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward / dgrad / head GEMM.  GMAX = max N-side chunks per CTA (64*GMAX TMEM columns).
@@ -76,26 +83,20 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
                                                         const float* __restrict__ bias,
                                                         const __nv_bfloat16* __restrict__ addend,
                                                         __nv_bfloat16* __restrict__ Y, float* __restrict__ part,
-                                                        TcParams p) {
+                                                        const __grid_constant__ TcParams p) {
   constexpr int STAGE_BYTES = TC_A_BYTES + GMAX * TC_B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[GMAX * 64];
-  // per-CTA schedule, built once in parallel: iteration -> (K chunk, present bits, first block slot)
-  __shared__ int sch_kc[2 * LCN_J], sch_slot[2 * LCN_J];
-  __shared__ uint32_t sch_bits[2 * LCN_J];
-  __shared__ int sch_n;
-  __shared__ uint32_t sch_written;
 
   uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x, tile = blockIdx.y;
-  int oc0, G;
-  group_range(g, p.NCN, p.n_groups, &oc0, &G);
+  const int oc0 = p.goc0[g], G = p.goc0[g + 1] - oc0;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
-  const uint32_t tmem_cols = G <= 1 ? 64u : (G == 2 ? 128u : 256u);
+  const uint32_t tmem_cols = G <= 1 ? 64u : (G == 2 ? 128u : (G <= 4 ? 256u : 512u));
   TC_STAMP(0);
 
   if (threadIdx.x == 0) {
@@ -107,115 +108,89 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), tmem_cols);
-  if (warp == 2) {
-    // schedule: lanes cover K chunks kc = lane, lane + 32 (NCK <= 34); compaction by ballot
-    int n = 0;
-    uint32_t written = 0;
-    for (int base_kc = 0; base_kc < p.NCK; base_kc += 32) {
-      int kc = base_kc + lane;
-      uint32_t bits = 0;
-      int slot = 0;
-      if (kc < p.NCK) {
-        int ka = kc / p.FCK, hk = kc - ka * p.FCK;
-        uint32_t km = p.kmask[ka];
-        for (int q = 0; q < G; ++q)
-          if ((km >> ((oc0 + q) / p.FCN)) & 1u) bits |= 1u << q;
-        if (bits) {
-          int oc = oc0 + (__ffs(bits) - 1);
-          int nb = oc / p.FCN, hn = oc - nb * p.FCN;
-          int pb = 0;
-          for (int q = 0; q < ka; ++q) pb += __popc(p.kmask[q]);
-          slot = p.FCK * p.FCN * pb + hk * (__popc(km) * p.FCN) + __popc(km & ((1u << nb) - 1u)) * p.FCN + hn;
-        }
-      }
-      uint32_t bal = __ballot_sync(0xffffffffu, bits != 0);
-      if (bits) {
-        int pos = n + __popc(bal & ((1u << lane) - 1u));
-        sch_kc[pos] = kc;
-        sch_bits[pos] = bits;
-        sch_slot[pos] = slot;
-      }
-      n += __popc(bal);
-      for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
-      written |= bits;
-    }
-    if (lane == 0) {
-      sch_n = n;
-      sch_written = written;
-    }
-  }
-  if (p.mode != TC_MODE_DGRAD)
-    for (int c = threadIdx.x; c < G * 64; c += TC_THREADS) {
-      int col = oc0 * 64 + c;
-      bias_s[c] = (p.mode == TC_MODE_HEAD && col >= 51) ? 0.f : bias[col];
-    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int n_it = sch_n;
   TC_STAMP(1);
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const __nv_bfloat16* a_tile = A + (size_t)tile * p.NCK * 8192;
-      for (int it = 0; it < n_it; ++it) {
-        int s = it % STAGES;
-        uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        int kc = sch_kc[it];
-        int cnt = __popc(sch_bits[it]);
-        const __nv_bfloat16* wsrc = Wp + (size_t)sch_slot[it] * 4096;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+    // ===== TMA producer (warp-uniform; one elected lane issues) =====
+    const __nv_bfloat16* a_tile = A + (size_t)tile * p.NCK * 8192;
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int kc = 0; kc < p.NCK; ++kc) {
+      const uint32_t bits = p.gbits[g][kc];
+      if (!bits) continue;
+      const uint32_t cnt = (uint32_t)__popc(bits);
+      const __nv_bfloat16* wsrc = Wp + (size_t)p.gslot[g][kc] * 4096;
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      if (elect_one()) {
         TC_STAMP(16 + 4 * it);
-        uint32_t sa = sbase + s * STAGE_BYTES;
+        const uint32_t sa = sbase + s * STAGE_BYTES;
         mbar_expect_tx(full0 + 8 * s, TC_A_BYTES + cnt * TC_B_BYTES);
         bulk_g2s(sa, a_tile + (size_t)kc * 8192, TC_A_BYTES, full0 + 8 * s);
         bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * s);
         TC_STAMP(17 + 4 * it);
       }
+      __syncwarp();
+      ++it;
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t written = 0;
-      const uint64_t desc_hi = (uint64_t)((1024u >> 4) & 0x3FFF) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
-      for (int it = 0; it < n_it; ++it) {
-        int s = it % STAGES;
-        uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        uint32_t bits = sch_bits[it];
-        mbar_wait(full0 + 8 * s, ph);
-        TC_STAMP(18 + 4 * it);
-        tc_fence_after();
-        uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + TC_A_BYTES;
-        uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-        int rank = 0, q = 0;
-        while (q < G) {
-          if (!((bits >> q) & 1u)) { ++q; continue; }
-          uint32_t acc = (written >> q) & 1u;      // maximal run of present chunks with equal accumulate state
-          int len = 1;
-          while (q + len < G && ((bits >> (q + len)) & 1u) && (((written >> (q + len)) & 1u) == acc)) ++len;
-          uint32_t idesc = umma_idesc(64 * len, 0, 0);
-          uint64_t bd0 = desc_hi | (uint64_t)(((sb + rank * TC_B_BYTES) >> 4) & 0x3FFF);
-          uint32_t d = tmem_base + q * 64;
+    // ===== MMA issuer (warp-uniform control flow and operands; one elected lane issues) =====
+    uint32_t written = 0;
+    const uint64_t desc_hi = (uint64_t)((1024u >> 4) & 0x3FFF) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int kc = 0; kc < p.NCK; ++kc) {
+      const uint32_t bits = p.gbits[g][kc];
+      if (!bits) continue;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+      const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+      if (lane == 0) TC_STAMP(18 + 4 * it);
+      // run detection is warp-uniform (uniform registers); only the tcgen05 instructions sit under elect_one
+      int rank = 0, q = 0;
+      while (q < G) {
+        if (!((bits >> q) & 1u)) { ++q; continue; }
+        const uint32_t acc = (written >> q) & 1u;      // maximal run of present chunks with equal accumulate state
+        int len = 1;
+        while (len < 4 && q + len < G && ((bits >> (q + len)) & 1u) && (((written >> (q + len)) & 1u) == acc)) ++len;
+        const uint32_t idesc = umma_idesc(64 * len, 0, 0);
+        const uint64_t bd0 = desc_hi | (uint64_t)(((sb + rank * TC_B_BYTES) >> 4) & 0x3FFF);
+        const uint32_t d = tmem_base + q * 64;
+        if (elect_one()) {
           umma_f16(d, ad0, bd0, idesc, acc);       // K = 64 -> 4 instructions of K = 16 (32 bytes each)
           umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
           umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
           umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
-          written |= ((1u << len) - 1u) << q;
-          rank += len;
-          q += len;
         }
-        umma_commit(empty0 + 8 * s);     // frees the smem stage when these MMAs have read it
-        TC_STAMP(19 + 4 * it);
+        rank += len;
+        q += len;
       }
-      umma_commit(tfull);                // accumulators complete
+      if (elect_one()) umma_commit(empty0 + 8 * s);     // frees the smem stage when these MMAs have read it
+      if (lane == 0) TC_STAMP(19 + 4 * it);
+      __syncwarp();
+      written |= bits;
+      ++it;
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
+    if (elect_one()) umma_commit(tfull);  // accumulators complete
+    __syncwarp();
   } else {
     // ===== epilogue: 4 warps, warp's TMEM lane quarter = warp id % 4 =====
     const int lq = warp & 3;
     const int row = lq * 32 + lane;
-    const uint32_t written = sch_written;
+    const uint32_t written = p.gwritten[g];
+    if (p.mode != TC_MODE_DGRAD) {
+      for (int c = threadIdx.x - 64; c < G * 64; c += 128) {
+        int col = oc0 * 64 + c;
+        bias_s[c] = (p.mode == TC_MODE_HEAD && col >= 51) ? 0.f : bias[col];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(tfull, 0);
     if (threadIdx.x == 64) TC_STAMP(2);
     tc_fence_after();
@@ -308,43 +283,59 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
           bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * 8192, sbase + q * TC_A_BYTES, TC_A_BYTES);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (p.mode == TC_MODE_FWD && part != nullptr) {
-        // BatchNorm partials of this tile: per column (mean, M2) over the valid rows, from the bf16 values.
-        // 32 lanes x 4 row-quarters per chunk: warp w handles chunks w, w+4 ...; combine quarters by shuffle-free
-        // exact pairwise merge (equal counts are not guaranteed -> use Chan's formula).
-        int tig = tile % (p.gstride / LCN_TILE);
-        int nvalid = min(LCN_TILE, p.bn_group - tig * LCN_TILE);
-        for (int q = warp - 2; q < G; q += 4) {
-          const uint8_t* tile_s = sgen + q * TC_A_BYTES;
-          float sh0 = 0.f, sh1 = 0.f, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-          const uint32_t coff = (uint32_t)(lane & 3) * 4;
-          const int chunk = lane >> 2;
-          {
-            uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + ((chunk ^ 0) << 4) + coff);
-            float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-            sh0 = t.x; sh1 = t.y;
-          }
-#pragma unroll 8
-          for (int r = 0; r < nvalid; ++r) {
-            uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
-            float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-            float d0 = t.x - sh0, d1 = t.y - sh1;
-            s1a += d0; s2a = fmaf(d0, d0, s2a);
-            s1b += d1; s2b = fmaf(d1, d1, s2b);
-          }
-          float n = (float)nvalid;
-          size_t o = ((size_t)tile * p.P + (oc0 + q) * 64 + lane * 2) * 2;
-          float4 out = make_float4(sh0 + s1a / n, fmaxf(s2a - s1a * s1a / n, 0.f), sh1 + s1b / n,
-                                   fmaxf(s2b - s1b * s1b / n, 0.f));
-          *reinterpret_cast<float4*>(part + o) = out;
-        }
-      }
-      if (warp == 2 && lane == 0) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        TC_STAMP(4);
-      }
     }
     if (threadIdx.x == 64) TC_STAMP(5);
+  }
+  if (p.mode == TC_MODE_FWD && part != nullptr) {
+    // BatchNorm partials of this tile: per column (mean, M2) over the valid rows, from the bf16 values staged in
+    // shared memory.  All six warps take part (the producer and MMA warps are idle by now): warp w handles chunks
+    // w, w+6, ...; a lane owns two columns and walks the rows with a shifted sum / sum of squares.
+    __syncwarp();
+    asm volatile("bar.sync 2, 192;" ::: "memory");
+    // rows r = warp, warp + 6, ... of every chunk; a lane owns two columns.  Sums are shifted by the chunk's row-0
+    // value (the same shift in every warp, so the partial sums of the six warps simply add).
+    const int tig = tile % (p.gstride / LCN_TILE);
+    const int nvalid = min(LCN_TILE, p.bn_group - tig * LCN_TILE);
+    float* red = reinterpret_cast<float*>(sgen + GMAX * TC_A_BYTES);       // [6 warps][G][64 columns][s1, s2]
+    const uint32_t coff = (uint32_t)(lane & 3) * 4;
+    const int chunk = lane >> 2;
+    for (int q = 0; q < G; ++q) {
+      const uint8_t* tile_s = sgen + q * TC_A_BYTES;
+      float sh0, sh1, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + (chunk << 4) + coff);
+        float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+        sh0 = t.x; sh1 = t.y;
+      }
+#pragma unroll 4
+      for (int r = warp; r < nvalid; r += 6) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
+        float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+        float d0 = t.x - sh0, d1 = t.y - sh1;
+        s1a += d0; s2a = fmaf(d0, d0, s2a);
+        s1b += d1; s2b = fmaf(d1, d1, s2b);
+      }
+      *reinterpret_cast<float4*>(red + ((size_t)(warp * G + q) * 64 + lane * 2) * 2) = make_float4(s1a, s2a, s1b, s2b);
+    }
+    asm volatile("bar.sync 2, 192;" ::: "memory");
+    const float n = (float)nvalid;
+    for (int c = threadIdx.x; c < G * 64; c += TC_THREADS) {
+      const int q = c >> 6, col = c & 63;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 6; ++w) {
+        const float2 v = *reinterpret_cast<const float2*>(red + ((size_t)(w * G + q) * 64 + col) * 2);
+        s1 += v.x; s2 += v.y;
+      }
+      const uint8_t* tile_s = sgen + q * TC_A_BYTES;
+      const float sh = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile_s + (((col >> 3)) << 4) + (col & 7) * 2));
+      *reinterpret_cast<float2*>(part + ((size_t)tile * p.P + (oc0 + q) * 64 + col) * 2) =
+          make_float2(sh + s1 / n, fmaxf(s2 - s1 * s1 / n, 0.f));
+    }
+  }
+  if (warp == 2 && lane == 0 && p.mode != TC_MODE_HEAD) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    TC_STAMP(4);
   }
   tc_fence_before();
   __syncthreads();
@@ -379,28 +370,135 @@ static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const 
   return LCN_OK;
 }
 
-// Pick the N-side grouping: both configurations keep 2 CTAs resident per SM (~97 KB smem each);
-// choose the one whose CTA count fills the 2*SM slots best (fewest waves, then least idle).
+// blocks under N-side chunk oc (= K chunks with a block into it)
+static int tc_col_blocks(const TcParams& p, int oc) {
+  int n = 0;
+  for (int ka = 0; ka < p.NCK / p.FCK; ++ka)
+    if ((p.kmask[ka] >> (oc / p.FCN)) & 1u) n += p.FCK;
+  return n;
+}
+
+// contiguous split of the N-side chunks into ng groups of <= 6 chunks minimising the largest block count
+// (a CTA's main-loop time is proportional to its blocks); returns that maximum.  DP over (groups, chunks).
+static int tc_partition(const TcParams& p, int ng, uint8_t* goc0) {
+  const int NC = p.NCN, INF = 1 << 28;
+  static thread_local int best[TC_MAX_CHUNKS + 1][TC_MAX_CHUNKS + 1], from[TC_MAX_CHUNKS + 1][TC_MAX_CHUNKS + 1];
+  int pre[TC_MAX_CHUNKS + 1];
+  pre[0] = 0;
+  for (int c = 0; c < NC; ++c) pre[c + 1] = pre[c] + tc_col_blocks(p, c);
+  for (int k = 0; k <= ng; ++k)
+    for (int c = 0; c <= NC; ++c) best[k][c] = INF;
+  best[0][0] = 0;
+  for (int k = 1; k <= ng; ++k)
+    for (int c = k; c <= NC; ++c)
+      for (int a = 1; a <= 6 && a <= c; ++a) {
+        if (best[k - 1][c - a] >= INF) continue;
+        int load = pre[c] - pre[c - a];
+        int v = best[k - 1][c - a] > load ? best[k - 1][c - a] : load;
+        if (v < best[k][c]) { best[k][c] = v; from[k][c] = a; }
+      }
+  if (best[ng][NC] >= INF) return INF;
+  int c = NC;
+  for (int k = ng; k >= 1; --k) {
+    goc0[k] = (uint8_t)c;
+    c -= from[k][c];
+  }
+  goc0[0] = 0;
+  return best[ng][NC];
+}
+
+// per (group, K chunk): present bits of the group's chunks and the slot of the first present block (k_pack_mid order)
+static void tc_fill_schedule(TcParams& p) {
+  memset(p.gbits, 0, sizeof(p.gbits));
+  memset(p.gslot, 0, sizeof(p.gslot));
+  memset(p.gwritten, 0, sizeof(p.gwritten));
+  for (int g = 0; g < p.n_groups; ++g) {
+    const int oc0 = p.goc0[g], G = p.goc0[g + 1] - oc0;
+    for (int kc = 0; kc < p.NCK; ++kc) {
+      const int ka = kc / p.FCK, hk = kc - ka * p.FCK;
+      const uint32_t km = p.kmask[ka];
+      uint32_t bits = 0;
+      for (int q = 0; q < G; ++q)
+        if ((km >> ((oc0 + q) / p.FCN)) & 1u) bits |= 1u << q;
+      p.gbits[g][kc] = (uint8_t)bits;
+      p.gwritten[g] |= (uint8_t)bits;
+      if (bits) {
+        const int oc = oc0 + __builtin_ctz(bits);
+        const int nb = oc / p.FCN, hn = oc - nb * p.FCN;
+        int pb = 0;
+        for (int q = 0; q < ka; ++q) pb += __builtin_popcount(p.kmask[q]);
+        p.gslot[g][kc] = (uint16_t)(p.FCK * p.FCN * pb + hk * (__builtin_popcount(km) * p.FCN) +
+                                    __builtin_popcount(km & ((1u << nb) - 1u)) * p.FCN + hn);
+      }
+    }
+  }
+}
+
+// choose the number of groups (whole waves of sm_count CTAs, minimal waves x per-CTA time), partition, fill the schedule
+static int tc_make_schedule(TcParams& p, int tiles, int sm_count, int force) {
+  int best_ng = p.NCN;
+  double best = 1e30;
+  uint8_t goc0[TC_MAX_CHUNKS + 1];
+  for (int ng = (p.NCN + 5) / 6; ng <= p.NCN; ++ng) {
+    const int maxblk = tc_partition(p, ng, goc0);
+    int gmax = 0;
+    for (int g = 0; g < ng; ++g) gmax = goc0[g + 1] - goc0[g] > gmax ? goc0[g + 1] - goc0[g] : gmax;
+    long ctas = (long)tiles * ng;
+    long waves = (ctas + sm_count - 1) / sm_count;
+    // per-CTA time ~ main loop (blocks) + epilogue (chunks) + fixed cost, in units of one block's MMA time
+    double c = (double)waves * (maxblk + 3.0 * gmax + 8.0);
+    if (c < best - 1e-9) { best = c; best_ng = ng; }
+  }
+  if (force > 0 && (p.NCN + force - 1) / force <= 6) best_ng = force < p.NCN ? force : p.NCN;
+  p.n_groups = best_ng;
+  tc_partition(p, best_ng, p.goc0);
+  int gmax = 0;
+  for (int g = 0; g < best_ng; ++g) gmax = p.goc0[g + 1] - p.goc0[g] > gmax ? p.goc0[g + 1] - p.goc0[g] : gmax;
+  tc_fill_schedule(p);
+  return gmax;
+}
+
+// Pick the N-side grouping.  One CTA is resident per SM (TMEM kernels), so the grid should be whole waves of
+// sm_count CTAs: choose the number of chunk groups that minimises waves x (work per CTA + fixed per-CTA cost).
 static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
                            const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, TcParams& p, int tiles,
                            int sm_count, cudaStream_t st) {
   static int force = -1;
   if (force < 0) {
-    const char* e = getenv("LCN_TC_G");
+    const char* e = getenv("LCN_TC_GROUPS");
     force = e ? atoi(e) : 0;
   }
-  int slots = 2 * sm_count;
-  auto cost = [&](int gmax) {
-    long ctas = (long)tiles * ((p.NCN + gmax - 1) / gmax);
-    long waves = (ctas + slots - 1) / slots;
-    return (double)waves * gmax;            // time ~ waves x work per CTA (~ group size)
-  };
-  int g = (cost(2) < cost(4)) ? 2 : 4;
-  if (force == 2 || force == 4) g = force;
-  if (p.NCN == 1) g = 2;
-  p.n_groups = (p.NCN + g - 1) / g;
-  if (g == 2) return launch_tc_gemm<2, 3>(A, W, bias, addend, Y, part, p, tiles, st);
-  return launch_tc_gemm<4, 2>(A, W, bias, addend, Y, part, p, tiles, st);
+  // The grouping and its schedule depend only on (mask, chunk geometry, tiles, SM count): computed once, then
+  // served from a small cache (the launch path must stay cheap: it runs ~20 times per train step).
+  struct Entry { uint32_t kmask[LCN_J]; int FCK, FCN, NCK, NCN, tiles, sm, force; TcParams sched; int gmax; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  int gmax = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    const Entry* hit = nullptr;
+    for (const Entry& e : cache)
+      if (e.FCK == p.FCK && e.FCN == p.FCN && e.NCK == p.NCK && e.NCN == p.NCN && e.tiles == tiles && e.sm == sm_count &&
+          e.force == force && memcmp(e.kmask, p.kmask, sizeof(e.kmask)) == 0) { hit = &e; break; }
+    if (hit == nullptr) {
+      Entry e;
+      memcpy(e.kmask, p.kmask, sizeof(e.kmask));
+      e.FCK = p.FCK; e.FCN = p.FCN; e.NCK = p.NCK; e.NCN = p.NCN; e.tiles = tiles; e.sm = sm_count; e.force = force;
+      e.sched = p;
+      e.gmax = tc_make_schedule(e.sched, tiles, sm_count, force);
+      cache.push_back(e);
+      hit = &cache.back();
+    }
+    p.n_groups = hit->sched.n_groups;
+    memcpy(p.gbits, hit->sched.gbits, sizeof(p.gbits));
+    memcpy(p.gslot, hit->sched.gslot, sizeof(p.gslot));
+    memcpy(p.gwritten, hit->sched.gwritten, sizeof(p.gwritten));
+    memcpy(p.goc0, hit->sched.goc0, sizeof(p.goc0));
+    gmax = hit->gmax;
+  }
+  if (gmax <= 2) return launch_tc_gemm<2, 4>(A, W, bias, addend, Y, part, p, tiles, st);
+  if (gmax <= 4) return launch_tc_gemm<4, 4>(A, W, bias, addend, Y, part, p, tiles, st);
+  return launch_tc_gemm<6, 3>(A, W, bias, addend, Y, part, p, tiles, st);
 }
 
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed, const __nv_bfloat16* A,

@@ -145,6 +145,7 @@ struct FwdArgs {                 // one call of the forward pass
   float* out;
   float dropout_rate;
   uint64_t seed, step;
+  const lcn_step_scalars* dyn;   // device-resident step scalars (overrides `step` when not null)
   cudaStream_t st;
 };
 
@@ -158,7 +159,7 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
                              const float* grads_raw, float* grads_out, cudaStream_t st);
 int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
                     const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg,
-                    cudaStream_t st);
+                    const lcn_step_scalars* dyn, cudaStream_t st);
 int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
                           int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,

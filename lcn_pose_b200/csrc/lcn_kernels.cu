@@ -511,8 +511,9 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act(const T* __restrict__ Z, 
                                                        const T* __restrict__ res, T* __restrict__ Aout,
                                                        uint8_t* __restrict__ keepbits, int P, int F, int rows_pad,
                                                        int bn_group, int gstride, float rate, uint64_t seed,
-                                                       uint64_t step, int layer) {
+                                                       uint64_t step, int layer, const lcn_step_scalars* __restrict__ dyn) {
   __shared__ __align__(16) float s_sc[256], s_sh[256];
+  if (dyn != nullptr) step = dyn->step;        // CUDA-graph replay: the step counter lives in device memory
   const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   // contiguous row range of this block (multiple of Y rows)
@@ -1111,8 +1112,10 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
                                               float* __restrict__ vv, const float* __restrict__ graw,
                                               float* __restrict__ gout, SegTable segs, LinTable lt, SupportBits sup,
                                               const float* __restrict__ mask, const float* __restrict__ maskgrad,
-                                              LayerScalars* sc, float lr_t, float b1, float b2, float eps, float reg) {
+                                              LayerScalars* sc, float lr_t, float b1, float b2, float eps, float reg,
+                                              const lcn_step_scalars* __restrict__ dyn) {
   __shared__ double sh[32];
+  if (dyn != nullptr) lr_t = dyn->lr_t;        // CUDA-graph replay: the step size lives in device memory
   int chunk = blockIdx.x;
   int s = 0;
   while (s + 1 < segs.n && segs.s[s + 1].chunk_start <= chunk) ++s;
@@ -1217,13 +1220,14 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
   k_adam<true><<<m->segs.total_chunks, 256, 0, st>>>(const_cast<float*>(params), nullptr, nullptr, grads_raw,
                                                      grads_out, m->segs, make_lin(m), m->sup, mask,
-                                                     mask + 2 * LCN_J * LCN_J, sc, 0.f, 0.f, 0.f, 0.f, 0.f);
+                                                     mask + 2 * LCN_J * LCN_J, sc, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
 
 int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
-                    const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg, cudaStream_t st) {
+                    const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg,
+                    const lcn_step_scalars* dyn, cudaStream_t st) {
   int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st);
   if (rc) return rc;
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
@@ -1231,7 +1235,7 @@ int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, cha
   k_zero_norm2<<<1, 32, 0, st>>>(sc, m->n_lin);
   k_adam<false><<<m->segs.total_chunks, 256, 0, st>>>(params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
                                                       m->sup, mask, mask + 2 * LCN_J * LCN_J, sc, lr_t, b1, b2, eps,
-                                                      reg);
+                                                      reg, dyn);
   LCN_CHECK_LAUNCH();
   return lcn_launch_prepare(m, params, ws, lay, /*recompute_norm=*/false, st);
 }
@@ -1305,7 +1309,7 @@ static int forward_impl(const FwdArgs& a) {
     int ew_grid = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
     k_bn_act<T><<<ew_grid, dim3(P / 8, ewy), 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
                                                       keepbits, P, F, (int)lay.rows_pad, lay.bn_group, lay.gstride,
-                                                      a.dropout_rate, a.seed, a.step, l);
+                                                      a.dropout_rate, a.seed, a.step, l, a.dyn);
     LCN_CHECK_LAUNCH();
   }
   int last = m->n_lin - 1;

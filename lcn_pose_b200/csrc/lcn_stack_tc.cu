@@ -16,27 +16,35 @@
 //   mid layers: block-sparse X * (W.M): only joint pairs inside the mask support are loaded and multiplied
 //   head      : 17*F -> 51 (N padded to 64) + xy skip connection, fp32 rows to the caller's output
 //
-// Warp roles (320 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (two warps per TMEM lane quarter, one per 32-column half of a chunk).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = epilogue (EW = 4 or 8 warps:
+// one or two per TMEM lane quarter; with two, each takes one 32-column half of a chunk).
+//
+// Two BN groups per SM.  A kernel that allocates TMEM is limited to ONE resident CTA per SM (measured:
+// profiles/micro/occ.cu), and the per-layer chain MMA -> statistics -> exchange -> BN epilogue -> store -> barrier of
+// one group is serial.  So a CTA hosts NV = 2 "virtual CTAs" (its own producer, MMA and epilogue warps, pipeline
+// stages, mbarriers and half of the TMEM columns each) that belong to two different virtual clusters working on two
+// different BN groups: one group's exchange / epilogue / cluster synchronisation overlaps the other group's MMA main
+// loop.  The virtual clusters synchronise with mbarriers (remote arrive, release/acquire at cluster scope); the
+// hardware cluster barrier is only used at kernel start and end.  256 TMEM columns per virtual CTA = 2 output chunks
+// x 2 row tiles, hence 9 CTAs per 256-row group (non-portable cluster size).  The (EW = 8, NV = 1) instantiation is the
+// one-group-per-SM variant (up to 384 columns, 6 CTAs per group).
 #include <stdlib.h>
 #include <string.h>
 
 #include "lcn_internal.cuh"
 #include "lcn_tc_ptx.cuh"
 
-#define ST_THREADS 320
-#define ST_EPI_THREADS 256
 #define ST_MAX_STAGES 4
 #define ST_A_BYTES 16384
 #define ST_B_BYTES 8192
-#define ST_STAGE_BYTES 65536   // TPG*16 KB of A + up to 32/48 KB of weight blocks (TPG=2: <=4, TPG=1: <=6 chunks)
 #define ST_MAX_COLS 384        // output columns per CTA: chunks*64
 #define ST_MAX_RUN 4           // chunks per MMA (N <= 256)
+#define ST_MAX_NS 9            // CTAs per cluster
 
 // optional timeline (clock64) of cluster 0 / CTA 0 over its first group: enabled with -DLCN_TC_PROFILE
 #ifdef LCN_TC_PROFILE
 __device__ unsigned long long g_st_prof[512];
-#define ST_STAMP(i) do { if (blockIdx.x == 0 && grp_cnt == 1) g_st_prof[(i)] = clock64(); } while (0)
+#define ST_STAMP(i) do { if (blockIdx.x == 0 && vc == 0 && grp_cnt == 1) g_st_prof[(i)] = clock64(); } while (0)
 extern "C" int lcn_debug_read_stack_prof(unsigned long long* h_out) {
   return cudaMemcpyFromSymbol(h_out, g_st_prof, sizeof(g_st_prof)) == cudaSuccess ? 0 : -2;
 }
@@ -59,12 +67,15 @@ struct StackParams {
   uint32_t kmask[LCN_J];        // input joint -> bitmask of output joints with a block
   // MMA program of a mid layer per cluster rank: per K chunk the runs of present output chunks with equal
   // accumulate state -> (TMEM column offset, B descriptor offset, instruction descriptor, accumulate)
-  uint4 prog[8][LCN_J][ST_MAX_RUN];
-  uint8_t prog_cnt[8][LCN_J];
-  uint8_t sch_cnt[8][LCN_J];    // per rank and K chunk: number of present blocks of the rank's output range ...
-  uint16_t sch_slot[8][LCN_J];  // ... and the slot of the first one in the packed layer (k_pack_mid forward order)
-  int8_t oc_start[10];          // output chunks of CTA r: [oc_start[r], oc_start[r+1])  (balanced by block count)
+  uint4 prog[ST_MAX_NS][LCN_J][ST_MAX_RUN];
+  uint8_t prog_cnt[ST_MAX_NS][LCN_J];
+  uint8_t sch_cnt[ST_MAX_NS][LCN_J];    // per rank and K chunk: number of present blocks of the rank's output range ...
+  uint16_t sch_slot[ST_MAX_NS][LCN_J];  // ... and the slot of the first one in the packed layer (k_pack_mid forward order)
+  int8_t oc_start[ST_MAX_NS + 1];       // output chunks of CTA r: [oc_start[r], oc_start[r+1])  (balanced by block count)
   int n_lin, in_F, TPG, stages, mc, nnz, tmem_cols;
+  int stage_bytes;              // TPG*16 KB of A + Gmax*8 KB of weight blocks
+  int vc_bytes;                 // shared memory of one virtual CTA (stages + statistics), multiple of 1024
+  int cols;                     // Gmax*64: output columns per CTA
   int dbg;                      // LCN_STACK_DBG experiments: 1 = no MMAs, 2 = no A loads, 4 = no B loads (wrong results)
   int64_t n_rows;
   int bn_group, n_groups;
@@ -78,7 +89,31 @@ __device__ __forceinline__ void st_range(int r, int NC, int n, int* c0, int* G) 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barrier of the epilogue warps of virtual CTA `vc`
+template <int EW>
+__device__ __forceinline__ void epi_bar(int vc) { asm volatile("bar.sync %0, %1;" ::"r"(vc + 1), "n"(EW * 32) : "memory"); }
+// arrive (release, cluster scope) on the same mbarrier of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  const uint32_t remote = mapa_shared(bar, rank);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait on a local mbarrier whose arrivals come from other CTAs (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 26)) {
+      printf("lcn_stack: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 // column sums over the 32 rows (lanes) of a warp for 32 columns held one row per lane:
 // recursive halving, 31 shuffles; on return lane L holds the total of column L in a[0].
@@ -120,19 +155,34 @@ __device__ __forceinline__ float warp_colsum32(float* a, int lane) {
   return a[0];
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_constant__ StackParams p) {
+template <int EW, int NV>
+__global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __grid_constant__ StackParams p) {
+  constexpr int ST_EPI_THREADS = 32 * EW;
+  constexpr int VT = 64 + 32 * EW;       // threads of one virtual CTA
+  constexpr int HSTEP = EW / 4;          // epilogue warps per TMEM lane quarter
+  constexpr int NBAR = 2 * ST_MAX_STAGES + 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * ST_MAX_STAGES + 2];
+  __shared__ __align__(8) uint64_t bars_all[NV * NBAR];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float colS[4][ST_MAX_COLS], colQ[4][ST_MAX_COLS];   // per TMEM lane quarter (fixed-order sum: deterministic)
-  __shared__ __align__(16) float colA[ST_MAX_COLS], colB[ST_MAX_COLS];
-  __shared__ __align__(8) float2 stat_all[LCN_J * 64];   // per (joint, channel): (mean, M2) of the group's valid rows
 
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int vc = __shfl_sync(0xffffffffu, (int)(threadIdx.x / VT), 0);     // virtual CTA of this warp
+  const int vtid = (int)threadIdx.x - vc * VT;
+  uint64_t* bars = bars_all + vc * NBAR;
+  const uint32_t sbase = ((smem_u32(smem_raw) + 1023u) & ~1023u) + (uint32_t)vc * (uint32_t)p.vc_bytes;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int ST_STAGE_BYTES = p.stage_bytes;
+  const int NCOL = p.cols;
+  // dedicated (never aliased with the pipeline stages: stat_all is written by the other CTAs of the cluster at any time)
+  float2* stat_all = reinterpret_cast<float2*>(sgen + (size_t)p.stages * ST_STAGE_BYTES);   // per (joint, channel): (mean, M2)
+  float* colA = reinterpret_cast<float*>(stat_all + LCN_J * 64);
+  float* colB = colA + NCOL;
+  // epilogue scratch inside the (then idle) pipeline stages: per-warp 32x33 transpose tiles, then the per-lane-quarter
+  // column sums (fixed-order sum: deterministic)
+  float* colS = reinterpret_cast<float*>(sgen) + EW * (32 * 33);
+  float* colQ = colS + 4 * NCOL;
+  const int warp = __shfl_sync(0xffffffffu, vtid >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank(), NS = cluster_nctarank();
-  const uint32_t cid = cluster_id_x(), ncl = cluster_nid_x();
+  const uint32_t cid = cluster_id_x() * NV + vc, ncl = cluster_nid_x() * NV;     // virtual cluster id / count
   const int TPG = p.TPG, S = p.stages;
   const int Kin = LCN_J * p.in_F;
   const uint32_t B_OFF = (uint32_t)TPG * ST_A_BYTES;
@@ -140,22 +190,27 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
   const int oc0 = p.oc_start[rank], G = p.oc_start[rank + 1] - oc0;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[ST_MAX_STAGES]);
   const uint32_t tfull = smem_u32(&bars[2 * ST_MAX_STAGES]), xfull = smem_u32(&bars[2 * ST_MAX_STAGES + 1]);
+  // virtual-cluster barriers: one arrival per CTA of the cluster.  xs1: every CTA has written its BN statistics into
+  // every stat_all;  xs2: every CTA has finished the layer (A_l stored, TMEM and pipeline stages free)
+  const uint32_t xs1 = smem_u32(&bars[2 * ST_MAX_STAGES + 2]), xs2 = smem_u32(&bars[2 * ST_MAX_STAGES + 3]);
 
-  if (threadIdx.x == 0) {
+  if (vtid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, p.mc ? NS : 1u);
     }
     mbar_init(tfull, 1);
     mbar_init(xfull, ST_EPI_THREADS);
+    mbar_init(xs1, NS);
+    mbar_init(xs2, NS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), (uint32_t)p.tmem_cols);
+  if (warp == 1 && vc == 0) tmem_alloc(smem_u32(&tmem_base_s), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   cluster_sync_all();                       // barrier inits are visible to every CTA of the cluster
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = tmem_base_s + (uint32_t)vc * (uint32_t)(p.tmem_cols / NV);
 
   __nv_bfloat16* buf0 = p.scratch + (size_t)cid * 2 * TPG * LCN_J * 8192;
   __nv_bfloat16* buf1 = buf0 + (size_t)TPG * LCN_J * 8192;
@@ -164,7 +219,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
   // kept incrementally -- a runtime modulo / division per iteration costs ~200 cycles of the issuing warps
   int st_s = 0;
   uint32_t st_ph = 0;
-  uint32_t layer_cnt = 0, grp_cnt = 0;
+  uint32_t layer_cnt = 0, grp_cnt = 0, bn_cnt = 0;
 
   for (int g = (int)cid; g < p.n_groups; g += (int)ncl, ++grp_cnt) {
     for (int l = 0; l < p.n_lin; ++l, ++layer_cnt) {
@@ -181,6 +236,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
       if (warp == 0) {
         // ===================== TMA producer =====================
         // warp-uniform like the MMA issuer: addresses come from kernel parameters / loop counters, one elected lane issues
+        // every CTA of the virtual cluster has finished the previous layer: A_{l-1} is in L2, all stages are free
+        if (layer_cnt > 0) mbar_wait_cluster(xs2, (layer_cnt - 1) & 1u);
         if (first) {
           const int s = st_s;
           const uint32_t ph = st_ph;
@@ -327,7 +384,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
             if (++s == S) { s = 0; ph ^= 1u; }
           }
 #ifdef LCN_TC_PROFILE
-          if (blockIdx.x == 0 && grp_cnt == 1) {
+          if (blockIdx.x == 0 && vc == 0 && grp_cnt == 1) {
             if (lane == 0) g_st_prof[16 * l + 11] = acc_wait;
             if (acc_issue) { g_st_prof[16 * l + 13] = acc_issue; g_st_prof[16 * l + 14] = acc_commit; }
           }
@@ -337,8 +394,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
         __syncwarp();
       } else {
         // ===================== epilogue: 8 warps =====================
-        const int e = threadIdx.x - 64;
-        const int lq = warp & 3, hset = (warp - 2) >> 2;
+        const int e = vtid - 64;
+        // TMEM lane quarter of a warp = its hardware warp index % 4 (not the index inside the virtual CTA)
+        const int lq = (int)(threadIdx.x >> 5) & 3, hset0 = (warp - 2) >> 2;
         const int row = lq * 32 + lane;
         const uint32_t tlane = (uint32_t)(lq * 32) << 16;
         if (first) {
@@ -346,7 +404,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
           const int s1 = st_s + 1 >= S ? st_s + 1 - S : st_s + 1, s2 = st_s + 2 >= S ? st_s + 2 - S : st_s + 2;
           uint8_t* xh = sgen + s1 * ST_STAGE_BYTES;
           uint8_t* xl = sgen + s2 * ST_STAGE_BYTES;
-          for (int t = e >> 7; t < TPG; t += 2) {
+          for (int t = e >> 7; t < TPG; t += ST_EPI_THREADS / 128) {
             const int r = e & 127;
             const int rin = t * LCN_TILE + r;
             const int64_t src = (int64_t)g * p.bn_group + rin;
@@ -378,47 +436,54 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
         // one warp polls the accumulator-ready barrier, the other seven block at a hardware barrier: 256 threads
         // spinning on mbarrier.try_wait slow down every barrier operation of the main loop (measured: 4x)
         if (warp == 2) mbar_wait(tfull, layer_cnt & 1u);
-        epi_bar();
+        epi_bar<EW>(vc);
         tc_fence_after();
         if (e == 0) ST_STAMP(16 * l + 1);
         if (!head) {
           // ---- pass 1: per-column sum / sum of squares of the accumulators over the group's valid rows ----
           // (32x32 transpose through a per-warp scratch in the idle pipeline stages: lane = row writes, lane = column sums)
           float* scr = reinterpret_cast<float*>(sgen) + (warp - 2) * (32 * 33);
-          for (int q = 0; q < G; ++q) {
-            float cs = 0.f, cq = 0.f;
-            for (int t = 0; t < TPG; ++t) {
-              uint32_t v[32];
-              tmem_ld32(tmem_base + tlane + (uint32_t)(t * G + q) * 64 + hset * 32, v);
-              const bool valid = t * LCN_TILE + row < p.bn_group;
-              __syncwarp();
+          for (int q = 0; q < G; ++q)
+            for (int hset = hset0; hset < 2; hset += HSTEP) {
+              float cs = 0.f, cq = 0.f;
+              for (int t = 0; t < TPG; ++t) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + tlane + (uint32_t)(t * G + q) * 64 + hset * 32, v);
+                const bool valid = t * LCN_TILE + row < p.bn_group;
+                __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = valid ? __uint_as_float(v[i]) : 0.f;
-              __syncwarp();
+                for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = valid ? __uint_as_float(v[i]) : 0.f;
+                __syncwarp();
 #pragma unroll
-              for (int r = 0; r < 32; ++r) {
-                const float a = scr[r * 33 + lane];
-                cs += a;
-                cq = fmaf(a, a, cq);
+                for (int r = 0; r < 32; ++r) {
+                  const float a = scr[r * 33 + lane];
+                  cs += a;
+                  cq = fmaf(a, a, cq);
+                }
               }
+              colS[lq * NCOL + q * 64 + hset * 32 + lane] = cs;
+              colQ[lq * NCOL + q * 64 + hset * 32 + lane] = cq;
             }
-            colS[lq][q * 64 + hset * 32 + lane] = cs;
-            colQ[lq][q * 64 + hset * 32 + lane] = cq;
-          }
-          epi_bar();
+          epi_bar<EW>(vc);
           if (e == 0) ST_STAMP(16 * l + 2);
           const float* bias = p.params + p.b_off[l];
           for (int c = e; c < G * 64; c += ST_EPI_THREADS) {
             // Z = acc + bias: mean = bias + S/n, M2 = Q - S^2/n  (shift by the bias keeps the cancellation small)
-            const float Ssum = (colS[0][c] + colS[1][c]) + (colS[2][c] + colS[3][c]);
-            const float Qsum = (colQ[0][c] + colQ[1][c]) + (colQ[2][c] + colQ[3][c]);
+            const float Ssum = (colS[c] + colS[NCOL + c]) + (colS[2 * NCOL + c] + colS[3 * NCOL + c]);
+            const float Qsum = (colQ[c] + colQ[NCOL + c]) + (colQ[2 * NCOL + c] + colQ[3 * NCOL + c]);
             const float ma = Ssum * inv_n;
             const float mean_c = __ldg(bias + oc0 * 64 + c) + ma;
             const float m2 = fmaxf(Qsum - Ssum * ma, 0.f);
             const uint32_t la = smem_u32(&stat_all[oc0 * 64 + c]);
             for (uint32_t r = 0; r < NS; ++r) st_cluster_f32x2(mapa_shared(la, r), mean_c, m2);
           }
-          cluster_sync_all();                                   // #1: every CTA holds the 17 x 64 column statistics
+          epi_bar<EW>(vc);
+          if (warp == 2) {
+            if (lane < (int)NS) mbar_arrive_cluster(xs1, (uint32_t)lane);
+            mbar_wait_cluster(xs1, bn_cnt & 1u);                 // #1: every CTA holds the 17 x 64 column statistics
+          }
+          ++bn_cnt;
+          epi_bar<EW>(vc);
           if (e == 0) ST_STAMP(16 * l + 3);
           for (int c = e; c < G * 64; c += ST_EPI_THREADS) {
             // BatchNormalization over batch x joints, biased variance, eps 1e-3 (models_att.py:599-607)
@@ -437,14 +502,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
             colA[c] = sc;
             colB[c] = __ldg(bias + oc0 * 64 + c) * sc + __ldg(p.params + p.beta_off[l] + f) - mean * sc;
           }
-          epi_bar();
+          epi_bar<EW>(vc);
           // ---- pass 2: BN + LeakyReLU (+ residual) out of TMEM -> bf16 swizzled tiles in smem -> bulk store per tile ----
           const bool has_res = p.res[l] != 0;
           const int U = TPG * G;
           // A_{l-2} lives in the buffer this layer overwrites; written by this CTA's bulk stores -> bypass L1.
           // The residual of unit u+1 is fetched while unit u is processed.
+          // Work items of a warp: (unit u, 32-column half); one half per warp with 8 epilogue warps, both with 4.
+          constexpr int NH = 2 / HSTEP;
           uint4 rr[4], rn[4];
-          auto res_load = [&](int u, uint4* dst) {
+          auto res_load = [&](int it, uint4* dst) {
+            const int u = it / NH, hset = hset0 + (it - u * NH) * HSTEP;
             const int t = u / G, q = u - t * G;
             const uint8_t* rrow = reinterpret_cast<const uint8_t*>(aout) + (((size_t)t * LCN_J + oc0 + q) * 128 + row) * 128;
 #pragma unroll
@@ -452,11 +520,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
           };
           if (has_res) res_load(0, rr);
           for (int t = 0; t < TPG; ++t) {
-            for (int q = 0; q < G; ++q) {
-              const int u = t * G + q;
+            for (int it = t * G * NH; it < (t + 1) * G * NH; ++it) {
+              const int u = it / NH, hset = hset0 + (it - u * NH) * HSTEP;
+              const int q = u - t * G;
               uint32_t v[32];
               tmem_ld32_nowait(tmem_base + tlane + (uint32_t)u * 64 + hset * 32, v);
-              if (has_res && u + 1 < U) res_load(u + 1, rn);
+              if (has_res && it + 1 < U * NH) res_load(it + 1, rn);
               tmem_ld_wait();
               float f[32];
               const float4* a4 = reinterpret_cast<const float4*>(colA + q * 64 + hset * 32);
@@ -504,7 +573,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
             }
             if (t == TPG - 1) tc_fence_before();
             fence_proxy_async();
-            epi_bar();
+            epi_bar<EW>(vc);
             if (warp == 2) {
               if (t == TPG - 1 && lane == 0) ST_STAMP(16 * l + 4);
               if (elect_one()) {
@@ -522,6 +591,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
                 }
               }
               __syncwarp();
+              if (t == TPG - 1 && lane < (int)NS) mbar_arrive_cluster(xs2, (uint32_t)lane);     // #2 (this CTA's part)
             }
           }
         } else if (t_hi > t_lo) {
@@ -530,43 +600,45 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_lcn_stack(const __grid_consta
           const int rin = t * LCN_TILE + row;
           const int64_t src = (int64_t)g * p.bn_group + rin;
           const bool ok = rin < p.bn_group && src < p.n_rows;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + tlane + hset * 32, v);
-          for (int k = 1; k < 2; ++k) {
-            uint32_t w[32];
-            tmem_ld32(tmem_base + tlane + (uint32_t)k * 64 + hset * 32, w);
+          for (int hset = hset0; hset < 2; hset += HSTEP) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + tlane + hset * 32, v);
+            {
+              uint32_t w[32];
+              tmem_ld32(tmem_base + tlane + 64u + hset * 32, w);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
-          }
-          if (ok) {
-            const float* bias = p.params + p.b_off[l];
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+            }
+            if (ok) {
+              const float* bias = p.params + p.b_off[l];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = hset * 32 + i;
-              if (c < 51) {
-                float val = __uint_as_float(v[i]) + __ldg(bias + c);
-                const int j = c / 3, cc = c - j * 3;
-                if (cc < 2) val += __ldg(p.x + src * Kin + j * p.in_F + cc);
-                p.out[src * 51 + c] = val;
+              for (int i = 0; i < 32; ++i) {
+                const int c = hset * 32 + i;
+                if (c < 51) {
+                  float val = __uint_as_float(v[i]) + __ldg(bias + c);
+                  const int j = c / 3, cc = c - j * 3;
+                  if (cc < 2) val += __ldg(p.x + src * Kin + j * p.in_F + cc);
+                  p.out[src * 51 + c] = val;
+                }
               }
             }
           }
           tc_fence_before();
         }
+        if (head) {
+          epi_bar<EW>(vc);
+          if (warp == 2 && lane < (int)NS) mbar_arrive_cluster(xs2, (uint32_t)lane);           // #2 (head layer)
+        }
+        if (e == 0) ST_STAMP(16 * l + 6);
       }
-      // warps 0/1 take part in the BN-statistics cluster barrier as well (every thread of the cluster arrives)
-      if (warp < 2 && !head) cluster_sync_all();
-      cluster_sync_all();                                       // #2: A_l is complete, TMEM and stages are free
-      tc_fence_after();
-      if (threadIdx.x == 64) ST_STAMP(16 * l + 6);
-      if (threadIdx.x == 64 && l == 0) { ST_STAMP(500); }
       for (int a = 0; a < n_it; ++a)
         if (++st_s == S) { st_s = 0; st_ph ^= 1u; }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  cluster_sync_all();       // no CTA exits while another one may still write into its shared memory / arrive on its barriers
+  if (warp == 1 && vc == 0) tmem_dealloc(tmem_base_s, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -603,13 +675,108 @@ static void stack_partition(const lcn_model* m, int ns, int gmax, int8_t* oc_sta
   for (int i = 0; i < ns; ++i) oc_start[i + 1] = (int8_t)(oc_start[i] + sizes[i]);
 }
 
-static void stack_config(int tpg, int* ns, int* stages, int* mc) {
-  int n = env_int("LCN_STACK_NS", tpg == 2 ? 6 : 3);
-  int gmax = (LCN_J + n - 1) / n;
-  if (n < 1 || n > 8 || gmax > (tpg == 2 ? 4 : 6)) n = tpg == 2 ? 6 : 3;
-  *ns = n;
-  *stages = 3;
-  *mc = env_int("LCN_STACK_MC", 1) ? 1 : 0;
+struct StackCfg {
+  int ns;        // CTAs per cluster (= per BatchNorm group)
+  int gmax;      // output chunks per CTA (upper bound)
+  int stages;    // pipeline stages
+  int mc;        // multicast the activation tiles over the cluster
+  int nv;        // virtual CTAs (BN groups in flight) per CTA: 2 -> <EW=4, NV=2> kernel, 1 -> <EW=8, NV=1>
+  size_t vc_bytes;
+  int tmem_cols;
+  int stage_bytes;
+  size_t smem;   // dynamic shared memory per CTA
+};
+
+static size_t stack_vc_bytes(const StackCfg& c) {
+  size_t b = (size_t)c.stages * c.stage_bytes + LCN_J * 64 * sizeof(float2) + 2 * (size_t)c.gmax * 64 * sizeof(float);
+  return (b + 1023) & ~(size_t)1023;
+}
+
+static void stack_fill(StackCfg* c, int tpg) {
+  c->gmax = (LCN_J + c->ns - 1) / c->ns;
+  const int cols = tpg * c->gmax * 64;      // per virtual CTA (the head layer needs 128)
+  const int per_vc = cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  c->tmem_cols = per_vc * c->nv;             // > 512: rejected by the caller
+  c->stage_bytes = tpg * ST_A_BYTES + c->gmax * ST_B_BYTES;
+  c->vc_bytes = stack_vc_bytes(*c);
+  c->smem = c->nv * c->vc_bytes + 1024;
+}
+
+template <int EW, int NV>
+static int stack_active_clusters(const StackCfg& c, int sm_count) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(k_lcn_stack<EW, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lcn_stack<EW, NV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      if (getenv("LCN_STACK_VERBOSE")) fprintf(stderr, "lcn_stack: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+      (void)cudaGetLastError();
+      return 0;
+    }
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)c.ns;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NV * (64 + 32 * EW));
+  cfg.dynamicSmemBytes = c.smem;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)(sm_count / c.ns * c.ns));
+  int active = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&active, k_lcn_stack<EW, NV>, &cfg);
+  if (getenv("LCN_STACK_VERBOSE"))
+    fprintf(stderr, "lcn_stack: occupancy query EW=%d NV=%d ns=%d smem=%zu -> %s, %d active clusters\n", EW, NV, c.ns, c.smem,
+            cudaGetErrorString(e), active);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return active;
+}
+
+// Configuration for `tpg` row tiles per BatchNorm group; `clusters` = how many clusters the device keeps resident.
+// Decided once per (tpg) and cached: the occupancy query needs the device, the workspace layout needs the answer.
+static StackCfg stack_config(int tpg, int sm_count, int* clusters) {
+  static StackCfg cache[3];
+  static int cache_cl[3] = {0, 0, 0};
+  if (cache_cl[tpg]) {
+    *clusters = cache_cl[tpg];
+    return cache[tpg];
+  }
+  StackCfg c;
+  memset(&c, 0, sizeof(c));
+  c.mc = env_int("LCN_STACK_MC", 1) ? 1 : 0;
+  int active = 0;
+  if (env_int("LCN_STACK_NV", 2) == 2) {
+    // two groups per SM: <= 256 TMEM columns each
+    c.nv = 2;
+    c.ns = env_int("LCN_STACK_NS", tpg == 2 ? 9 : 5);
+    c.stages = env_int("LCN_STACK_STAGES", 2);
+    stack_fill(&c, tpg);
+    if (c.ns >= 1 && c.ns <= ST_MAX_NS && c.tmem_cols <= 512 && c.smem <= 231424) active = stack_active_clusters<4, 2>(c, sm_count);
+  }
+  if (active == 0) {
+    c.nv = 1;
+    c.ns = env_int("LCN_STACK_NS1", tpg == 2 ? 6 : 3);
+    if (c.ns < 1 || c.ns > ST_MAX_NS || (LCN_J + c.ns - 1) / c.ns > (tpg == 2 ? 4 : 6)) c.ns = tpg == 2 ? 6 : 3;
+    c.stages = 3;
+    stack_fill(&c, tpg);
+    active = stack_active_clusters<8, 1>(c, sm_count);
+    if (active <= 0) active = sm_count / c.ns;
+  }
+  const int want = sm_count / c.ns;
+  if (active > want) active = want;
+  if (getenv("LCN_STACK_VERBOSE"))
+    fprintf(stderr, "lcn_stack: tpg=%d ns=%d gmax=%d stages=%d mc=%d nv=%d tmem=%d stage=%d smem=%zu clusters=%d\n", tpg, c.ns,
+            c.gmax, c.stages, c.mc, c.nv, c.tmem_cols, c.stage_bytes, c.smem, active);
+  cache[tpg] = c;
+  cache_cl[tpg] = active;
+  *clusters = active;
+  return c;
 }
 
 bool lcn_stack_eligible(const lcn_model* m, int bn_group, int training) {
@@ -620,19 +787,19 @@ bool lcn_stack_eligible(const lcn_model* m, int bn_group, int training) {
 }
 
 size_t lcn_stack_scratch_bytes(const lcn_model* m, int bn_group) {
-  int tpg = (bn_group + LCN_TILE - 1) / LCN_TILE, ns, st, mc;
-  stack_config(tpg, &ns, &st, &mc);
-  size_t clusters = (size_t)(m->sm_count / ns);
-  return clusters * 2 * tpg * LCN_J * ST_A_BYTES;
+  int tpg = (bn_group + LCN_TILE - 1) / LCN_TILE, clusters = 0;
+  const StackCfg c = stack_config(tpg, m->sm_count, &clusters);
+  return (size_t)clusters * c.nv * 2 * tpg * LCN_J * ST_A_BYTES;
 }
 
 int lcn_stack_forward(const lcn_model* m, const WsLayout& lay, const float* params, char* ws, const float* x,
                       float* out, void* taps, cudaStream_t st) {
   StackParams p;
   memset(&p, 0, sizeof(p));
-  int ns, stages, mc;
   const int tpg = lay.tiles_per_group;
-  stack_config(tpg, &ns, &stages, &mc);
+  int max_clusters = 0;
+  const StackCfg c = stack_config(tpg, m->sm_count, &max_clusters);
+  const int ns = c.ns;
   p.x = x;
   p.out = out;
   p.params = params;
@@ -649,7 +816,7 @@ int lcn_stack_forward(const lcn_model* m, const WsLayout& lay, const float* para
     p.res[l] = m->L[l].res_from >= 0 ? 1 : 0;
   }
   for (int a = 0; a < LCN_J; ++a) p.kmask[a] = m->sup.row[a];
-  stack_partition(m, ns, tpg == 2 ? 4 : 6, p.oc_start);
+  stack_partition(m, ns, c.gmax, p.oc_start);
   for (int r = 0; r < ns; ++r) {
     const int oc0 = p.oc_start[r], G = p.oc_start[r + 1] - oc0;
     uint32_t written = 0;
@@ -682,22 +849,18 @@ int lcn_stack_forward(const lcn_model* m, const WsLayout& lay, const float* para
   p.n_lin = m->n_lin;
   p.in_F = m->d.in_F;
   p.TPG = tpg;
-  p.stages = stages;
-  p.mc = mc;
+  p.stages = c.stages;
+  p.mc = c.mc;
   p.nnz = m->nnz;
-  p.tmem_cols = 512;
+  p.tmem_cols = c.tmem_cols;
+  p.stage_bytes = c.stage_bytes;
+  p.vc_bytes = (int)c.vc_bytes;
+  p.cols = c.gmax * 64;
   p.dbg = env_int("LCN_STACK_DBG", 0);
   p.n_rows = lay.n_rows;
   p.bn_group = lay.bn_group;
   p.n_groups = lay.n_groups;
 
-  const size_t smem = (size_t)stages * ST_STAGE_BYTES + 1024;
-  static bool attr = false;
-  if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_lcn_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  int max_clusters = m->sm_count / ns;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute at[1];
@@ -705,21 +868,18 @@ int lcn_stack_forward(const lcn_model* m, const WsLayout& lay, const float* para
   at[0].val.clusterDim.x = (unsigned)ns;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(ST_THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(c.nv == 2 ? 384 : 320);
+  cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cfg.gridDim = dim3((unsigned)(max_clusters * ns));
-  int active = 0;
-  if (cudaOccupancyMaxActiveClusters(&active, k_lcn_stack, &cfg) == cudaSuccess && active > 0) {
-    if (active < max_clusters) max_clusters = active;
-  } else {
-    (void)cudaGetLastError();
-  }
-  int clusters = lay.n_groups < max_clusters ? lay.n_groups : max_clusters;
-  if (getenv("LCN_STACK_VERBOSE")) fprintf(stderr, "lcn_stack: ns=%d stages=%d mc=%d clusters=%d (active %d) groups=%d\n", ns, stages, mc, clusters, active, lay.n_groups);
+  const int need = (lay.n_groups + c.nv - 1) / c.nv;
+  const int clusters = need < max_clusters ? need : max_clusters;
   cfg.gridDim = dim3((unsigned)(clusters * ns));
-  LCN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_lcn_stack, p));
+  if (c.nv == 2) {
+    LCN_CHECK_CUDA((cudaLaunchKernelEx(&cfg, k_lcn_stack<4, 2>, p)));
+  } else {
+    LCN_CHECK_CUDA((cudaLaunchKernelEx(&cfg, k_lcn_stack<8, 1>, p)));
+  }
   return LCN_OK;
 }

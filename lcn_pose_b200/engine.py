@@ -77,6 +77,11 @@ class LcnEngine:
         self.seed = 2019
         self._prepared = False
         self._fwd_geom = None
+        # device-resident step scalars (lcn_step_scalars: uint64 step, float lr_t, float reserved) + pinned staging
+        self.dyn_dev = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        self.dyn_pin = torch.zeros((64, 16), dtype=torch.uint8).pin_memory()   # ring: the host runs ahead of the GPU
+        self._dyn_ev = [None] * 64
+        self._graphs = {}
 
     def __del__(self):
         try:
@@ -163,8 +168,9 @@ class LcnEngine:
         self._prepared = True
 
     # ---- forward / train ------------------------------------------------------------------------
-    def forward(self, x, bn_group=None, training=False, dropout=0.0, out=None):
-        """x: [n, 17*in_F] float32 CUDA tensor.  Returns [n, 51] float32 (models_att.py:707-775)."""
+    def forward(self, x, bn_group=None, training=False, dropout=0.0, out=None, dyn=False):
+        """x: [n, 17*in_F] float32 CUDA tensor.  Returns [n, 51] float32 (models_att.py:707-775).
+        dyn=True: the dropout step counter is read from self.dyn_dev on the device (CUDA-graph replay)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         n = x.shape[0]
         bn_group = n if bn_group is None else int(bn_group)
@@ -175,7 +181,7 @@ class LcnEngine:
             out = torch.empty((n, J * 3), dtype=torch.float32, device=self.device)
         L.check(self.lib.lcn_model_forward(self.h, _ptr(self.params), _ptr(self.ws), size, _ptr(x), n, bn_group,
                                            int(training), float(dropout), self.seed, self.step + 1, _ptr(out),
-                                           self._stream()))
+                                           _ptr(self.dyn_dev) if dyn else C.c_void_p(0), self._stream()))
         self._fwd_geom = (n, bn_group, bool(training))
         return out
 
@@ -220,17 +226,87 @@ class LcnEngine:
                                                   _ptr(self.grads_raw), _ptr(g), self._stream()))
         return g
 
-    def adam(self, beta1=0.9, beta2=0.999, eps=1e-8):
-        """TF1 AdamOptimizer.apply_gradients (models_att.py:404-409) + weight re-preparation."""
-        self.step += 1
-        t = self.step
+    def adam(self, beta1=0.9, beta2=0.999, eps=1e-8, dyn=False):
+        """TF1 AdamOptimizer.apply_gradients (models_att.py:404-409) + weight re-preparation.
+        dyn=True: lr_t is read from self.dyn_dev on the device (CUDA-graph replay); self.step is not advanced."""
+        if not dyn:
+            self.step += 1
+        t = max(self.step, 1)
         lr = self.lr_at(t)
         lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
         L.check(self.lib.lcn_model_adam_step(self.h, _ptr(self.params), _ptr(self.adam_m), _ptr(self.adam_v),
                                              _ptr(self.ws), self.ws.numel(), _ptr(self.grads_raw), lr_t, beta1, beta2,
-                                             eps, self.regularization, self._stream()))
+                                             eps, self.regularization, _ptr(self.dyn_dev) if dyn else C.c_void_p(0),
+                                             self._stream()))
         self._prepared = True
         return lr
+
+    # ---- CUDA-graph train step ----------------------------------------------------------------
+    def _stage_scalars(self, t, beta1=0.9, beta2=0.999):
+        """Write lcn_step_scalars{step=t, lr_t} to the device (pinned staging, stream ordered)."""
+        lr = self.lr_at(t)
+        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        slot = t % 64
+        if self._dyn_ev[slot] is not None:
+            self._dyn_ev[slot].synchronize()          # the copy that last used this pinned slot has executed
+        buf = self.dyn_pin.numpy()[slot]
+        buf[0:8] = np.frombuffer(np.uint64(t).tobytes(), dtype=np.uint8)
+        buf[8:12] = np.frombuffer(np.float32(lr_t).tobytes(), dtype=np.uint8)
+        self.dyn_dev.copy_(self.dyn_pin[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._dyn_ev[slot] = ev
+        return lr
+
+    def train_step_graph(self, x, labels, dropout=0.0, allreduce=None):
+        """train_step() as CUDA-graph replays: the ~60 launches of one step (forward, loss, backward, chain rule,
+        Adam, weight re-preparation) are captured once per (batch shape, dropout, buffers) and replayed; the
+        per-step scalars (dropout counter, Adam step size) travel through 16 bytes of device memory.
+        `x` / `labels` must be the SAME device tensors every call (copy new batches into them).
+        allreduce: optional callable run between backward and Adam on the gradient bucket (data parallel);
+        then two graphs are replayed around it.  Returns (loss device scalar, learning rate used)."""
+        key = (x.data_ptr(), labels.data_ptr(), tuple(x.shape), float(dropout), allreduce is not None)
+        n = x.shape[0]
+        if key not in self._graphs:
+            self._ensure_ws(n, n, True)
+            if not self._prepared:
+                self.prepare()
+            out = torch.empty((n, J * 3), dtype=torch.float32, device=self.device)
+            self._stage_scalars(self.step + 1)
+            # warm-up on a side stream (first-call attribute setup must not happen under capture)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            saved = (self.params.clone(), self.adam_m.clone(), self.adam_v.clone())
+            with torch.cuda.stream(side):
+                self.forward(x, bn_group=n, training=True, dropout=dropout, out=out, dyn=True)
+                self.backward(x, labels, dropout)
+                self.adam(dyn=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self.params.copy_(saved[0]); self.adam_m.copy_(saved[1]); self.adam_v.copy_(saved[2])
+            self.prepare()
+            torch.cuda.synchronize(self.device)
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self.forward(x, bn_group=n, training=True, dropout=dropout, out=out, dyn=True)
+                self.backward(x, labels, dropout)
+                if allreduce is None:
+                    self.adam(dyn=True)
+            g2 = None
+            if allreduce is not None:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    self.adam(dyn=True)
+            self._graphs[key] = (g1, g2, out)
+        g1, g2, _ = self._graphs[key]
+        lr = self._stage_scalars(self.step + 1)
+        g1.replay()
+        if g2 is not None:
+            allreduce(self.grads_raw)
+            g2.replay()
+        self.step += 1
+        self._prepared = True
+        self._fwd_geom = (n, n, True)
+        return self.loss_dev, lr
 
     def train_step(self, x, labels, dropout=0.0, out=None):
         """One sess.run([op_train, ...]) of the reference (models_att.py:210-212): fwd, loss, bwd, Adam.

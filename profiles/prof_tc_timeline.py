@@ -24,3 +24,21 @@ for cold in (0,1):
         b = 16+4*it
         if t[b]==0: break
         print(' it', it, 'empty_ok', t[b]-t0, 'issued', t[b+1]-t0, 'full_ok', t[b+2]-t0, 'mma_issued', t[b+3]-t0)
+# kernel duration by CUDA events: back to back (warm L2) and with an L2 flush before every launch
+def timed(flush_each, reps=20):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        if flush_each: flush.zero_()
+        a.record()
+        L.check(eng.lib.lcn_layer_gemm(eng.h, eng.params.data_ptr(), eng.ws.data_ptr(), eng.ws.numel(), 4096, 4096, 2, 0, st))
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+    return ts[0], ts[len(ts) // 2]
+print("events us (min, median): warm", timed(False), "flushed", timed(True))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(50):
+    L.check(eng.lib.lcn_layer_gemm(eng.h, eng.params.data_ptr(), eng.ws.data_ptr(), eng.ws.numel(), 4096, 4096, 2, 0, st))
+b.record(); torch.cuda.synchronize()
+print("50 back-to-back launches: us per launch", a.elapsed_time(b) * 1e3 / 50)

@@ -201,3 +201,24 @@ def test_library_is_the_loaded_native_code():
     assert "liblcn_b200.so" in maps
     assert torch.cuda.get_device_capability(0)[0] == 10
     assert L.load().lcn_version()
+
+
+def test_graph_replayed_train_steps_equal_eager_steps():
+    """CUDA-graph replay of the train step (device-resident step scalars, lcn_step_scalars) reproduces the eager call
+    sequence: same Philox dropout counters, same TF1 Adam step sizes -> identical losses; parameters agree to float
+    rounding (the weight-gradient kernel accumulates row splits with floating-point reductions in arrival order)."""
+    import torch
+    n = 384
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    for path in ("bf16", "fp32"):
+        eng_a, _, _ = make_pair(L=1, knn=2, path=path)
+        eng_b, _, _ = make_pair(L=1, knn=2, path=path)
+        la, lb = [], []
+        for _ in range(4):
+            la.append(float(eng_a.train_step(xd, yd, dropout=0.25)[0].item()))
+            lb.append(float(eng_b.train_step_graph(xd, yd, dropout=0.25)[0].item()))
+        assert la == lb, (path, la, lb)
+        assert eng_a.step == eng_b.step == 4
+        assert torch.allclose(eng_a.params, eng_b.params, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(eng_a.adam_v, eng_b.adam_v, rtol=1e-3, atol=1e-12)
