@@ -44,14 +44,46 @@ def measured_peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json names the report); None when absent."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled during the timed region: NVML (about 1 ms per sample) when pynvml is
+    importable, else nvidia-smi (about 100 ms per sample)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, False, []
 
     def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            bits = [(N.nvmlClocksEventReasonHwSlowdown if hasattr(N, "nvmlClocksEventReasonHwSlowdown") else N.nvmlClocksThrottleReasonHwSlowdown),
+                    (N.nvmlClocksEventReasonHwThermalSlowdown if hasattr(N, "nvmlClocksEventReasonHwThermalSlowdown") else N.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    (N.nvmlClocksEventReasonSwThermalSlowdown if hasattr(N, "nvmlClocksEventReasonSwThermalSlowdown") else N.nvmlClocksThrottleReasonSwThermalSlowdown),
+                    (N.nvmlClocksEventReasonSwPowerCap if hasattr(N, "nvmlClocksEventReasonSwPowerCap") else N.nvmlClocksThrottleReasonSwPowerCap)]
+            get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = get(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits])
+                time.sleep(0.002)
+            return
+        except Exception:
+            pass
+        self.run_smi()
+
+    def run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
@@ -163,9 +195,7 @@ def run_gpu(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     n_bn = 1 + 2 * LAYERS
 
-    def allreduce(bucket):
-        dist.all_reduce(bucket)                     # one bucket: raw gradient of every tensor
-        bucket.div_(world)
+    from lcn_pose_b200.dist import average_gradient_bucket as allreduce   # one bucket: raw gradient of every tensor
 
     def step(xx, yy):
         if args.no_graph:
@@ -231,11 +261,41 @@ def run_gpu(args, rank, world, local_rank):
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    # ---- BASELINE.json configs[2] (secondary numbers, not the headline): inference at BN group 256 + Protocol-1/2
+    # evaluation, pose batch sharded over the ranks with no communication on the data path ----
+    inf = None
+    if args.infer_poses > 0:
+        from lcn_pose_b200.engine import eval_mpjpe
+        n_inf = (args.infer_poses // 256) * 256
+        eng2 = LcnEngine(F=F, in_F=2, num_layers=LAYERS, mask_type="locally_connected",
+                         neighbour_matrix=O.get_neighbour_matrix_by_hand(knn=KNN), path=args.path, device=f"cuda:{local_rank}")
+        eng2.init_params(seed=42)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        xi = torch.rand((n_inf, 34), device=dev, generator=gen) - 0.5
+        oi = torch.empty((n_inf, 51), device=dev)
+        gt = torch.randn((n_inf, 17, 3), device=dev, generator=gen) * 300 + torch.tensor([0., 0., 4500.], device=dev)
+        box = torch.tensor([0., 0., 999., 999.], device=dev).repeat(n_inf, 1)
+        cam = torch.tensor([1145.05, 1143.78, 512.54, 515.45], device=dev).repeat(n_inf, 1)
+        rd = gt[:, 0, 2].contiguous()
+
+        def best_ms(fn, reps=3):
+            fn()
+            barrier()
+            evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for a, b in evs2:
+                a.record(); fn(); b.record()
+            barrier()
+            return min(a.elapsed_time(b) for a, b in evs2)
+        f_ms = best_ms(lambda: eng2.forward(xi, bn_group=256, out=oi))
+        pred = oi.view(n_inf, 17, 3)
+        p1_ms = best_ms(lambda: eval_mpjpe(pred, gt, box, cam, rd, False, want_err=False))
+        p2_ms = best_ms(lambda: eval_mpjpe(pred, gt, box, cam, rd, True, want_err=False))
+        inf = [f_ms, p1_ms, p2_ms]
     # ---- max over ranks ----
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s] + (inf or [0, 0, 0]), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = t.tolist()
+    dev_ms, e2e_s, f_ms, p1_ms, p2_ms = t.tolist()
     if rank == 0:
         tf_burst, tf_sust, hbm, how = measured_peaks()
         value = world * BATCH * args.steps / (dev_ms * 1e-3)
@@ -254,8 +314,17 @@ def run_gpu(args, rank, world, local_rank):
                 "step_tensor_frac": value / world * TRAIN_FLOP_PER_POSE / (tf_sust * 1e12),
                 "roofline": {"bound": "tensor", "kernel": "mid-layer forward GEMM (block-sparse, 175 nonzero 64x64 blocks)",
                              "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
-                             "traffic": None, "peak_source": how, "ms_per_launch": gemm_ms},
+                             "traffic": ncu_traffic(), "peak_source": how, "ms_per_launch": gemm_ms},
                 "clocks": sampler.summary() if sampler else None}
+        if inf is not None:
+            tot = world * n_inf
+            line["inference"] = {
+                "workload": f"configs[2] shape: LCN knn={KNN} layers={LAYERS} F={F} inference at BN group 256 + Protocol-1/2 "
+                            f"evaluation, {n_inf} synthetic poses per GPU resident in HBM, sharded by BN group, no collective",
+                "forward_poses_per_s": tot / (f_ms * 1e-3),
+                "forward_tensor_frac_burst": n_inf / (f_ms * 1e-3) * FWD_FLOP_PER_POSE / (tf_burst * 1e12),
+                "eval_p1_poses_per_s": tot / (p1_ms * 1e-3), "eval_p1_hbm_frac": n_inf * 444 / (p1_ms * 1e-3) / (hbm * 1e9),
+                "eval_p2_poses_per_s": tot / (p2_ms * 1e-3), "eval_p2_hbm_frac": n_inf * 444 / (p2_ms * 1e-3) / (hbm * 1e9)}
         # CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only)
         if world == 1 and not args.no_cpu_baseline:
             cb, cs = 1024, 8
@@ -271,12 +340,13 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default=os.environ.get("LCN_BENCH_PATH", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--dropout", type=float, default=0.25)     # params_help.py:166 training default
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--infer-poses", type=int, default=1 << 22, help="poses per GPU of the secondary inference+eval leg (0: skip)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -290,6 +290,15 @@ extern "C" int lcn_model_prepare_weights(lcn_model* m, const float* d_params, vo
   return lcn_launch_prepare(m, d_params, (char*)d_ws, lay, true, (cudaStream_t)stream);
 }
 
+bool lcn_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LCN_DISABLE_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,
                                  int64_t n_rows, int32_t bn_group, int training, float dropout_rate, uint64_t seed,
                                  uint64_t step, float* d_out, const lcn_step_scalars* d_dyn, void* stream) {

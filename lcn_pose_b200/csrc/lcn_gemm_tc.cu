@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ addend,
                                                         __nv_bfloat16* __restrict__ Y, float* __restrict__ part,
                                                         const __grid_constant__ TcParams p) {
+  lcn_pdl_trigger();
   constexpr int STAGE_BYTES = TC_A_BYTES + GMAX * TC_B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
   const uint32_t tmem_base = tmem_base_s;
   TC_STAMP(1);
 
@@ -365,7 +367,7 @@ static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const 
     LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm<GMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  k_tc_gemm<GMAX, STAGES><<<dim3(p.n_groups, tiles), TC_THREADS, smem, st>>>(A, W, bias, addend, Y, part, p);
+  lcn_launch(k_tc_gemm<GMAX, STAGES>, dim3(dim3(p.n_groups, tiles)), dim3(TC_THREADS), smem, st, A, W, bias, addend, Y, part, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
@@ -589,6 +591,7 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src, ui
 __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __restrict__ A,
                                                          const __nv_bfloat16* __restrict__ dZ,
                                                          float* __restrict__ dW, TcwParams p) {
+  lcn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TCW_STAGES + 1];
   __shared__ uint32_t tmem_base_s;
@@ -635,6 +638,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
   const uint32_t tmem_base = tmem_base_s;
 
   const int n_it = 2 * (t1 - t0);                  // two 64-row half tiles per 128-row tile
@@ -713,9 +717,16 @@ static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bflo
     units += (cnt + TC_G - 1) / TC_G;
   }
   p.tiles = tiles;
-  // two CTAs are resident per SM (~82 KB smem, <=256 TMEM columns each): give every CTA the smallest row
-  // range for which the whole grid is a single wave of 2*SMs slots
-  int slots = 2 * sm_count;
+  // One CTA is resident per SM (TMEM kernels: profiles/micro/occ.cu).  The row range per CTA is the smallest for
+  // which the grid has at most 2 x SMs CTAs: two waves of ~7-tile CTAs measured faster than one wave of 16-tile CTAs
+  // (0.820 vs 0.854 ms per train step) because ~54 units x 2 row splits fill only 108 of the 148 SMs.
+  // LCN_TCW_SLOTS overrides the slot count for experiments.
+  static int slots_env = -1;
+  if (slots_env < 0) {
+    const char* e = getenv("LCN_TCW_SLOTS");
+    slots_env = e ? atoi(e) : 0;
+  }
+  int slots = slots_env > 0 ? slots_env : 2 * sm_count;
   int tpc = 1;
   while (tpc < tiles && (long)units * ((tiles + tpc - 1) / tpc) > slots) ++tpc;
   p.tiles_per_cta = tpc;
@@ -726,7 +737,7 @@ static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bflo
     LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  k_tc_wgrad<<<dim3(units, splits), TC_THREADS, smem, st>>>(A, dZ, dW, p);
+  lcn_launch(k_tc_wgrad, dim3(dim3(units, splits)), dim3(TC_THREADS), smem, st, A, dZ, dW, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }

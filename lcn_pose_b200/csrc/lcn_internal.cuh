@@ -1,5 +1,6 @@
 // Internal definitions shared by the liblcn_b200 translation units (not part of the C ABI).
 #pragma once
+#include <string.h>
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -127,6 +128,48 @@ void lcn_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 #define LCN_CHECK_LAUNCH() LCN_CHECK_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the train / per-layer path starts with lcn_pdl_prologue():
+// it lets the NEXT kernel of the stream be scheduled onto SMs as they free up (griddepcontrol.launch_dependents) and
+// then waits until the PREVIOUS kernel has completed and flushed its memory (griddepcontrol.wait) before touching
+// global memory.  lcn_launch() sets the matching launch attribute.  ~60 short kernels make one train step: this hides
+// the per-kernel launch latency and block ramp-up (measured: DESIGN.md section 6).  LCN_DISABLE_PDL=1 turns the
+// attribute off (the device-side instructions are then no-ops).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lcn_pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+// split form: trigger at kernel start, wait after the kernel's own setup (barrier init, TMEM allocation)
+__device__ __forceinline__ void lcn_pdl_trigger() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void lcn_pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+bool lcn_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline void lcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = lcn_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through LCN_CHECK_LAUNCH
+}
 #define LCN_REQUIRE(cond, ...)   \
   do {                           \
     if (!(cond)) {               \

@@ -62,11 +62,13 @@ __device__ __forceinline__ double block_reduce_sum_d(double v, double* sh /* >= 
 // weight preparation
 // ------------------------------------------------------------------------------------------------
 __global__ void k_zero_norm2(LayerScalars* sc, int n) {
+  lcn_pdl_prologue();
   if (threadIdx.x < n) sc[threadIdx.x].norm2 = 0.0;
 }
 
 // ||W_l||_F^2 of the full, unmasked matrix (tf.clip_by_norm, models_att.py:659)
 __global__ void k_sumsq(const float* __restrict__ params, LinTable lt, LayerScalars* sc) {
+  lcn_pdl_prologue();
   __shared__ double sh[32];
   int l = blockIdx.y;
   int64_t n4 = (int64_t)lt.Fi[l] * lt.Fo[l] * LCN_J * LCN_J / 4;
@@ -84,6 +86,7 @@ __global__ void k_sumsq(const float* __restrict__ params, LinTable lt, LayerScal
 __global__ void k_mask_scalars(const float* __restrict__ params, int64_t mask_off, SupportBits sup,
                                ConstMask cmask, int n_lin, int max_norm,
                                LayerScalars* sc, float* mask_out) {
+  lcn_pdl_prologue();
   int t = threadIdx.x;
   if (t < LCN_J * LCN_J) {
     int i = t / LCN_J, j = t % LCN_J;
@@ -111,6 +114,7 @@ __global__ void k_mask_scalars(const float* __restrict__ params, int64_t mask_of
 // dense masked effective weight of an edge layer: Wm = W * inv_norm * mask[i,j]
 __global__ void k_pack_edge(const float* __restrict__ w, int Fi, int Fo, const LayerScalars* sc, int l,
                             const float* __restrict__ mask, float* __restrict__ wm) {
+  lcn_pdl_prologue();
   int Kout = LCN_J * Fo;
   int64_t n = (int64_t)LCN_J * Fi * Kout;
   float inv = sc[l].inv_norm;
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ para
                                                   const float* __restrict__ mask, int F, int FC, int nnz,
                                                   float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
                                                   __nv_bfloat16* __restrict__ wp16b, int write32, int write16) {
+  lcn_pdl_prologue();
   __shared__ float tile[64][65];     // tile[fi][fo], scaled
   int mid = blockIdx.y, l = mid + 1;
   int sb = blockIdx.x;
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ para
 //   wl16b[kc]: B[n = channel][k = output column]                     (dgrad:    dA = dOut * Wm4^T)
 __global__ void k_pack_last16(const float* __restrict__ wm_last, __nv_bfloat16* __restrict__ wl16f,
                               __nv_bfloat16* __restrict__ wl16b) {
+  lcn_pdl_prologue();
   int kc = blockIdx.x;
   for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
     int n = e >> 6, k = e & 63;      // n: output column jc, k: channel within chunk
@@ -190,6 +196,7 @@ __global__ void k_pack_last16(const float* __restrict__ wm_last, __nv_bfloat16* 
 // bf16 image of the first layer's masked weight for the fused inference kernel: one 64x64 block per output
 // chunk, B[n = output column of the chunk][k = input feature (17*in_F used, zero padded to 64)]
 __global__ void k_pack_first16(const float* __restrict__ wm_first, int Kin, int P, __nv_bfloat16* __restrict__ wf16) {
+  lcn_pdl_prologue();
   int oc = blockIdx.x;
   for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
     int n = e >> 6, k = e & 63;
@@ -204,31 +211,31 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
   LinTable lt = make_lin(m);
   if (recompute_norm) {
-    k_zero_norm2<<<1, 32, 0, st>>>(sc, m->n_lin);
-    k_sumsq<<<dim3(64, m->n_lin), 256, 0, st>>>(params, lt, sc);
+    lcn_launch(k_zero_norm2, dim3(1), dim3(32), 0, st, sc, m->n_lin);
+    lcn_launch(k_sumsq, dim3(dim3(64, m->n_lin)), dim3(256), 0, st, params, lt, sc);
     LCN_CHECK_LAUNCH();
   }
   ConstMask cmask;
   memcpy(cmask.v, m->d.const_mask, sizeof(cmask.v));
-  k_mask_scalars<<<1, 320, 0, st>>>(params, m->mask_off, m->sup, cmask, m->n_lin, m->d.max_norm, sc, mask);
+  lcn_launch(k_mask_scalars, dim3(1), dim3(320), 0, st, params, m->mask_off, m->sup, cmask, m->n_lin, m->d.max_norm, sc, mask);
   LCN_CHECK_LAUNCH();
   int last = m->n_lin - 1;
-  k_pack_edge<<<64, 256, 0, st>>>(params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
+  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_first));
-  k_pack_edge<<<64, 256, 0, st>>>(params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
+  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_last));
   if (m->d.path == LCN_PATH_BF16) {
-    k_pack_last16<<<LCN_J * m->FC, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_wm_last),
+    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_last),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
     if (m->L[0].Kin <= 64)
-      k_pack_first16<<<LCN_J * m->FC, 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
+      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
                                                     m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
   }
   int n_mid = m->n_lin - 2;
   const bool use_tc = m->d.path == LCN_PATH_BF16 && lcn_tc_enabled();
   if (n_mid > 0) {
-    k_pack_mid<<<dim3(m->nnz * m->FC * m->FC, n_mid), 256, 0, st>>>(
+    lcn_launch(k_pack_mid, dim3(dim3(m->nnz * m->FC * m->FC, n_mid)), dim3(256), 0, st, 
         params, lt, make_pairs(m), m->sup, sc, mask, m->d.F, m->FC, m->nnz,
         reinterpret_cast<float*>(ws + lay.off_wp32), reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f),
         reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b), use_tc ? 0 : 1, use_tc ? 1 : 0);
@@ -263,6 +270,7 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
                                                      const float* __restrict__ wm, const float* __restrict__ bias,
                                                      T* __restrict__ Z, float* __restrict__ part, int P,
                                                      __nv_bfloat16* __restrict__ x16) {
+  lcn_pdl_prologue();
   constexpr int KIN = LCN_J * IN_F;
   __shared__ __align__(16) float xs[KIN][LCN_TILE];
   __shared__ unsigned char valid_s[LCN_TILE];
@@ -333,6 +341,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
                                                    const float* __restrict__ bias, const T* __restrict__ addend,
                                                    T* __restrict__ Y, float* __restrict__ part, JointLists lists,
                                                    int P, int FC, int bn_group, int gstride) {
+  lcn_pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                          // [128][65]
   float* Bs = smem + LCN_TILE * GS_APAD;     // [64][68]
@@ -453,6 +462,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, cons
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bn_finalize(const float* __restrict__ part, float* __restrict__ stat, int P,
                                                      int F, int tiles_per_group, int bn_group) {
+  lcn_pdl_prologue();
   __shared__ double sa[256];
   __shared__ double smean[2];
   int g = blockIdx.x, tid = threadIdx.x;
@@ -512,6 +522,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act(const T* __restrict__ Z, 
                                                        uint8_t* __restrict__ keepbits, int P, int F, int rows_pad,
                                                        int bn_group, int gstride, float rate, uint64_t seed,
                                                        uint64_t step, int layer, const lcn_step_scalars* __restrict__ dyn) {
+  lcn_pdl_prologue();
   __shared__ __align__(16) float s_sc[256], s_sh[256];
   if (dyn != nullptr) step = dyn->step;        // CUDA-graph replay: the step counter lives in device memory
   const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
@@ -611,6 +622,7 @@ __global__ void __launch_bounds__(128) k_last_layer(const T* __restrict__ A, con
                                                     const float* __restrict__ bias, const float* __restrict__ x,
                                                     int in_F, RowGeom g, float* __restrict__ out_user,
                                                     float* __restrict__ out_ws, SupportBits sup, int P, int FC) {
+  lcn_pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                         // [128][65]
   float* Ws = smem + LCN_TILE * GS_APAD;    // [64][17][4]
@@ -670,6 +682,7 @@ __global__ void __launch_bounds__(256) k_loss_dout(const float* __restrict__ out
                                                    int64_t n_rows, float* __restrict__ dout,
                                                    __nv_bfloat16* __restrict__ dout16, float* __restrict__ db,
                                                    double* loss_acc) {
+  lcn_pdl_prologue();
   __shared__ double sh[32];
   __shared__ float csum[4][64];
   int c = threadIdx.x & 63, rs = threadIdx.x >> 6;
@@ -700,6 +713,7 @@ __global__ void __launch_bounds__(256) k_loss_dout(const float* __restrict__ out
     atomicAdd(&db[threadIdx.x], csum[0][threadIdx.x] + csum[1][threadIdx.x] + csum[2][threadIdx.x] + csum[3][threadIdx.x]);
 }
 __global__ void k_loss_final(const double* loss_acc, int64_t n_rows, float* loss_out) {
+  lcn_pdl_prologue();
   loss_out[0] = (float)(loss_acc[0] / ((double)n_rows * 51.0));
 }
 
@@ -712,6 +726,7 @@ __global__ void __launch_bounds__(256) k_last_layer_bwd(const T* __restrict__ A,
                                                         const float* __restrict__ wm, T* __restrict__ dA,
                                                         float* __restrict__ dwm, float* __restrict__ db, int P,
                                                         int rows_per_block) {
+  lcn_pdl_prologue();
   __shared__ float ds[32][52];
   int c = blockIdx.y * 256 + threadIdx.x;
   bool act = c < P;
@@ -800,6 +815,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_reduce(const T* __restric
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float* __restrict__ sums,
                                                               int P, int F, int bn_group, float rate) {
+  lcn_pdl_prologue();
   extern __shared__ __align__(16) float red[];   // [Y][P/8][16]
   __shared__ __align__(16) float s_a[256], s_b[256], s_c[256], s_d[256];
   const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
@@ -868,6 +884,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_apply(const T* __restrict
                                                              float* __restrict__ dbpart, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int P, int F, int rows_pad,
                                                              int bn_group, float rate) {
+  lcn_pdl_prologue();
   extern __shared__ __align__(16) float red[];   // [Y-1][P] column sums of the other row-threads
   __shared__ __align__(16) float s_a[256], s_b[256], s_c[256], s_d[256];
   const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
@@ -950,6 +967,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_apply(const T* __restrict
 // db[l][col] = sum over the per-block partial rows written by k_bn_bwd_apply.  grid (ceil(P/64), n_bn), 256 threads
 __global__ void __launch_bounds__(256) k_db_reduce(const float* __restrict__ dbpart, int nblocks, int P,
                                                    float* __restrict__ graw, LinTable lt_b /* w_off holds b_off */) {
+  lcn_pdl_prologue();
   __shared__ float sh[4][64];
   int l = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
   float a = 0.f;
@@ -970,6 +988,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_wgrad_simt(const T* __restrict__ A, const T* __restrict__ dZ,
                                                     float* __restrict__ dW, PairTable pt, int P, int FC,
                                                     int rows_per_block) {
+  lcn_pdl_prologue();
   __shared__ __align__(16) float As[32][64];
   __shared__ __align__(16) float Ds[32][64];
   int sb = blockIdx.x;
@@ -1015,6 +1034,7 @@ template <typename T, int IN_F>
 __global__ void __launch_bounds__(256) k_first_wgrad(const float* __restrict__ x, int64_t n_rows,
                                                      const T* __restrict__ dZ, float* __restrict__ dW, int P,
                                                      int rows_per_block) {
+  lcn_pdl_prologue();
   constexpr int KIN = LCN_J * IN_F;
   __shared__ float xs[32][KIN];
   int c = blockIdx.y * 256 + threadIdx.x;
@@ -1050,6 +1070,7 @@ __global__ void __launch_bounds__(256) k_first_wgrad(const float* __restrict__ x
 // pairdot[l][p] = <dWm_l(block p), W_l(block p)>      grid (nnz, n_lin), 256 threads
 __global__ void k_pairdot(const float* __restrict__ params, const float* __restrict__ graw, LinTable lt,
                           PairTable pt, float* __restrict__ pairdot) {
+  lcn_pdl_prologue();
   __shared__ double sh[32];
   int p = blockIdx.x, l = blockIdx.y;
   int Fi = lt.Fi[l], Fo = lt.Fo[l], Kout = LCN_J * Fo;
@@ -1070,6 +1091,7 @@ __global__ void k_pairdot(const float* __restrict__ params, const float* __restr
 __global__ void k_maskgrad(const float* __restrict__ params, int64_t mask_off, SupportBits sup, PairTable pt,
                            int nnz, int n_lin, const float* __restrict__ pairdot, const float* __restrict__ mask,
                            LayerScalars* sc, float* __restrict__ maskgrad /*[289]*/) {
+  lcn_pdl_prologue();
   __shared__ float dM[LCN_J * LCN_J];
   __shared__ float soft[LCN_J * LCN_J];
   int t = threadIdx.x;
@@ -1114,6 +1136,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
                                               const float* __restrict__ mask, const float* __restrict__ maskgrad,
                                               LayerScalars* sc, float lr_t, float b1, float b2, float eps, float reg,
                                               const lcn_step_scalars* __restrict__ dyn) {
+  lcn_pdl_prologue();
   __shared__ double sh[32];
   if (dyn != nullptr) lr_t = dyn->lr_t;        // CUDA-graph replay: the step size lives in device memory
   int chunk = blockIdx.x;
@@ -1205,8 +1228,8 @@ static int launch_grad_chain(const lcn_model* m, const float* params, char* ws, 
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
   float* pairdot = reinterpret_cast<float*>(ws + lay.off_pairdot);
   float* maskgrad = mask + 2 * LCN_J * LCN_J;
-  k_pairdot<<<dim3(m->nnz, m->n_lin), 256, 0, st>>>(params, graw, make_lin(m), make_pairs(m), pairdot);
-  k_maskgrad<<<1, 320, 0, st>>>(params, m->mask_off, m->sup, make_pairs(m), m->nnz, m->n_lin, pairdot, mask, sc,
+  lcn_launch(k_pairdot, dim3(dim3(m->nnz, m->n_lin)), dim3(256), 0, st, params, graw, make_lin(m), make_pairs(m), pairdot);
+  lcn_launch(k_maskgrad, dim3(1), dim3(320), 0, st, params, m->mask_off, m->sup, make_pairs(m), m->nnz, m->n_lin, pairdot, mask, sc,
                                 maskgrad);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
@@ -1218,7 +1241,7 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
   if (rc) return rc;
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
-  k_adam<true><<<m->segs.total_chunks, 256, 0, st>>>(const_cast<float*>(params), nullptr, nullptr, grads_raw,
+  lcn_launch(k_adam<true>, dim3(m->segs.total_chunks), dim3(256), 0, st, const_cast<float*>(params), nullptr, nullptr, grads_raw,
                                                      grads_out, m->segs, make_lin(m), m->sup, mask,
                                                      mask + 2 * LCN_J * LCN_J, sc, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr);
   LCN_CHECK_LAUNCH();
@@ -1232,8 +1255,8 @@ int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, cha
   if (rc) return rc;
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
-  k_zero_norm2<<<1, 32, 0, st>>>(sc, m->n_lin);
-  k_adam<false><<<m->segs.total_chunks, 256, 0, st>>>(params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
+  lcn_launch(k_zero_norm2, dim3(1), dim3(32), 0, st, sc, m->n_lin);
+  lcn_launch(k_adam<false>, dim3(m->segs.total_chunks), dim3(256), 0, st, params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
                                                       m->sup, mask, mask + 2 * LCN_J * LCN_J, sc, lr_t, b1, b2, eps,
                                                       reg, dyn);
   LCN_CHECK_LAUNCH();
@@ -1281,8 +1304,8 @@ static int forward_impl(const FwdArgs& a) {
       const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
       __nv_bfloat16* x16 = (tc && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
       switch (m->d.in_F) {
-        case 2: k_first_layer<T, 2><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
-        case 3: k_first_layer<T, 3><<<grid, 256, 0, st>>>(a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
+        case 2: lcn_launch(k_first_layer<T, 2>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
+        case 3: lcn_launch(k_first_layer<T, 3>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
         default: lcn_set_error("in_F=%d not supported (2 or 3)", m->d.in_F); return LCN_EINVAL;
       }
     } else {
@@ -1294,20 +1317,20 @@ static int forward_impl(const FwdArgs& a) {
         if (rc) return rc;
       } else {
         const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
-        k_gemm_simt<T, false><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(
+        lcn_launch(k_gemm_simt<T, false>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
             Ain, wp, a.params + L.b_off, nullptr, Z, part, m->by_out, P, FC, lay.bn_group, lay.gstride);
       }
     }
     LCN_CHECK_LAUNCH();
     float* stat = bn_stat(ws, lay, m, l);
-    k_bn_finalize<<<dim3(lay.n_groups, F / 2), 256, 0, st>>>(part, stat, P, F, lay.tiles_per_group, lay.bn_group);
+    lcn_launch(k_bn_finalize, dim3(dim3(lay.n_groups, F / 2)), dim3(256), 0, st, part, stat, P, F, lay.tiles_per_group, lay.bn_group);
     const T* res = L.res_from >= 0 ? reinterpret_cast<const T*>(a_buf(ws, lay, L.res_from)) : nullptr;
     const int ewy = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
     uint8_t* keepbits = (lay.training && a.dropout_rate > 0.f)
                             ? reinterpret_cast<uint8_t*>(ws + lay.off_keep) + (size_t)l * lay.rows_pad * (P / 8)
                             : nullptr;
     int ew_grid = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
-    k_bn_act<T><<<ew_grid, dim3(P / 8, ewy), 0, st>>>(Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
+    lcn_launch(k_bn_act<T>, dim3(ew_grid), dim3(dim3(P / 8, ewy)), 0, st, Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
                                                       keepbits, P, F, (int)lay.rows_pad, lay.bn_group, lay.gstride,
                                                       a.dropout_rate, a.seed, a.step, l, a.dyn);
     LCN_CHECK_LAUNCH();
@@ -1320,7 +1343,7 @@ static int forward_impl(const FwdArgs& a) {
                          a.params + m->L[last].b_off, a.x, a.out, out_ws, st);
     if (rc) return rc;
   } else {
-    k_last_layer<T><<<lay.tiles, 128, gemm_smem, st>>>(Ain, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+    lcn_launch(k_last_layer<T>, dim3(lay.tiles), dim3(128), gemm_smem, st, Ain, reinterpret_cast<const float*>(ws + lay.off_wm_last),
                                                        a.params + m->L[last].b_off, a.x, m->d.in_F, g, a.out, out_ws,
                                                        m->sup, P, FC);
   }
@@ -1346,10 +1369,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   float* dout = reinterpret_cast<float*>(ws + lay.off_dout);
   double* lacc = reinterpret_cast<double*>(ws + lay.off_loss);
   __nv_bfloat16* dout16 = tc ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dout16) : nullptr;
-  k_loss_dout<<<(unsigned)(lay.rows_pad / 64), 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_out), labels,
+  lcn_launch(k_loss_dout, dim3((unsigned)(lay.rows_pad / 64)), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_out), labels,
                                                              lay.n_rows, dout, dout16,
                                                              tc ? graw + m->L[m->n_lin - 1].b_off : nullptr, lacc);
-  k_loss_final<<<1, 1, 0, st>>>(lacc, lay.n_rows, loss);
+  lcn_launch(k_loss_final, dim3(1), dim3(1), 0, st, lacc, lay.n_rows, loss);
   LCN_CHECK_LAUNCH();
 
   auto D = [&](int i) { return reinterpret_cast<T*>(ws + lay.off_d + (size_t)i * lay.d_stride); };
@@ -1371,7 +1394,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
                                      51 * sizeof(float), P, cudaMemcpyDeviceToDevice, st));
   } else {
     const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, m->n_bn - 1));
-    k_last_layer_bwd<T><<<dim3((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256), 256, 0, st>>>(
+    lcn_launch(k_last_layer_bwd<T>, dim3(dim3((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256)), dim3(256), 0, st, 
         Ain, dout, reinterpret_cast<const float*>(ws + lay.off_wm_last), D(cur), graw + m->L[last].w_off,
         graw + m->L[last].b_off, P, rows_blk);
     LCN_CHECK_LAUNCH();
@@ -1386,9 +1409,9 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     const float* stat = bn_stat(ws, lay, m, l);
     float* sums = reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)l * F * 2;
     const uint8_t* keepbits = reinterpret_cast<const uint8_t*>(ws + lay.off_keep) + (size_t)l * lay.rows_pad * (P / 8);
-    k_bn_bwd_reduce<T><<<eg, dim3(P / 8, ewy), red_smem, st>>>(D(cur), Z, keepbits, stat, params + L.gamma_off,
+    lcn_launch(k_bn_bwd_reduce<T>, dim3(eg), dim3(dim3(P / 8, ewy)), red_smem, st, D(cur), Z, keepbits, stat, params + L.gamma_off,
                                                              params + L.beta_off, sums, P, F, lay.bn_group, rate);
-    k_bn_bwd_apply<T><<<eg, dim3(P / 8, ewy), (size_t)ewy * P * sizeof(float), st>>>(
+    lcn_launch(k_bn_bwd_apply<T>, dim3(eg), dim3(dim3(P / 8, ewy)), (size_t)ewy * P * sizeof(float), st, 
         D(cur), Z, keepbits, stat, params + L.gamma_off, params + L.beta_off, sums, dZ,
         reinterpret_cast<float*>(ws + lay.off_dbpart) + (size_t)l * eg * P, graw + L.gamma_off, graw + L.beta_off, P, F, (int)lay.rows_pad, lay.bn_group, rate);
     LCN_CHECK_LAUNCH();
@@ -1402,8 +1425,8 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     }
     if (l == 0) {
       dim3 grid((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256);
-      if (m->d.in_F == 2) k_first_wgrad<T, 2><<<grid, 256, 0, st>>>(x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
-      else k_first_wgrad<T, 3><<<grid, 256, 0, st>>>(x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
+      if (m->d.in_F == 2) lcn_launch(k_first_wgrad<T, 2>, dim3(grid), dim3(256), 0, st, x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
+      else lcn_launch(k_first_wgrad<T, 3>, dim3(grid), dim3(256), 0, st, x, lay.n_rows, dZ, graw + L.w_off, P, rows_blk);
       LCN_CHECK_LAUNCH();
       break;
     }
@@ -1428,10 +1451,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
                        nullptr, st);
       if (rc) return rc;
     } else {
-      k_wgrad_simt<T><<<dim3(m->nnz * FC * FC, (unsigned)(lay.rows_pad / rows_blk)), 256, 0, st>>>(
+      lcn_launch(k_wgrad_simt<T>, dim3(dim3(m->nnz * FC * FC, (unsigned)(lay.rows_pad / rows_blk))), dim3(256), 0, st, 
           Ain, dZ, graw + L.w_off, pt, P, FC, rows_blk);
       const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
-      k_gemm_simt<T, true><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(
+      lcn_launch(k_gemm_simt<T, true>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
           dZ, wp, nullptr, addend, D(nxt), nullptr, m->by_in, P, FC, lay.bn_group, lay.gstride);
     }
     LCN_CHECK_LAUNCH();
@@ -1442,7 +1465,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LinTable lb;
     lb.n = m->n_bn;
     for (int l = 0; l < m->n_bn; ++l) lb.w_off[l] = m->L[l].b_off;
-    k_db_reduce<<<dim3((P + 63) / 64, m->n_bn), 256, 0, st>>>(reinterpret_cast<const float*>(ws + lay.off_dbpart),
+    lcn_launch(k_db_reduce, dim3(dim3((P + 63) / 64, m->n_bn)), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_dbpart),
                                                               (int)eg, P, graw, lb);
     LCN_CHECK_LAUNCH();
   }
@@ -1474,10 +1497,10 @@ static int layer_gemm_impl(const lcn_model* m, const float* params, char* ws, co
   }
   const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
   if (transposed)
-    k_gemm_simt<T, true><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(Ain, wp, nullptr, nullptr, Y, nullptr,
+    lcn_launch(k_gemm_simt<T, true>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, Ain, wp, nullptr, nullptr, Y, nullptr,
                                                                               m->by_in, P, FC, lay.bn_group, lay.gstride);
   else
-    k_gemm_simt<T, false><<<dim3(lay.tiles, LCN_J * FC), 256, gemm_smem, st>>>(
+    lcn_launch(k_gemm_simt<T, false>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
         Ain, wp, params + m->L[l].b_off, nullptr, Y, part, m->by_out, P, FC, lay.bn_group, lay.gstride);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
@@ -1494,6 +1517,7 @@ int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, con
 template <typename T>
 __global__ void k_read_rows(const T* __restrict__ src, float* __restrict__ dst, int64_t n_logical, int P,
                             int bn_group, int gstride) {
+  lcn_pdl_prologue();
   int64_t n = n_logical * P;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t lr = e / P;
@@ -1504,6 +1528,7 @@ __global__ void k_read_rows(const T* __restrict__ src, float* __restrict__ dst, 
 }
 __global__ void k_unpack_mid(const float* __restrict__ wp32, PairTable pt, int nnz, int F, int FC,
                              float* __restrict__ dst) {
+  lcn_pdl_prologue();
   int P = LCN_J * F;
   int sb = blockIdx.x;
   int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
@@ -1523,8 +1548,8 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
     LCN_REQUIRE(lay.training, "activation taps need a training-mode workspace layout");
     LCN_REQUIRE(layer >= 0 && layer < m->n_bn, "layer %d out of range", layer);
     const char* src = kind == 0 ? z_buf(ws, lay, layer) : kind == 1 ? a_buf(ws, lay, layer) : ws + lay.off_dz;
-    if (bf) k_read_rows<__nv_bfloat16><<<256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
-    else k_read_rows<float><<<256, 256, 0, st>>>(reinterpret_cast<const float*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
+    if (bf) lcn_launch(k_read_rows<__nv_bfloat16>, dim3(256), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
+    else lcn_launch(k_read_rows<float>, dim3(256), dim3(256), 0, st, reinterpret_cast<const float*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
   } else if (kind == 2) {
     LCN_REQUIRE(layer >= 0 && layer < m->n_lin, "layer %d out of range", layer);
     const LayerInfo& L = m->L[layer];
@@ -1535,7 +1560,7 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
       LCN_REQUIRE(!(bf && lcn_tc_enabled()), "the mid-layer weight tap needs the fp32 path (or LCN_DISABLE_TC=1)");
       LCN_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * P * P, st));
       const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(layer - 1) * m->nnz * m->FC * m->FC * 4096;
-      k_unpack_mid<<<m->nnz * m->FC * m->FC, 256, 0, st>>>(wp, make_pairs(m), m->nnz, F, m->FC, dst);
+      lcn_launch(k_unpack_mid, dim3(m->nnz * m->FC * m->FC), dim3(256), 0, st, wp, make_pairs(m), m->nnz, F, m->FC, dst);
     }
   } else if (kind == 3) {
     LCN_CHECK_CUDA(cudaMemcpyAsync(dst, ws + lay.off_mask, sizeof(float) * LCN_J * LCN_J, cudaMemcpyDeviceToDevice, st));
@@ -1554,6 +1579,7 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
 
 // dropout keep decisions, exactly as k_bn_act draws them
 __global__ void k_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t n4, float rate, uint8_t* keep) {
+  lcn_pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t rb[4];
     lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)i, rb);
@@ -1563,7 +1589,7 @@ __global__ void k_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t 
 extern "C" int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int32_t cols, float rate,
                                 uint8_t* d_keep, void* stream) {
   LCN_REQUIRE(cols % 4 == 0, "cols must be a multiple of 4");
-  k_dropout_mask<<<256, 256, 0, (cudaStream_t)stream>>>(seed, step, layer, rows * cols / 4, rate, d_keep);
+  lcn_launch(k_dropout_mask, dim3(256), dim3(256), 0, (cudaStream_t)stream, seed, step, layer, rows * cols / 4, rate, d_keep);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }

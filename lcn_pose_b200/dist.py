@@ -1,0 +1,44 @@
+"""Host-side multi-GPU plumbing: one process per GPU, torch.distributed for the rendezvous.
+
+* Inference / evaluation shard the pose set at BatchNorm-group granularity (the reference's BN uses batch statistics at
+  inference too, models_att.py:588-612 + SURVEY 9-Q2, so a batch of `batch_size` consecutive poses is the unit of
+  independence): no collective on the data path, one small all-reduce of the per-joint error sums at the end.
+* Data-parallel training all-reduces ONE bucket (the flat raw-gradient vector, parameter layout) between backward
+  and the fused Adam step; BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
+Everything here is backend agnostic (nccl on GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_groups(n_rows, batch_size, rank, world):
+    """Contiguous range of BN groups of this rank -> (row_begin, row_end).  Groups are ceil(n_rows / batch_size)
+    batches as base_model.predict forms them (models_att.py:86-97); the last one may be partial (zero padded by
+    the kernels).  Ranks get floor/ceil(groups / world) groups, earlier ranks the larger share."""
+    groups = (n_rows + batch_size - 1) // batch_size
+    base, extra = divmod(groups, world)
+    g0 = rank * base + min(rank, extra)
+    g1 = g0 + base + (1 if rank < extra else 0)
+    return min(g0 * batch_size, n_rows), min(g1 * batch_size, n_rows)
+
+
+def all_reduce_eval_sums(sums, group=None):
+    """Sum the evaluator's accumulators ([n_actions+1, 19] float64: 17 per-joint error sums, count, PCK hits) over
+    the ranks; the MPJPE means are then sums[:, :17].sum() / (17 * count) on every rank."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def average_gradient_bucket(bucket, group=None):
+    """Data-parallel exchange step: mean of the flat raw-gradient bucket over the ranks (one collective)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+        bucket.div_(dist.get_world_size(group))
+    return bucket
+
+
+def broadcast_parameters(flat_params, src=0, group=None):
+    """Replicas start from rank `src`'s parameters (the reference has a single process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat_params, src=src, group=group)
+    return flat_params
