@@ -5,14 +5,18 @@
 //   err[j] = || pred_j - gt_j ||_2  (evaluate.py:61), per-joint sums, PCK@50mm (evaluate.py:78-106)
 //
 // HBM-bound: 444 B read (+68 B written when per-joint errors are requested) per pose.  One warp owns
-// 32 consecutive poses per iteration: the 2 x 6528 B of pred/gt are staged in shared memory with
-// coalesced float4 loads, then each lane works on its own pose out of shared memory (row stride 51
-// words, odd -> conflict free) with the 3x3 SVD (one-sided Jacobi) entirely in registers.
+// 32 consecutive poses per iteration: the 2 x 6528 B of pred/gt arrive in shared memory as two 1-D bulk TMA copies
+// (cp.async.bulk, completion on a per-warp mbarrier), DOUBLE BUFFERED -- the copies of chunk i+1 (and the
+// box / camera / root-depth words of its poses) are in flight while the lanes work on chunk i -- then each lane
+// works on its own pose out of shared memory (row stride 51 words, odd -> conflict free) with the 3x3 SVD
+// (one-sided Jacobi) entirely in registers.  2 blocks x 4 warps per SM keep ~100 KB of loads in flight per SM.
 #include <algorithm>
 
 #include "lcn_internal.cuh"
+#include "lcn_tc_ptx.cuh"
 
-#define EV_WARPS 4
+#define EV_WARPS 8
+#define EV_CHUNK_BYTES (32 * 51 * 4)   // 6528 B of pred (or gt) for 32 poses: a multiple of 16
 #define EV_POSE 51
 
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
@@ -24,11 +28,12 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
 }
 
 // one Jacobi rotation orthogonalising columns p,q of G (3x3, column vectors) and accumulating V
-__device__ __forceinline__ void jacobi_rot(float* gp, float* gq, float* vp, float* vq) {
+// returns true when the pair was not yet orthogonal (a rotation was applied)
+__device__ __forceinline__ bool jacobi_rot(float* gp, float* gq, float* vp, float* vq) {
   float alpha = gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2];
   float beta = gq[0] * gq[0] + gq[1] * gq[1] + gq[2] * gq[2];
   float gamma = gp[0] * gq[0] + gp[1] * gq[1] + gp[2] * gq[2];
-  if (gamma * gamma <= 1e-14f * alpha * beta) return;
+  if (gamma * gamma <= 1e-14f * alpha * beta) return false;
   float zeta = (beta - alpha) / (2.f * gamma);
   float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
   float c = rsqrtf(1.f + t * t), s = c * t;
@@ -41,22 +46,33 @@ __device__ __forceinline__ void jacobi_rot(float* gp, float* gq, float* vp, floa
     vp[k] = c * a - s * b;
     vq[k] = s * a + c * b;
   }
+  return true;
 }
 
-__global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict__ pred, const float* __restrict__ gt,
+// EV_BUFS staging buffers per warp.  2: double buffered, one block of 8 warps per SM (Protocol 1: pure streaming, the
+// next chunk's copies overlap this chunk's arithmetic inside the warp).  1: 13 KB per warp, two blocks = 16 warps per
+// SM (Protocol 2: the per-pose SVD chain is latency bound, more resident warps hide it).
+template <int EV_BUFS>
+__global__ void __launch_bounds__(EV_WARPS * 32, EV_BUFS == 1 ? 2 : 1) k_eval(const float* __restrict__ pred, const float* __restrict__ gt,
                                                        const float* __restrict__ box, const float* __restrict__ cam,
                                                        const float* __restrict__ root_depth,
                                                        const int32_t* __restrict__ action, int n_actions, int64_t n,
                                                        int flags, float* __restrict__ err_out,
                                                        float* __restrict__ pose_out, double* __restrict__ sums) {
   const int protocol2 = flags & 1, camera_frame = flags & 2;
-  extern __shared__ __align__(16) float smem[];
-  // per warp: pred[32*51], gt[32*51]; then per block: action sums (double)
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[EV_WARPS][2];
+  // per warp: two buffers of {pred[32*51], gt[32*51]}; then per block: action sums (double)
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sp = smem + warp * (2 * 32 * EV_POSE);
-  float* sg = sp + 32 * EV_POSE;
-  double* asum = reinterpret_cast<double*>(smem + EV_WARPS * 2 * 32 * EV_POSE);   // [n_actions][19]
+  float* wbuf = smem + warp * (EV_BUFS * 2 * 32 * EV_POSE);
+  double* asum = reinterpret_cast<double*>(smem + EV_WARPS * EV_BUFS * 2 * 32 * EV_POSE);   // [n_actions][19]
   for (int e = threadIdx.x; e < n_actions * 19; e += blockDim.x) asum[e] = 0.0;
+  const uint32_t bar0 = smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
   double jsum[LCN_J];
@@ -66,101 +82,143 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
 
   int64_t n_chunks = (n + 31) / 32;
   int64_t wglobal = (int64_t)blockIdx.x * EV_WARPS + warp, wstride = (int64_t)gridDim.x * EV_WARPS;
-  for (int64_t ch = wglobal; ch < n_chunks; ch += wstride) {
+  // full chunks travel by bulk copy into buffer `b`; the (single, last) partial chunk is loaded by the lanes
+  auto issue = [&](int64_t ch, int b) {
+    if (ch >= n_chunks || (ch + 1) * 32 > n) return;
+    if (lane == 0) {
+      const uint32_t bar = bar0 + 8 * b;
+      float* dp = wbuf + b * (2 * 32 * EV_POSE);
+      mbar_expect_tx(bar, 2 * EV_CHUNK_BYTES);
+      bulk_g2s(smem_u32(dp), pred + ch * 32 * EV_POSE, EV_CHUNK_BYTES, bar);
+      bulk_g2s(smem_u32(dp + 32 * EV_POSE), gt + ch * 32 * EV_POSE, EV_CHUNK_BYTES, bar);
+    }
+  };
+  // per-pose scalars of a chunk (box, camera, root depth, action): fetched one chunk ahead into registers
+  float4 bx_n = make_float4(0.f, 0.f, 1999.f, 0.f), cm_n = make_float4(1.f, 1.f, 0.f, 0.f);
+  float rd_n = 0.f;
+  int act_n = -1;
+  auto fetch_scalars = [&](int64_t ch) {
+    bx_n = make_float4(0.f, 0.f, 1999.f, 0.f);
+    cm_n = make_float4(1.f, 1.f, 0.f, 0.f);
+    rd_n = 0.f;
+    act_n = -1;
+    int64_t ip = ch * 32 + lane;
+    if (ch < n_chunks && ip < n) {
+      if (!camera_frame) {
+        bx_n = ld_stream4(box + ip * 4);
+        cm_n = ld_stream4(cam + ip * 4);                     // fx, fy, cx, cy
+        rd_n = __ldg(root_depth + ip);
+      }
+      if (action != nullptr) act_n = __ldg(action + ip);
+    }
+  };
+  issue(wglobal, 0);
+  fetch_scalars(wglobal);
+  int buf = 0;
+  uint32_t phase[2] = {0u, 0u};
+  for (int64_t ch = wglobal; ch < n_chunks; ch += wstride, buf ^= (EV_BUFS - 1)) {
     int64_t p0 = ch * 32;
     int cnt = (int)min((int64_t)32, n - p0);
-    const float* gp = pred + p0 * EV_POSE;
-    const float* gg = gt + p0 * EV_POSE;
-    __syncwarp();
+    float* sp = wbuf + buf * (2 * 32 * EV_POSE);
+    float* sg = sp + 32 * EV_POSE;
+    const float4 bx = bx_n, cm = cm_n;
+    const float rd = rd_n;
+    const int act = act_n;
+    // next chunk of this warp.  Double buffered: into the other buffer now (last read two iterations ago, fenced
+    // below); single buffered: after this chunk's reads, at the bottom of the loop.  The per-pose scalars of the
+    // next chunk are always fetched one chunk ahead.
+    if (EV_BUFS == 2) issue(ch + wstride, buf ^ 1);
+    fetch_scalars(ch + wstride);
     if (cnt == 32) {
-#pragma unroll 4
-      for (int v = lane; v < 32 * EV_POSE / 4; v += 32) {
-        *reinterpret_cast<float4*>(sp + v * 4) = ld_stream4(gp + v * 4);
-        *reinterpret_cast<float4*>(sg + v * 4) = ld_stream4(gg + v * 4);
-      }
+      mbar_wait(bar0 + 8 * buf, phase[buf]);
+      phase[buf] ^= 1u;
     } else {
+      const float* gp = pred + p0 * EV_POSE;
+      const float* gg = gt + p0 * EV_POSE;
       for (int v = lane; v < cnt * EV_POSE; v += 32) {
         sp[v] = gp[v];
         sg[v] = gg[v];
       }
+      __syncwarp();
     }
-    __syncwarp();
     bool active = lane < cnt;
     float e[LCN_J];
 #pragma unroll
     for (int j = 0; j < LCN_J; ++j) e[j] = 0.f;
-    int act = -1;
     if (active) {
-      int64_t ip = p0 + lane;
-      float4 bx = make_float4(0.f, 0.f, 1999.f, 0.f), cm = make_float4(1.f, 1.f, 0.f, 0.f);
-      float rd = 0.f;
-      if (!camera_frame) {
-        bx = *reinterpret_cast<const float4*>(box + ip * 4);
-        cm = *reinterpret_cast<const float4*>(cam + ip * 4);   // fx, fy, cx, cy
-        rd = root_depth[ip];
-      }
-      if (action != nullptr) act = action[ip];
-      float inv_ratio = 2000.0f / (bx.z - bx.x + 1.0f);
-      float ifx = 1.0f / cm.x, ify = 1.0f / cm.y;
-      const float* mp = sp + lane * EV_POSE;
+      const float inv_ratio = 2000.0f / (bx.z - bx.x + 1.0f);
+      const float ifx = 1.0f / cm.x, ify = 1.0f / cm.y;
+      float* mp = sp + lane * EV_POSE;
       const float* mg = sg + lane * EV_POSE;
-      float P[LCN_J][3], G[LCN_J][3];
-      float pb[3] = {0, 0, 0}, gb[3] = {0, 0, 0};
-#pragma unroll
-      for (int j = 0; j < LCN_J; ++j) {
+      // prediction joint j in the camera frame (tools.py:187-193); the pose is re-read from shared memory in every
+      // pass instead of living in 102 registers: the kernel then fits 128 registers -> 16 warps per SM
+      auto cam_joint = [&](int j, float* q) {
         if (camera_frame) {
-          P[j][0] = mp[j * 3 + 0]; P[j][1] = mp[j * 3 + 1]; P[j][2] = mp[j * 3 + 2];
+          q[0] = mp[j * 3 + 0]; q[1] = mp[j * 3 + 1]; q[2] = mp[j * 3 + 2];
         } else {
           float z = mp[j * 3 + 2] * inv_ratio + rd;          // tools.py:187
-          P[j][0] = (mp[j * 3 + 0] - cm.z) * ifx * z;        // tools.py:190,192
-          P[j][1] = (mp[j * 3 + 1] - cm.w) * ify * z;        // tools.py:191,193
-          P[j][2] = z;
+          q[0] = (mp[j * 3 + 0] - cm.z) * ifx * z;           // tools.py:190,192
+          q[1] = (mp[j * 3 + 1] - cm.w) * ify * z;           // tools.py:191,193
+          q[2] = z;
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          G[j][c] = mg[j * 3 + c];
-          pb[c] += P[j][c];
-          gb[c] += G[j][c];
-        }
-      }
+      };
       if (protocol2) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          pb[c] *= (1.0f / LCN_J);
-          gb[c] *= (1.0f / LCN_J);
-        }
-        float ssA = 0.f, ssB = 0.f;
+        // pass 1: moments of both poses relative to their root joints (values ~1e2 mm instead of ~1e3-1e4 mm: the
+        // centred second moments keep fp32 accuracy), then the shift to the centroids in closed form
+        float p0[3], g0r[3];
+        cam_joint(0, p0);
+        g0r[0] = mg[0]; g0r[1] = mg[1]; g0r[2] = mg[2];
+        float sP[3] = {0, 0, 0}, sG[3] = {0, 0, 0}, ssA = 0.f, ssB = 0.f;
         float M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // M[a][b] = sum_k A0[k][a] * B0[k][b]
 #pragma unroll
-        for (int j = 0; j < LCN_J; ++j) {
+        for (int j = 1; j < LCN_J; ++j) {
+          float q[3], g[3];
+          cam_joint(j, q);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            P[j][c] -= pb[c];                               // B0 (prediction), tools.py:130
-            G[j][c] -= gb[c];                               // A0 (ground truth), tools.py:129
-            ssA = fmaf(G[j][c], G[j][c], ssA);
-            ssB = fmaf(P[j][c], P[j][c], ssB);
+            q[c] -= p0[c];
+            g[c] = mg[j * 3 + c] - g0r[c];
+            sP[c] += q[c];
+            sG[c] += g[c];
+            ssA = fmaf(g[c], g[c], ssA);
+            ssB = fmaf(q[c], q[c], ssB);
           }
 #pragma unroll
-          for (int a = 0; a < 3; ++a)
+          for (int a2 = 0; a2 < 3; ++a2)
 #pragma unroll
-            for (int b = 0; b < 3; ++b) M[a][b] = fmaf(G[j][a], P[j][b], M[a][b]);
+            for (int b2 = 0; b2 < 3; ++b2) M[a2][b2] = fmaf(g[a2], q[b2], M[a2][b2]);
         }
-        float nA = sqrtf(ssA), nB = sqrtf(ssB);
+        float pb[3], gb[3];                                   // centroids relative to the roots (tools.py:127-130)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          pb[c] = sP[c] * (1.0f / LCN_J);
+          gb[c] = sG[c] * (1.0f / LCN_J);
+        }
+        ssA -= (float)LCN_J * (gb[0] * gb[0] + gb[1] * gb[1] + gb[2] * gb[2]);
+        ssB -= (float)LCN_J * (pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2]);
+#pragma unroll
+        for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+          for (int b2 = 0; b2 < 3; ++b2) M[a2][b2] -= (float)LCN_J * gb[a2] * pb[b2];
+        float nA = sqrtf(fmaxf(ssA, 0.f)), nB = sqrtf(fmaxf(ssB, 0.f));
         float inv_ab = 1.0f / (nA * nB);
         // columns of M (scaled to the unit-norm problem of tools.py:133-144)
         float g0[3], g1[3], g2[3], v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          g0[a] = M[a][0] * inv_ab;
-          g1[a] = M[a][1] * inv_ab;
-          g2[a] = M[a][2] * inv_ab;
+        for (int a2 = 0; a2 < 3; ++a2) {
+          g0[a2] = M[a2][0] * inv_ab;
+          g1[a2] = M[a2][1] * inv_ab;
+          g2[a2] = M[a2][2] * inv_ab;
         }
-        // one-sided Jacobi: M V = U S  (np.linalg.svd, tools.py:145)
+        // one-sided Jacobi: M V = U S  (np.linalg.svd, tools.py:145).  At most 6 sweeps; the warp stops as soon as a
+        // whole sweep rotated nothing in any of its lanes (cyclic Jacobi converges quadratically)
+        const unsigned lanes = __activemask();
 #pragma unroll 1
         for (int sweep = 0; sweep < 6; ++sweep) {
-          jacobi_rot(g0, g1, v0, v1);
-          jacobi_rot(g0, g2, v0, v2);
-          jacobi_rot(g1, g2, v1, v2);
+          bool r = jacobi_rot(g0, g1, v0, v1);
+          r |= jacobi_rot(g0, g2, v0, v2);
+          r |= jacobi_rot(g1, g2, v1, v2);
+          if (!__any_sync(lanes, r)) break;
         }
         float s0 = sqrtf(g0[0] * g0[0] + g0[1] * g0[1] + g0[2] * g0[2]);
         float s1 = sqrtf(g1[0] * g1[0] + g1[1] * g1[1] + g1[2] * g1[2]);
@@ -170,35 +228,42 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
         // R = V U^T (tools.py:146-147): R[b][c] = sum_s V[b][s] U[c][s], U[:,s] = g_s / s_s
         float R[3][3];
 #pragma unroll
-        for (int b = 0; b < 3; ++b)
+        for (int b2 = 0; b2 < 3; ++b2)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) R[b][c] = v0[b] * g0[c] * i0 + v1[b] * g1[c] * i1 + v2[b] * g2[c] * i2;
-        // Z - gt = nA*tr*(B0/nB) R - A0   (tools.py:168 minus the common centroid)
-        float sc = nA * tr / nB;
+          for (int c = 0; c < 3; ++c) R[b2][c] = v0[b2] * g0[c] * i0 + v1[b2] * g1[c] * i1 + v2[b2] * g2[c] * i2;
+        // pass 2: Z - gt = nA*tr*(B0/nB) R - A0   (tools.py:168 minus the common centroid)
+        const float sc = nA * tr / nB;
 #pragma unroll
         for (int j = 0; j < LCN_J; ++j) {
-          float d2 = 0.f, zc[3];
+          float q[3], g[3], zc[3];
+          cam_joint(j, q);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            zc[c] = sc * (P[j][0] * R[0][c] + P[j][1] * R[1][c] + P[j][2] * R[2][c]) - G[j][c];
+            q[c] -= p0[c] + pb[c];                          // B0 (prediction), tools.py:130
+            g[c] = mg[j * 3 + c] - g0r[c] - gb[c];          // A0 (ground truth), tools.py:129
+          }
+          float d2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            zc[c] = sc * (q[0] * R[0][c] + q[1] * R[1][c] + q[2] * R[2][c]) - g[c];
             d2 = fmaf(zc[c], zc[c], d2);
           }
           e[j] = sqrtf(d2);
+          if (pose_out != nullptr) {   // aligned pose Z (tools.py:168); a lane only rewrites its own 51 words
 #pragma unroll
-          for (int c = 0; c < 3; ++c) P[j][c] = zc[c] + G[j][c] + gb[c];   // aligned pose Z (tools.py:168)
+            for (int c = 0; c < 3; ++c) mp[j * 3 + c] = zc[c] + mg[j * 3 + c];
+          }
         }
       } else {
 #pragma unroll
         for (int j = 0; j < LCN_J; ++j) {
-          float dx = P[j][0] - G[j][0], dy = P[j][1] - G[j][1], dz = P[j][2] - G[j][2];
+          float q[3];
+          cam_joint(j, q);
+          float dx = q[0] - mg[j * 3 + 0], dy = q[1] - mg[j * 3 + 1], dz = q[2] - mg[j * 3 + 2];
           e[j] = sqrtf(dx * dx + dy * dy + dz * dz);
-        }
-      }
-      if (pose_out != nullptr) {   // every lane only rewrites its own 51 words of the staging area
-        float* mo = sp + lane * EV_POSE;
-#pragma unroll
-        for (int j = 0; j < LCN_J; ++j) {
-          mo[j * 3 + 0] = P[j][0]; mo[j * 3 + 1] = P[j][1]; mo[j * 3 + 2] = P[j][2];
+          if (pose_out != nullptr) {
+            mp[j * 3 + 0] = q[0]; mp[j * 3 + 1] = q[1]; mp[j * 3 + 2] = q[2];
+          }
         }
       }
       int pck = 0;
@@ -232,6 +297,11 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_eval(const float* __restrict_
       float* dst = err_out + p0 * LCN_J;
       for (int v = lane; v < cnt * LCN_J; v += 32) dst[v] = sp[v];
     }
+    // this buffer is overwritten by a bulk copy (async proxy) issued at the top of the NEXT iteration: order the
+    // lanes' generic-proxy accesses before it
+    fence_proxy_async();
+    __syncwarp();
+    if (EV_BUFS == 1) issue(ch + wstride, 0);
   }
   // block reduction of the "all poses" row, then one atomic per entry per block
   __syncthreads();
@@ -271,19 +341,25 @@ extern "C" int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const floa
   LCN_REQUIRE((((uintptr_t)d_pred | (uintptr_t)d_gt | (uintptr_t)d_box | (uintptr_t)d_cam) & 15) == 0,
               "pred/gt/box/cam must be 16-byte aligned");
   if (d_action == nullptr) n_actions = 0;
-  size_t smem = (size_t)EV_WARPS * 2 * 32 * EV_POSE * sizeof(float) + (size_t)n_actions * 19 * sizeof(double);
+  const int bufs = (flags & 1) ? 1 : 2;
+  size_t smem = (size_t)EV_WARPS * bufs * 2 * 32 * EV_POSE * sizeof(float) + (size_t)n_actions * 19 * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr = true;
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t chunks = (n + 31) / 32;
   int64_t blocks = (chunks + EV_WARPS - 1) / EV_WARPS;
-  int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * 4);
-  k_eval<<<grid, EV_WARPS * 32, smem, (cudaStream_t)stream>>>(d_pred, d_gt, d_box, d_cam, d_root_depth, d_action,
-                                                            n_actions, n, flags, d_err, d_pose_out, d_sums);
+  int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * (bufs == 1 ? 2 : 1));
+  if (bufs == 1)
+    k_eval<1><<<grid, EV_WARPS * 32, smem, (cudaStream_t)stream>>>(d_pred, d_gt, d_box, d_cam, d_root_depth, d_action,
+                                                                 n_actions, n, flags, d_err, d_pose_out, d_sums);
+  else
+    k_eval<2><<<grid, EV_WARPS * 32, smem, (cudaStream_t)stream>>>(d_pred, d_gt, d_box, d_cam, d_root_depth, d_action,
+                                                                 n_actions, n, flags, d_err, d_pose_out, d_sums);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
