@@ -191,6 +191,22 @@ int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const float* d_box, c
  * d_pose [n,17,3] in place; d_res [n,2] = (res_w, res_h). */
 int lcn_denormalize(float* d_pose, const float* d_res, int64_t n, void* stream);
 
+/* (f) Pose augmentations of tools/data.py on the device (train.py:85-104, inference.py:75-111 run them on the host):
+ * d_src / d_dst [n, 17*k] fp32, k = 2 or 3 coordinates per joint, out of place.
+ *   LCN_AUG_FLIP      flip_data        tools/data.py:10-25   (negate x, swap left/right joints)
+ *   LCN_AUG_ROTATE    rotate_data      tools/data.py:289-322 (angle_deg about z, pivot = joint 0 of each pose)
+ *   LCN_AUG_TRANSLATE translation_data tools/data.py:27-54   (scalar t added to every coordinate) */
+#define LCN_AUG_FLIP 1
+#define LCN_AUG_ROTATE 2
+#define LCN_AUG_TRANSLATE 3
+int lcn_augment(const float* d_src, float* d_dst, int64_t n, int k, int op, float angle_deg, float t, void* stream);
+
+/* (f) undo, tools/data.py:269-287 (test-time augmentation of inference.py:110-111): d_preds [(n_ops+1), n, 17, 3];
+ * slice_f is un-flipped (:236-249), slice_r rotated by angle_deg about joint 0 (:289-322), slice_t un-translated by t
+ * (:205-218); a negative slice index = that operation is absent.  d_out [n, 51] = mean over the n_ops+1 slices. */
+int lcn_tta_undo(const float* d_preds, float* d_out, int64_t n, int n_ops, int slice_f, int slice_r, int slice_t,
+                 float angle_deg, float t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ J = 17
 LCN_PATH_FP32, LCN_PATH_BF16 = 0, 1
 LCN_MASK_LOCALLY_CONNECTED, LCN_MASK_CONSTANT = 0, 1
 LCN_EVAL_PROTOCOL2, LCN_EVAL_CAMERA_FRAME = 1, 2
+LCN_AUG_FLIP, LCN_AUG_ROTATE, LCN_AUG_TRANSLATE = 1, 2, 3
 
 
 class LcnError(RuntimeError):
@@ -46,6 +47,8 @@ PROTOTYPES = {
     "lcn_dropout_mask": (C.c_int, [_u64, _u64, C.c_int, _i64, _i32, _f, _vp, _vp]),
     "lcn_eval_mpjpe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp, _vp]),
     "lcn_denormalize": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "lcn_augment": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _f, _f, _vp]),
+    "lcn_tta_undo": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f, _f, _vp]),
 }
 
 _lib = None

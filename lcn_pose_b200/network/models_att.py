@@ -130,14 +130,18 @@ class base_model(object):
         xd = torch.as_tensor(np.ascontiguousarray(train_data, dtype=np.float32)).to(eng.device)
         yd = torch.as_tensor(np.ascontiguousarray(train_labels, dtype=np.float32)).to(eng.device)
         sampler = PermutationSampler(n, self.batch_size)
+        # fixed batch buffers: the step is a CUDA-graph replay (LcnEngine.train_step_graph) fed by a device gather
+        bx = torch.empty((self.batch_size, xd.shape[1]), dtype=torch.float32, device=eng.device)
+        by = torch.empty((self.batch_size, yd.shape[1]), dtype=torch.float32, device=eng.device)
         ema = DebiasedEma(0.9)
         losses, training_error, validation_error = [], [], []
         min_loss = 10000
         self._restored = True
         for step in range(starting_step, num_steps + 1):
             idx = torch.as_tensor(sampler.next()).to(eng.device, non_blocking=True)
-            bx, by = xd.index_select(0, idx), yd.index_select(0, idx)
-            loss_dev, learning_rate = eng.train_step(bx, by, dropout=self.dropout)
+            torch.index_select(xd, 0, idx, out=bx)
+            torch.index_select(yd, 0, idx, out=by)
+            loss_dev, learning_rate = eng.train_step_graph(bx, by, dropout=self.dropout)
             if eval_frequency > 0 and step % eval_frequency == 0:
                 loss_average = ema.update(float(loss_dev.item()))
                 epoch = step * self.batch_size / n

@@ -125,6 +125,11 @@ def main():
     out.update(aug_x2=x2, aug_x3=x3, aug_flip2=data.flip_data(x2), aug_flip3=data.flip_data(x3),
                aug_rot2=data.rotate_data(x2, 37.0), aug_rot3=data.rotate_data(x3, 37.0),
                aug_tr2=data.translation_data(x2, 0.07), aug_tr3=data.translation_data(x3, 0.07))
+    # ---- test-time-augmentation undo (tools/data.py:269-287): original + flip + rotate(180) + translate slices ----
+    u_in = rng.normal(0, 0.3, (4 * 6, 51))
+    out.update(aug_undo_in=u_in,
+               aug_undo_out=data.undo(u_in, {"f": 1, "r": 2, "t": 3}, number_actions=3, angle=180, translation=0.07),
+               aug_undo_fr_out=data.undo(u_in[:18], {"r": 1, "f": 2}, number_actions=2, angle=180, translation=0.0))
     np.savez_compressed(os.path.join(HERE, "reference_numpy.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_numpy.npz"), "with", len(out), "arrays")
 

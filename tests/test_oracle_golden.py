@@ -94,3 +94,11 @@ def test_predict_zero_pads_last_batch():
     pad = np.zeros((4, 34)); pad[:3] = x[8:]
     np.testing.assert_allclose(pr[8:], O.forward(cfg, p, pad)[0][:3], atol=1e-15)
     np.testing.assert_allclose(pr[:4], O.forward(cfg, p, x[:4])[0], atol=1e-15)
+
+
+def test_tta_undo_matches_reference(golden):
+    g = golden
+    got = O.undo(g["aug_undo_in"], {"f": 1, "r": 2, "t": 3}, number_actions=3, angle=180, translation=0.07)
+    np.testing.assert_allclose(got, g["aug_undo_out"], atol=1e-14)
+    got = O.undo(g["aug_undo_in"][:18], {"r": 1, "f": 2}, number_actions=2, angle=180, translation=0.0)
+    np.testing.assert_allclose(got, g["aug_undo_fr_out"], atol=1e-14)
