@@ -32,8 +32,11 @@ def all_reduce_eval_sums(sums, group=None):
 def average_gradient_bucket(bucket, group=None):
     """Data-parallel exchange step: mean of the flat raw-gradient bucket over the ranks (one collective)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
-        bucket.div_(dist.get_world_size(group))
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(bucket, op=dist.ReduceOp.AVG, group=group)      # averaged inside the collective
+        else:
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+            bucket.div_(dist.get_world_size(group))
     return bucket
 
 
