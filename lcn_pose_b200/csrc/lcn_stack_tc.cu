@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
   constexpr int ST_EPI_THREADS = 32 * EW;
   constexpr int VT = 64 + 32 * EW;       // threads of one virtual CTA
   constexpr int HSTEP = EW / 4;          // epilogue warps per TMEM lane quarter
-  constexpr int NBAR = 2 * ST_MAX_STAGES + 4;
+  constexpr int NBAR = 2 * ST_MAX_STAGES + 5;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars_all[NV * NBAR];
   __shared__ uint32_t tmem_base_s;
@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
   float* colB = colA + NCOL;
   // epilogue scratch inside the (then idle) pipeline stages: per-warp 32x33 transpose tiles, then the per-lane-quarter
   // column sums (fixed-order sum: deterministic)
-  float* colS = reinterpret_cast<float*>(sgen) + EW * (32 * 33);
+  // -- placed at the END of the stage area: the front holds the output tiles (and the prefetched residual tiles)
+  float* scr0 = reinterpret_cast<float*>(sgen + (size_t)p.stages * ST_STAGE_BYTES) - (EW * (32 * 33) + 8 * NCOL);
+  float* colS = scr0 + EW * (32 * 33);
   float* colQ = colS + 4 * NCOL;
   const int warp = __shfl_sync(0xffffffffu, vtid >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank(), NS = cluster_nctarank();
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
   // virtual-cluster barriers: one arrival per CTA of the cluster.  xs1: every CTA has written its BN statistics into
   // every stat_all;  xs2: every CTA has finished the layer (A_l stored, TMEM and pipeline stages free)
   const uint32_t xs1 = smem_u32(&bars[2 * ST_MAX_STAGES + 2]), xs2 = smem_u32(&bars[2 * ST_MAX_STAGES + 3]);
+  const uint32_t xres = smem_u32(&bars[2 * ST_MAX_STAGES + 4]);      // residual tiles of the current layer have landed
 
   if (vtid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
     mbar_init(xfull, ST_EPI_THREADS);
     mbar_init(xs1, NS);
     mbar_init(xs2, NS);
+    mbar_init(xres, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1 && vc == 0) tmem_alloc(smem_u32(&tmem_base_s), (uint32_t)p.tmem_cols);
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
   // kept incrementally -- a runtime modulo / division per iteration costs ~200 cycles of the issuing warps
   int st_s = 0;
   uint32_t st_ph = 0;
-  uint32_t layer_cnt = 0, grp_cnt = 0, bn_cnt = 0;
+  uint32_t layer_cnt = 0, grp_cnt = 0, bn_cnt = 0, res_cnt = 0;
 
   for (int g = (int)cid; g < p.n_groups; g += (int)ncl, ++grp_cnt) {
     for (int l = 0; l < p.n_lin; ++l, ++layer_cnt) {
@@ -440,9 +444,25 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
         tc_fence_after();
         if (e == 0) ST_STAMP(16 * l + 1);
         if (!head) {
+          const bool has_res = p.res[l] != 0;
+          constexpr int NH = 2 / HSTEP;          // work items of a warp: (unit u, 32-column half)
+          const int U = TPG * G;
+          if (has_res && warp == 2) {
+            // residual A_{l-2} (the buffer this layer overwrites, written by this CTA's own bulk stores): its tiles are
+            // bulk-copied straight into the places where the output tiles will be staged -- every thread later reads
+            // the 64 B it overwrites.  The copies land while pass 1 and the statistics exchange run.
+            if (elect_one()) {
+              mbar_expect_tx(xres, (uint32_t)U * ST_A_BYTES);
+              for (int u = 0; u < U; ++u) {
+                const int t = u / G, q = u - t * G;
+                bulk_g2s(sbase + (uint32_t)u * ST_A_BYTES, aout + ((size_t)t * LCN_J + oc0 + q) * 8192, ST_A_BYTES, xres);
+              }
+            }
+            __syncwarp();
+          }
           // ---- pass 1: per-column sum / sum of squares of the accumulators over the group's valid rows ----
           // (32x32 transpose through a per-warp scratch in the idle pipeline stages: lane = row writes, lane = column sums)
-          float* scr = reinterpret_cast<float*>(sgen) + (warp - 2) * (32 * 33);
+          float* scr = scr0 + (warp - 2) * (32 * 33);
           for (int q = 0; q < G; ++q)
             for (int hset = hset0; hset < 2; hset += HSTEP) {
               float cs = 0.f, cq = 0.f;
@@ -502,30 +522,18 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
             colA[c] = sc;
             colB[c] = __ldg(bias + oc0 * 64 + c) * sc + __ldg(p.params + p.beta_off[l] + f) - mean * sc;
           }
+          if (has_res) {
+            if (warp == 2) mbar_wait(xres, res_cnt & 1u);          // the residual tiles have landed
+            ++res_cnt;
+          }
           epi_bar<EW>(vc);
           // ---- pass 2: BN + LeakyReLU (+ residual) out of TMEM -> bf16 swizzled tiles in smem -> bulk store per tile ----
-          const bool has_res = p.res[l] != 0;
-          const int U = TPG * G;
-          // A_{l-2} lives in the buffer this layer overwrites; written by this CTA's bulk stores -> bypass L1.
-          // The residual of unit u+1 is fetched while unit u is processed.
-          // Work items of a warp: (unit u, 32-column half); one half per warp with 8 epilogue warps, both with 4.
-          constexpr int NH = 2 / HSTEP;
-          uint4 rr[4], rn[4];
-          auto res_load = [&](int it, uint4* dst) {
-            const int u = it / NH, hset = hset0 + (it - u * NH) * HSTEP;
-            const int t = u / G, q = u - t * G;
-            const uint8_t* rrow = reinterpret_cast<const uint8_t*>(aout) + (((size_t)t * LCN_J + oc0 + q) * 128 + row) * 128;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = __ldcg(reinterpret_cast<const uint4*>(rrow + (((hset * 4 + c) ^ (row & 7)) << 4)));
-          };
-          if (has_res) res_load(0, rr);
           for (int t = 0; t < TPG; ++t) {
             for (int it = t * G * NH; it < (t + 1) * G * NH; ++it) {
               const int u = it / NH, hset = hset0 + (it - u * NH) * HSTEP;
               const int q = u - t * G;
               uint32_t v[32];
               tmem_ld32_nowait(tmem_base + tlane + (uint32_t)u * 64 + hset * 32, v);
-              if (has_res && it + 1 < U * NH) res_load(it + 1, rn);
               tmem_ld_wait();
               float f[32];
               const float4* a4 = reinterpret_cast<const float4*>(colA + q * 64 + hset * 32);
@@ -542,10 +550,12 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
                 f[4 * i + 2] = fmaxf(y2, LCN_LRELU * y2);
                 f[4 * i + 3] = fmaxf(y3, LCN_LRELU * y3);
               }
+              uint8_t* tile_s = sgen + (size_t)u * ST_A_BYTES;
               if (has_res) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rr[c]);
+                  const uint4 rv = *reinterpret_cast<const uint4*>(tile_s + row * 128 + (((hset * 4 + c) ^ (row & 7)) << 4));
+                  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     const float2 r2 = __bfloat1622float2(hp[k]);
@@ -553,10 +563,7 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
                     f[c * 8 + 2 * k + 1] += r2.y;
                   }
                 }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) rr[c] = rn[c];
               }
-              uint8_t* tile_s = sgen + (size_t)u * ST_A_BYTES;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]);
