@@ -205,7 +205,7 @@ def test_library_is_the_loaded_native_code():
 
 def test_graph_replayed_train_steps_equal_eager_steps():
     """CUDA-graph replay of the train step (device-resident step scalars, lcn_step_scalars) reproduces the eager call
-    sequence: same Philox dropout counters, same TF1 Adam step sizes -> identical losses; parameters agree to float
+    sequence: same Philox dropout counters, same TF1 Adam step sizes -> losses and parameters agree to float
     rounding (the weight-gradient kernel accumulates row splits with floating-point reductions in arrival order)."""
     import torch
     n = 384
@@ -218,7 +218,7 @@ def test_graph_replayed_train_steps_equal_eager_steps():
         for _ in range(4):
             la.append(float(eng_a.train_step(xd, yd, dropout=0.25)[0].item()))
             lb.append(float(eng_b.train_step_graph(xd, yd, dropout=0.25)[0].item()))
-        assert la == lb, (path, la, lb)
+        assert np.allclose(la, lb, rtol=1e-5, atol=0), (path, la, lb)     # see docstring: fp reductions in arrival order
         assert eng_a.step == eng_b.step == 4
         assert torch.allclose(eng_a.params, eng_b.params, rtol=1e-4, atol=1e-6)
         assert torch.allclose(eng_a.adam_v, eng_b.adam_v, rtol=1e-3, atol=1e-12)
