@@ -138,7 +138,7 @@ def cpu_train_steps(batch, steps, warmup):
                 m[k].mul_(0.9).add_(w.grad, alpha=0.1)
                 v2[k].mul_(0.999).addcmul_(w.grad, w.grad, value=0.001)
                 w.sub_(lr_t * m[k] / (v2[k].sqrt() + 1e-8))
-        return float(loss)
+        return float(loss.detach())
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -191,7 +191,6 @@ def run_gpu(args, rank, world, local_rank):
     xd, yd = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
     x_pin, y_pin = torch.as_tensor(x).pin_memory(), torch.as_tensor(y).pin_memory()
     xe, ye = torch.empty_like(xd), torch.empty_like(yd)
-    loss_pin = torch.zeros(1).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     n_bn = 1 + 2 * LAYERS
 
@@ -230,17 +229,36 @@ def run_gpu(args, rank, world, local_rank):
         b.record()
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H loss ----
+    # ---- end to end through the public API: every step copies ITS inputs from pinned host memory to the device,
+    # runs the step and reads the loss back into pinned host memory.  The input copy of step i+1 runs on a copy
+    # stream into the other of two device buffers while step i computes (what an input pipeline does); the host
+    # waits for the GPU once, after the last loss has landed. ----
+    main_s = torch.cuda.current_stream()
+    copy_s = torch.cuda.Stream(device=dev)
+    bufs = [(xe, ye), (torch.empty_like(xd), torch.empty_like(yd))]
+    losses_pin = torch.zeros(args.steps).pin_memory()
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    for b in range(2):                               # graph capture / warm-up of both buffer sets, untimed
+        bufs[b][0].copy_(x_pin); bufs[b][1].copy_(y_pin)
+        step(*bufs[b])
+        consumed[b].record(main_s)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        xe.copy_(x_pin, non_blocking=True)
-        ye.copy_(y_pin, non_blocking=True)
-        step(xe, ye)
-        loss_pin.copy_(eng.loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    for i in range(args.steps):
+        b = i & 1
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(consumed[b])           # the step that last read this buffer pair has finished
+            bufs[b][0].copy_(x_pin, non_blocking=True)
+            bufs[b][1].copy_(y_pin, non_blocking=True)
+            copied[b].record(copy_s)
+        main_s.wait_event(copied[b])
+        step(*bufs[b])
+        consumed[b].record(main_s)
+        losses_pin[i:i + 1].copy_(eng.loss_dev, non_blocking=True)
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert bool(torch.isfinite(losses_pin).all()), "non-finite loss in the end-to-end loop"
     # ---- dominant kernel alone: forward mid-layer GEMM (block-sparse X*(W.M)) ----
     import ctypes as C
     from lcn_pose_b200 import _lib as L
