@@ -299,6 +299,63 @@ bool lcn_pdl_enabled() {
   return v == 1;
 }
 
+// ---- LCN_TRACE: per-kernel in-stream durations (debug) ----
+#include <map>
+#include <mutex>
+namespace {
+struct TraceRec { const void* func; cudaEvent_t a, b; };
+std::vector<TraceRec> g_trace;
+std::mutex g_trace_mu;
+}
+bool lcn_trace_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LCN_TRACE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+void lcn_trace_mark(const void* func, cudaStream_t st, int end) {
+  std::lock_guard<std::mutex> lock(g_trace_mu);
+  if (!end) {
+    TraceRec r;
+    r.func = func;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_trace.push_back(r);
+  } else if (!g_trace.empty()) {
+    cudaEventRecord(g_trace.back().b, st);
+  }
+}
+// prints "name launches total_us avg_us" per kernel and clears the trace; returns the number of records
+extern "C" int lcn_debug_trace_dump() {
+  std::lock_guard<std::mutex> lock(g_trace_mu);
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<int, double>> agg;
+  for (const TraceRec& r : g_trace) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    const char* name = nullptr;
+    if (cudaFuncGetName(&name, r.func) != cudaSuccess || name == nullptr) name = "?";
+    auto& e = agg[name];
+    e.first += 1;
+    e.second += ms * 1e3;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  double tot = 0;
+  for (auto& kv : agg) tot += kv.second.second;
+  for (auto& kv : agg)
+    printf("%-70.70s n=%5d total=%10.1f us avg=%8.2f us share=%5.1f%%\n", kv.first.c_str(), kv.second.first, kv.second.second,
+           kv.second.second / kv.second.first, 100.0 * kv.second.second / (tot > 0 ? tot : 1));
+  printf("traced launches %zu, total %.1f us\n", g_trace.size(), tot);
+  fflush(stdout);
+  int n = (int)g_trace.size();
+  g_trace.clear();
+  return n;
+}
+
 extern "C" int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,
                                  int64_t n_rows, int32_t bn_group, int training, float dropout_rate, uint64_t seed,
                                  uint64_t step, float* d_out, const lcn_step_scalars* d_dyn, void* stream) {

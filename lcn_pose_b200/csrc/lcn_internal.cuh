@@ -155,6 +155,10 @@ __device__ __forceinline__ void lcn_pdl_wait() {
 #endif
 }
 bool lcn_pdl_enabled();
+// LCN_TRACE=1 (profiling scripts only, eager launches): CUDA events around every lcn_launch; lcn_debug_trace_dump()
+// prints the in-stream duration of each kernel by name (warm caches, unlike an ncu launch list).
+bool lcn_trace_enabled();
+void lcn_trace_mark(const void* func, cudaStream_t st, int end);
 template <typename... KArgs, typename... Args>
 static inline void lcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -168,7 +172,10 @@ static inline void lcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = lcn_pdl_enabled() ? 1 : 0;
+  const bool trace = lcn_trace_enabled();
+  if (trace) lcn_trace_mark(reinterpret_cast<const void*>(kernel), st, 0);
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through LCN_CHECK_LAUNCH
+  if (trace) lcn_trace_mark(reinterpret_cast<const void*>(kernel), st, 1);
 }
 #define LCN_REQUIRE(cond, ...)   \
   do {                           \

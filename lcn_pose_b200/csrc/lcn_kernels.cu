@@ -613,6 +613,94 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act(const T* __restrict__ Z, 
   }
 }
 
+// Same arithmetic for ONE BatchNorm group in bf16 with <= BA_R rows per thread (training at batch <= ~4.7 k): every
+// load of the thread's rows (Z, residual) is issued before the first use, so the L2 latency is paid once per
+// block instead of once per row (the register double buffer of k_bn_act exposes it BA_R-1 times); the Philox
+// draws of the dropout mask overlap the loads.
+#define BA_R 8
+__global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act_pre(const __nv_bfloat16* __restrict__ Z,
+                                                           const float* __restrict__ stat,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const __nv_bfloat16* __restrict__ res,
+                                                           __nv_bfloat16* __restrict__ Aout,
+                                                           uint8_t* __restrict__ keepbits, int P, int F, int rows_pad,
+                                                           int bn_group, float rate, uint64_t seed, uint64_t step,
+                                                           int layer, const lcn_step_scalars* __restrict__ dyn) {
+  lcn_pdl_prologue();
+  __shared__ __align__(16) float s_sc[256], s_sh[256];
+  if (dyn != nullptr) step = dyn->step;
+  const int Y = blockDim.y, c8 = threadIdx.x * 8, f0 = c8 % F;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int per = ((rows_pad / Y + gridDim.x - 1) / gridDim.x) * Y;      // contiguous rows of this block (<= BA_R * Y)
+  const int r_begin = blockIdx.x * per, r_end = min(r_begin + per, rows_pad);
+  if (r_begin >= r_end) return;
+  uint4 zr[BA_R], rr[BA_R];
+#pragma unroll
+  for (int i = 0; i < BA_R; ++i) {
+    const int r = r_begin + threadIdx.y + i * Y;
+    zr[i] = make_uint4(0u, 0u, 0u, 0u);
+    rr[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < r_end && r < bn_group) {
+      const size_t o = lcn_off<__nv_bfloat16>(r, c8, P);
+      zr[i] = *reinterpret_cast<const uint4*>(Z + o);
+      if (res != nullptr) rr[i] = *reinterpret_cast<const uint4*>(res + o);
+    }
+  }
+  if (tid < F) {
+    const float mean = stat[tid * 2], rstd = stat[tid * 2 + 1];
+    const float a = gamma[tid] * rstd;
+    s_sc[tid] = a;
+    s_sh[tid] = beta[tid] - mean * a;
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    sc[q] = s_sc[f0 + q];
+    sh[q] = s_sh[f0 + q];
+  }
+  const float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+#pragma unroll
+  for (int i = 0; i < BA_R; ++i) {
+    const int r = r_begin + threadIdx.y + i * Y;
+    if (r >= r_end) continue;
+    float y[8];
+    uint32_t kb = 0xffu;
+    if (r >= bn_group) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y[q] = 0.f;
+    } else {
+      if (rate > 0.f) {
+        uint32_t rb[8];
+        const uint64_t i4 = ((uint64_t)r * P + c8) >> 2;
+        lcn_philox4(seed, step, (uint32_t)layer, i4, rb);
+        lcn_philox4(seed, step, (uint32_t)layer, i4 + 1, rb + 4);
+        kb = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) kb |= (lcn_keep(rb[q], rate) ? 1u : 0u) << q;
+      }
+      const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&zr[i]);
+      const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 z2 = __bfloat1622float2(hz[e]), r2 = __bfloat1622float2(hr[e]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int q = 2 * e + h;
+          float v = fmaf(h ? z2.y : z2.x, sc[q], sh[q]);
+          v = v > 0.f ? v : LCN_LRELU * v;
+          v = ((kb >> q) & 1u) ? v * inv_keep : 0.f;
+          if (res != nullptr) v += h ? r2.y : r2.x;
+          y[q] = v;
+        }
+      }
+    }
+    lcn_st8(Aout, lcn_off<__nv_bfloat16>(r, c8, P), y);
+    if (keepbits != nullptr && rate > 0.f) keepbits[(size_t)r * (P >> 3) + threadIdx.x] = (uint8_t)kb;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // last layer + output head: out = A * Wm4 + b4, xy residual from the 2D input (models_att.py:750-773)
 // grid tiles, 128 threads (thread = row), input chunks streamed through shared memory.
@@ -1492,7 +1580,20 @@ static int forward_impl(const FwdArgs& a) {
                             ? reinterpret_cast<uint8_t*>(ws + lay.off_keep) + (size_t)l * lay.rows_pad * (P / 8)
                             : nullptr;
     int ew_grid = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
-    lcn_launch(k_bn_act<T>, dim3(ew_grid), dim3(dim3(P / 8, ewy)), 0, st, Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
+    bool pre = false;
+    if constexpr (sizeof(T) == 2) {
+      // one BN group, <= BA_R rows per thread: all loads up front (k_bn_act_pre)
+      const int per = (int)(((lay.rows_pad / ewy + ew_grid - 1) / ew_grid) * ewy);
+      if (lay.n_groups == 1 && per <= BA_R * ewy && !getenv("LCN_DISABLE_BNACT_PRE")) {
+        pre = true;
+        lcn_launch(k_bn_act_pre, dim3(ew_grid), dim3(P / 8, ewy), 0, st, reinterpret_cast<const __nv_bfloat16*>(Z), stat,
+                   a.params + L.gamma_off, a.params + L.beta_off, reinterpret_cast<const __nv_bfloat16*>(res),
+                   reinterpret_cast<__nv_bfloat16*>(Aout), keepbits, P, F, (int)lay.rows_pad, lay.bn_group, a.dropout_rate,
+                   a.seed, a.step, l, a.dyn);
+      }
+    }
+    if (!pre)
+      lcn_launch(k_bn_act<T>, dim3(ew_grid), dim3(dim3(P / 8, ewy)), 0, st, Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
                                                       keepbits, P, F, (int)lay.rows_pad, lay.bn_group, lay.gstride,
                                                       a.dropout_rate, a.seed, a.step, l, a.dyn);
     LCN_CHECK_LAUNCH();
