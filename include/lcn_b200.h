@@ -165,7 +165,8 @@ int lcn_model_read_tensor(lcn_model* m, void* d_ws, size_t ws_bytes, int kind, i
                           int64_t n_rows, int32_t bn_group, float* d_dst, void* stream);
 
 /* Dropout keep decisions (1 = keep) exactly as the fused kernels draw them: Philox4x32-10 keyed on
- * seed, counter (element/4, layer, step).  tf.nn.dropout keeps u >= rate (models_att.py:673). */
+ * seed, counter (element/8, layer, step), 16 random bits per element (u = bits/65536, rate rounded up to a
+ * multiple of 2^-16).  tf.nn.dropout keeps u >= rate (models_att.py:673).  cols must be a multiple of 8. */
 int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int32_t cols, float rate,
                      uint8_t* d_keep, void* stream);
 

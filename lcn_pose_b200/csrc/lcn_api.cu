@@ -192,7 +192,19 @@ extern "C" int lcn_model_create(const lcn_model_desc* desc, lcn_model** out) {
   return LCN_OK;
 }
 
-extern "C" void lcn_model_destroy(lcn_model* m) { delete m; }
+extern "C" void lcn_model_destroy(lcn_model* m) {
+  if (m == nullptr) return;
+  if (m->aux.ready) {
+    cudaStreamDestroy(m->aux.st);
+    cudaEventDestroy(m->aux.ev_go);
+    cudaEventDestroy(m->aux.ev_done);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(m->aux.ev_dz[i]);
+      cudaEventDestroy(m->aux.ev_wg[i]);
+    }
+  }
+  delete m;
+}
 extern "C" int64_t lcn_model_param_count(const lcn_model* m) { return m ? m->n_params : 0; }
 extern "C" int lcn_model_num_tensors(const lcn_model* m) { return m ? (int)m->tensors.size() : 0; }
 extern "C" int lcn_model_tensor_info(const lcn_model* m, int index, char* name_buf, int name_buf_len, int64_t* offset,
@@ -258,7 +270,7 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_z = take(act * w.n_z);
   w.off_a = take(act * w.n_a);
   w.off_d = take(act * w.n_d);
-  w.off_dz = take(training ? act : 0);
+  w.off_dz = take(training ? 2 * act : 0);
   w.off_dbpart = take(training ? sizeof(float) * (size_t)m->n_bn * 2 * m->sm_count * P : 0);
   w.off_keep = take(training ? (size_t)m->n_bn * w.rows_pad * (P / 8) : 0);
   w.off_stack = take(w.fused ? lcn_stack_scratch_bytes(m, bn_group) : 0);

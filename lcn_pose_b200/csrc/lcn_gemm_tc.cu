@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
     }
   }
   if (warp == 2 && lane == 0 && p.mode != TC_MODE_HEAD) {
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; writes land by grid end
     TC_STAMP(4);
   }
   tc_fence_before();
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
     if (lane < 16) {
       for (int q = 0; q < len; ++q)
         bulk_reduce_add_f32(dW + (size_t)(ic * 64 + m) * p.ldw + ocs[q] * 64, smem_u32(out_s + m * TCW_PITCH + q * 64), 256);
-      bulk_commit_wait();
+      bulk_commit_wait_read();
     }
   }
   tc_fence_before();

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -62,7 +63,19 @@ struct TensorMeta {
   int rows, cols;
 };
 
+// Side stream of the backward pass (bf16 tensor-core path): the weight-gradient GEMM of layer l is off the critical
+// path (dZ_l -> dgrad_l -> BN backward of l-1 -> ...), so it is enqueued on a stream owned by the model and joined
+// with events (plain fork/join, capturable into the caller's CUDA graph).  Created on first use; `mu` serialises
+// the enqueue of concurrent backward calls on the same model (the events are shared).
+struct LcnAux {
+  std::mutex mu;
+  bool ready = false, failed = false;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_go = nullptr, ev_done = nullptr, ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
+};
+
 struct lcn_model {
+  mutable LcnAux aux;
   lcn_model_desc d;
   int n_lin, n_bn, P, FC, nnz;
   JointLists by_out, by_in;
@@ -108,7 +121,7 @@ struct WsLayout {
   size_t off_z, z_stride; int n_z;   // Z buffers
   size_t off_a, a_stride; int n_a;   // A buffers
   size_t off_d, d_stride; int n_d;   // gradient ping-pong buffers (training)
-  size_t off_dz;                     // dZ buffer (training)
+  size_t off_dz;                     // dZ buffers (training): layer l uses buffer l & 1 (wgrad of l overlaps BN backward of l-1)
   size_t off_dbpart;                 // float[n_bn][2*SMs][P] per-block bias-gradient partial rows (training)
   size_t off_keep;                   // uint8[n_bn][rows_pad][P/8] dropout keep bits (training)
   int fused;                         // inference runs as the fused cluster kernel (lcn_stack_tc.cu)
@@ -327,7 +340,7 @@ __device__ __forceinline__ void lcn_st8(__nv_bfloat16* p, size_t i, const float 
   *reinterpret_cast<uint4*>(p + i) = u;
 }
 
-// Philox4x32-10 counter-based generator; one call yields the 4 uniforms of elements 4*idx4 .. 4*idx4+3.
+// Philox4x32-10 counter-based generator; one call yields 128 random bits (lcn_keep8: the keep bits of 8 elements).
 __device__ __host__ __forceinline__ void lcn_philox4(uint64_t seed, uint64_t step, uint32_t layer, uint64_t idx4,
                                                      uint32_t out[4]) {
   uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = layer, c3 = (uint32_t)step;
@@ -345,7 +358,22 @@ __device__ __host__ __forceinline__ void lcn_philox4(uint64_t seed, uint64_t ste
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-// keep decision of tf.nn.dropout: u >= rate with u in [0,1) (24-bit)
-__device__ __host__ __forceinline__ bool lcn_keep(uint32_t bits, float rate) {
-  return (float)(bits >> 8) * (1.0f / 16777216.0f) >= rate;
+// keep decisions of tf.nn.dropout (u >= rate) for the 8 consecutive elements 8*idx8 .. 8*idx8+7: ONE Philox call,
+// 16 random bits per element (u = bits / 65536, rate rounded up to a multiple of 2^-16: exact for 0.25 / 0.5);
+// bit q of the result = element q kept.  Halves the integer work of the activation kernels, which were bound by
+// the instruction count of two Philox calls per 8 elements.
+__device__ __host__ __forceinline__ uint32_t lcn_keep_thr16(float rate) {
+  float t = rate * 65536.0f;
+  uint32_t u = (uint32_t)t;
+  if ((float)u < t) ++u;
+  return u > 65536u ? 65536u : u;
+}
+__device__ __host__ __forceinline__ uint32_t lcn_keep8(uint64_t seed, uint64_t step, uint32_t layer, uint64_t idx8,
+                                                       uint32_t thr16) {
+  uint32_t rb[4];
+  lcn_philox4(seed, step, layer, idx8, rb);
+  uint32_t kb = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) kb |= ((((rb[q >> 1] >> (16 * (q & 1))) & 0xffffu) >= thr16) ? 1u : 0u) << q;
+  return kb;
 }

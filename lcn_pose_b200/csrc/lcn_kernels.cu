@@ -262,8 +262,12 @@ __device__ __forceinline__ bool row_valid(const RowGeom& g, int64_t pr, int64_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// first layer: Z0 = X * Wm1 + b1  (models_att.py:729), K = 17*in_F, plus BN partials
-// grid (tiles, ceil(P/256)), 256 threads; thread = one output column, 128 rows
+// first layer: Z0 = X * Wm1 + b1  (models_att.py:729), K = 17*in_F, plus BN partials.  CUDA cores on purpose: K is
+// too small for an MMA tile and the fp32 input stays exact.
+// grid (tiles, P/64), 256 threads: a CTA owns a 128-row x 64-column tile, a thread 4 rows x 8 columns (the K loop
+// reads 3 x 16 B of shared memory per 32 FMAs; rows leave as 16-byte vectors of the tiled layout).  BN partials
+// (mean, M2 per column over the tile's valid rows) use sums shifted by the bias, reduced by shuffles across the 4
+// row groups of a warp and through shared memory across the 8 warps.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int IN_F>
 __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x, RowGeom g,
@@ -273,59 +277,99 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
   lcn_pdl_prologue();
   constexpr int KIN = LCN_J * IN_F;
   __shared__ __align__(16) float xs[KIN][LCN_TILE];
+  __shared__ __align__(16) float wsm[KIN][64];
+  __shared__ __align__(16) float red[8][64][2];
   __shared__ unsigned char valid_s[LCN_TILE];
-  int tile = blockIdx.x;
-  for (int e = threadIdx.x; e < LCN_TILE * KIN; e += blockDim.x) {
-    int r = e / KIN, k = e - r * KIN;
+  const int tile = blockIdx.x, col0 = blockIdx.y * 64;
+  {
+    // thread = (row, k parity): conflict-free shared-memory stores; the strided global reads of a row hit L1
+    const int r = threadIdx.x & (LCN_TILE - 1);
     int64_t src;
-    bool v = row_valid(g, (int64_t)tile * LCN_TILE + r, &src);
-    xs[k][r] = (src >= 0) ? x[src * KIN + k] : 0.f;
-    if (k == 0) valid_s[r] = v;
+    const bool v = row_valid(g, (int64_t)tile * LCN_TILE + r, &src);
+    if (threadIdx.x < LCN_TILE) valid_s[r] = v;
+    for (int k = threadIdx.x >> 7; k < KIN; k += 2) xs[k][r] = (src >= 0) ? x[src * KIN + k] : 0.f;
+  }
+  for (int e = threadIdx.x; e < KIN * 16; e += 256) {
+    int k = e >> 4, c4 = (e & 15) * 4;
+    *reinterpret_cast<float4*>(&wsm[k][c4]) = *reinterpret_cast<const float4*>(wm + (size_t)k * P + col0 + c4);
   }
   __syncthreads();
   if (x16 != nullptr && blockIdx.y == 0) {   // bf16 tile of the (zero padded) input: operand of the tensor-core wgrad
-    for (int e = threadIdx.x; e < LCN_TILE * 64; e += blockDim.x) {
+    for (int e = threadIdx.x; e < LCN_TILE * 64; e += 256) {
       int r = e >> 6, cc = e & 63;
       x16[lcn_off<__nv_bfloat16>((int64_t)tile * LCN_TILE + r, cc, 64)] = __float2bfloat16_rn(cc < KIN ? xs[cc][r] : 0.f);
     }
   }
-  int c = blockIdx.y * 256 + threadIdx.x;
-  if (c >= P) return;
-  float w[KIN];
+  const int cg = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c0 = cg * 8, r0 = rg * 4;
+  float b[8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + c0), b1 = *reinterpret_cast<const float4*>(bias + col0 + c0 + 4);
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  float acc[4][8];
 #pragma unroll
-  for (int k = 0; k < KIN; ++k) w[k] = wm[(size_t)k * P + c];
-  float b = bias[c];
-  float shift = 0.f, s1 = 0.f, s2 = 0.f;
-  int nv = 0;
-  for (int r4 = 0; r4 < LCN_TILE; r4 += 4) {
-    float acc[4] = {b, b, b, b};
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k < KIN; ++k) {
-      float4 xv = *reinterpret_cast<const float4*>(&xs[k][r4]);
-      acc[0] = fmaf(xv.x, w[k], acc[0]);
-      acc[1] = fmaf(xv.y, w[k], acc[1]);
-      acc[2] = fmaf(xv.z, w[k], acc[2]);
-      acc[3] = fmaf(xv.w, w[k], acc[3]);
+    for (int q = 0; q < 8; ++q) acc[i][q] = b[q];
+#pragma unroll 2
+  for (int k = 0; k < KIN; ++k) {
+    const float4 xv = *reinterpret_cast<const float4*>(&xs[k][r0]);
+    const float4 w0 = *reinterpret_cast<const float4*>(&wsm[k][c0]), w1 = *reinterpret_cast<const float4*>(&wsm[k][c0 + 4]);
+    const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(xr[i], wv[q], acc[i][q]);
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s1[q] = s2[q] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool v = valid_s[r0 + i];
+    float y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      y[q] = v ? acc[i][q] : 0.f;
+      const float d = v ? acc[i][q] - b[q] : 0.f;
+      s1[q] += d;
+      s2[q] = fmaf(d, d, s2[q]);
     }
+    lcn_st8(Z, lcn_off<T>((int64_t)tile * LCN_TILE + r0 + i, col0 + c0, P), y);
+  }
+  // reduce over the 32 row groups: lanes {cg, cg+8, cg+16, cg+24} of a warp, then the 8 warps
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int r = r4 + q;
-      bool v = valid_s[r];
-      float val = v ? acc[q] : 0.f;
-      lcn_st(Z, lcn_off<T>((int64_t)tile * LCN_TILE + r, c, P), val);
-      if (v) {
-        if (nv == 0) shift = val;
-        float d = val - shift;
-        s1 += d;
-        s2 = fmaf(d, d, s2);
-        ++nv;
-      }
+  for (int q = 0; q < 8; ++q) {
+    s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 8);
+    s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 8);
+    s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 16);
+    s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 16);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      red[warp][c0 + q][0] = s1[q];
+      red[warp][c0 + q][1] = s2[q];
     }
   }
-  float mean = shift + s1 / (float)nv;
-  float m2 = fmaxf(s2 - s1 * s1 / (float)nv, 0.f);
-  part[((size_t)tile * P + c) * 2 + 0] = mean;
-  part[((size_t)tile * P + c) * 2 + 1] = m2;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int tig = tile % (int)(g.gstride / LCN_TILE);
+    const int n = min(LCN_TILE, (int)g.bn_group - tig * LCN_TILE);   // valid rows of this tile (row_valid: rin < bn_group)
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      t1 += red[w][threadIdx.x][0];
+      t2 += red[w][threadIdx.x][1];
+    }
+    const float nf = (float)max(n, 1);
+    const int c = col0 + threadIdx.x;
+    *reinterpret_cast<float2*>(part + ((size_t)tile * P + c) * 2) =
+        make_float2(bias[c] + t1 / nf, fmaxf(t2 - t1 * t1 / nf, 0.f));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -532,6 +576,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act(const T* __restrict__ Z, 
   int r_begin = blockIdx.x * per, r_end = min(r_begin + per, rows_pad);
   if (r_begin >= r_end) return;
   float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  const uint32_t thr16 = lcn_keep_thr16(rate);
   float sc[8], sh[8];
   int cur_g = -1;
   float zc[8], rc[8], zn[8], rn[8];
@@ -583,13 +628,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act(const T* __restrict__ Z, 
         for (int q = 0; q < 8; ++q) y[q] = 0.f;
       } else {
         if (rate > 0.f) {
-          uint32_t rb[8];
-          uint64_t i4 = ((uint64_t)r * P + c8) >> 2;
-          lcn_philox4(seed, step, (uint32_t)layer, i4, rb);
-          lcn_philox4(seed, step, (uint32_t)layer, i4 + 1, rb + 4);
-          kb = 0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) kb |= (lcn_keep(rb[q], rate) ? 1u : 0u) << q;
+          kb = lcn_keep8(seed, step, (uint32_t)layer, ((uint64_t)r * P + c8) >> 3, thr16);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -661,6 +700,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act_pre(const __nv_bfloat16* 
     sh[q] = s_sh[f0 + q];
   }
   const float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  const uint32_t thr16 = lcn_keep_thr16(rate);
 #pragma unroll
   for (int i = 0; i < BA_R; ++i) {
     const int r = r_begin + threadIdx.y + i * Y;
@@ -672,13 +712,7 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act_pre(const __nv_bfloat16* 
       for (int q = 0; q < 8; ++q) y[q] = 0.f;
     } else {
       if (rate > 0.f) {
-        uint32_t rb[8];
-        const uint64_t i4 = ((uint64_t)r * P + c8) >> 2;
-        lcn_philox4(seed, step, (uint32_t)layer, i4, rb);
-        lcn_philox4(seed, step, (uint32_t)layer, i4 + 1, rb + 4);
-        kb = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) kb |= (lcn_keep(rb[q], rate) ? 1u : 0u) << q;
+        kb = lcn_keep8(seed, step, (uint32_t)layer, ((uint64_t)r * P + c8) >> 3, thr16);
       }
       const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&zr[i]);
       const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
@@ -1550,7 +1584,7 @@ static int forward_impl(const FwdArgs& a) {
     T* Z = reinterpret_cast<T*>(z_buf(ws, lay, l));
     T* Aout = reinterpret_cast<T*>(a_buf(ws, lay, l));
     if (l == 0) {
-      dim3 grid(lay.tiles, (P + 255) / 256);
+      dim3 grid(lay.tiles, P / 64);
       const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
       __nv_bfloat16* x16 = (tc && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
       switch (m->d.in_F) {
@@ -1619,12 +1653,46 @@ int lcn_launch_forward(const FwdArgs& a) {
   return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<float>(a);
 }
 
+// side stream + events of the model (LcnAux); nullptr when disabled (LCN_DISABLE_AUX_STREAM=1) or creation failed
+static LcnAux* lcn_aux_get(const lcn_model* m) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("LCN_DISABLE_AUX_STREAM");
+    enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  LcnAux& a = m->aux;
+  if (a.failed) return nullptr;
+  if (!a.ready) {
+    bool ok = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[6] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1]};
+    for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      (void)cudaGetLastError();
+      a.failed = true;
+      return nullptr;
+    }
+    a.ready = true;
+  }
+  return &a;
+}
+
 template <typename T>
 static int backward_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, const float* x,
                          const float* labels, float rate, uint64_t seed, uint64_t step, float* loss,
                          float* graw, cudaStream_t st) {
   const int P = m->P, F = m->d.F, FC = m->FC;
   const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  // weight-gradient GEMMs go to the model's side stream (see LcnAux); `wst` is the stream they are enqueued on
+  std::unique_lock<std::mutex> aux_lock;
+  LcnAux* ax = nullptr;
+  if (tc) {
+    aux_lock = std::unique_lock<std::mutex>(m->aux.mu);
+    ax = lcn_aux_get(m);
+    if (ax == nullptr) aux_lock.unlock();
+  }
+  cudaStream_t wst = ax ? ax->st : st;
+  bool wg_pending[2] = {false, false};
   size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
   LCN_CHECK_CUDA(cudaMemsetAsync(graw, 0, sizeof(float) * m->n_params, st));
   LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_loss, 0, 2 * sizeof(double), st));
@@ -1639,7 +1707,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   LCN_CHECK_LAUNCH();
 
   auto D = [&](int i) { return reinterpret_cast<T*>(ws + lay.off_d + (size_t)i * lay.d_stride); };
-  T* dZ = reinterpret_cast<T*>(ws + lay.off_dz);
+  auto dZbuf = [&](int l) { return reinterpret_cast<T*>(ws + lay.off_dz + (size_t)(l & 1) * lay.d_stride); };
   int last = m->n_lin - 1;
   int rows_blk = 512;
   while (lay.rows_pad % rows_blk) rows_blk >>= 1;   // rows_pad is a multiple of 128
@@ -1649,12 +1717,16 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     float* dwl = reinterpret_cast<float*>(ws + lay.off_dw_last);
     LCN_CHECK_CUDA(cudaMemsetAsync(dwl, 0, sizeof(float) * P * 64, st));
     LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_dw_first, 0, sizeof(float) * 64 * P, st));
+    if (ax) {                       // fork: everything enqueued so far (memsets, loss gradient) precedes the side stream
+      LCN_CHECK_CUDA(cudaEventRecord(ax->ev_go, st));
+      LCN_CHECK_CUDA(cudaStreamWaitEvent(wst, ax->ev_go, 0));
+    }
     int rc = lcn_tc_head_dgrad(m, lay, dout16, ws + lay.off_wl16b, reinterpret_cast<__nv_bfloat16*>(D(cur)), st);
     if (rc) return rc;
-    rc = lcn_tc_wgrad_last(m, lay, Ain, dout16, dwl, st);
+    rc = lcn_tc_wgrad_last(m, lay, Ain, dout16, dwl, wst);
     if (rc) return rc;
     LCN_CHECK_CUDA(cudaMemcpy2DAsync(graw + m->L[last].w_off, 51 * sizeof(float), dwl, 64 * sizeof(float),
-                                     51 * sizeof(float), P, cudaMemcpyDeviceToDevice, st));
+                                     51 * sizeof(float), P, cudaMemcpyDeviceToDevice, wst));
   } else {
     const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, m->n_bn - 1));
     lcn_launch(k_last_layer_bwd<T>, dim3(dim3((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256)), dim3(256), 0, st, 
@@ -1694,6 +1766,11 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     const float* stat = bn_stat(ws, lay, m, l);
     float* sums = reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)l * F * 2;
     const uint8_t* keepbits = reinterpret_cast<const uint8_t*>(ws + lay.off_keep) + (size_t)l * lay.rows_pad * (P / 8);
+    T* dZ = dZbuf(l);
+    if (ax && wg_pending[l & 1]) {   // the weight gradient of layer l+2 has read this dZ buffer
+      LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_wg[l & 1], 0));
+      wg_pending[l & 1] = false;
+    }
     if (fused_bwd) {
       if constexpr (sizeof(T) == 2) {
         unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)m->n_bn * F * 2) + l;
@@ -1711,12 +1788,16 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
           reinterpret_cast<float*>(ws + lay.off_dbpart) + (size_t)l * eg * P, graw + L.gamma_off, graw + L.beta_off, P, F, (int)lay.rows_pad, lay.bn_group, rate);
     }
     LCN_CHECK_LAUNCH();
+    if (ax) {                        // dZ_l is ready: the side stream may start the weight gradient of layer l
+      LCN_CHECK_CUDA(cudaEventRecord(ax->ev_dz[l & 1], st));
+      LCN_CHECK_CUDA(cudaStreamWaitEvent(wst, ax->ev_dz[l & 1], 0));
+    }
     if (l == 0 && tc) {
       float* dwf = reinterpret_cast<float*>(ws + lay.off_dw_first);
       int rc = lcn_tc_wgrad_first(m, lay, reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_x16),
-                                  reinterpret_cast<const __nv_bfloat16*>(dZ), dwf, st);
+                                  reinterpret_cast<const __nv_bfloat16*>(dZ), dwf, wst);
       if (rc) return rc;
-      LCN_CHECK_CUDA(cudaMemcpyAsync(graw + L.w_off, dwf, sizeof(float) * L.Kin * P, cudaMemcpyDeviceToDevice, st));
+      LCN_CHECK_CUDA(cudaMemcpyAsync(graw + L.w_off, dwf, sizeof(float) * L.Kin * P, cudaMemcpyDeviceToDevice, wst));
       break;
     }
     if (l == 0) {
@@ -1739,8 +1820,12 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     }
     if (tc) {
       int rc = lcn_tc_wgrad(m, lay, reinterpret_cast<const __nv_bfloat16*>(Ain),
-                            reinterpret_cast<const __nv_bfloat16*>(dZ), graw + L.w_off, st);
+                            reinterpret_cast<const __nv_bfloat16*>(dZ), graw + L.w_off, wst);
       if (rc) return rc;
+      if (ax) {
+        LCN_CHECK_CUDA(cudaEventRecord(ax->ev_wg[l & 1], wst));
+        wg_pending[l & 1] = true;
+      }
       const char* wp = ws + lay.off_wp16b + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
       rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), wp, nullptr,
                        reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(D(nxt)),
@@ -1756,6 +1841,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LCN_CHECK_LAUNCH();
     (void)keep;
     cur = nxt;
+  }
+  if (ax) {                          // join: the caller's stream continues after the last weight gradient
+    LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, wst));
+    LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   }
   {
     LinTable lb;
@@ -1874,18 +1963,18 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
 }
 
 // dropout keep decisions, exactly as k_bn_act draws them
-__global__ void k_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t n4, float rate, uint8_t* keep) {
+__global__ void k_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t n8, float rate, uint8_t* keep) {
   lcn_pdl_prologue();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t rb[4];
-    lcn_philox4(seed, step, (uint32_t)layer, (uint64_t)i, rb);
-    for (int q = 0; q < 4; ++q) keep[i * 4 + q] = lcn_keep(rb[q], rate) ? 1 : 0;
+  const uint32_t thr16 = lcn_keep_thr16(rate);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t kb = lcn_keep8(seed, step, (uint32_t)layer, (uint64_t)i, thr16);
+    for (int q = 0; q < 8; ++q) keep[i * 8 + q] = (uint8_t)((kb >> q) & 1u);
   }
 }
 extern "C" int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int32_t cols, float rate,
                                 uint8_t* d_keep, void* stream) {
-  LCN_REQUIRE(cols % 4 == 0, "cols must be a multiple of 4");
-  lcn_launch(k_dropout_mask, dim3(256), dim3(256), 0, (cudaStream_t)stream, seed, step, layer, rows * cols / 4, rate, d_keep);
+  LCN_REQUIRE(cols % 8 == 0, "cols must be a multiple of 8");
+  lcn_launch(k_dropout_mask, dim3(256), dim3(256), 0, (cudaStream_t)stream, seed, step, layer, rows * cols / 8, rate, d_keep);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
