@@ -193,17 +193,34 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    // head mode (last layer, models_att.py:765-773): row geometry and the row's xy inputs are fetched while the main
+    // loop runs (independent loads, all in flight before the accumulators are read)
+    int64_t src = -1;
+    bool valid = false;
+    float xr[2 * LCN_J];
+    if (p.mode == TC_MODE_HEAD) {
+      const int64_t pr = (int64_t)tile * LCN_TILE + row;
+      const int64_t grp = pr / p.gstride;
+      const int rin = (int)(pr - grp * p.gstride);
+      src = grp * p.bn_group + rin;
+      valid = rin < p.bn_group;
+      if (!(valid && src < p.n_rows)) src = -1;
+#pragma unroll
+      for (int j = 0; j < LCN_J; ++j) {
+        xr[2 * j] = src >= 0 ? p.x[src * (LCN_J * p.in_F) + j * p.in_F] : 0.f;
+        xr[2 * j + 1] = src >= 0 ? p.x[src * (LCN_J * p.in_F) + j * p.in_F + 1] : 0.f;
+      }
+    }
     mbar_wait(tfull, 0);
     if (threadIdx.x == 64) TC_STAMP(2);
     tc_fence_after();
     if (p.mode == TC_MODE_HEAD) {
-      // last layer: 51 valid columns of one chunk -> fp32 prediction rows (models_att.py:765-773)
-      int64_t pr = (int64_t)tile * LCN_TILE + row;
-      int64_t grp = pr / p.gstride;
-      int rin = (int)(pr - grp * p.gstride);
-      int64_t src = grp * p.bn_group + rin;
-      bool valid = rin < p.bn_group;
-      if (!(valid && src < p.n_rows)) src = -1;
+      // 51 valid columns of one chunk -> fp32 prediction rows: through a shared-memory tile (pitch 51 words: conflict
+      // free for thread = row), then coalesced stores
+      float* stg = reinterpret_cast<float*>(sgen);                          // [128][51]
+      int64_t* src_s = reinterpret_cast<int64_t*>(sgen + 128 * 51 * 4);     // [128]
+      src_s[row] = valid ? src : -2;                                        // -2: tile padding row (out_ws gets zeros)
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
         if (written & 1u) {
@@ -214,15 +231,22 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          int c = h * 32 + i;
+          const int c = h * 32 + i;
           if (c < 51) {
             float val = __uint_as_float(v[i]) + bias_s[c];
-            int j = c / 3, cc = c - j * 3;
-            if (cc < 2 && src >= 0) val += p.x[src * (LCN_J * p.in_F) + j * p.in_F + cc];
-            if (p.out_ws != nullptr) p.out_ws[(size_t)pr * 51 + c] = valid ? val : 0.f;
-            if (src >= 0) p.out_user[src * 51 + c] = val;
+            const int j = c / 3, cc = c - j * 3;
+            if (cc < 2) val += xr[2 * j + cc];
+            stg[row * 51 + c] = val;
           }
         }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int e = threadIdx.x - 64; e < 128 * 51; e += 128) {
+        const int r = e / 51, c = e - r * 51;
+        const int64_t sr = src_s[r];
+        const float val = stg[e];
+        if (p.out_ws != nullptr) p.out_ws[(size_t)tile * (LCN_TILE * 51) + e] = sr != -2 ? val : 0.f;
+        if (sr >= 0) p.out_user[sr * 51 + c] = val;
       }
     } else {
       for (int q = 0; q < G; ++q) {

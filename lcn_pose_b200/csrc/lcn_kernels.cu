@@ -205,6 +205,30 @@ __global__ void k_pack_first16(const float* __restrict__ wm_first, int Kin, int 
   }
 }
 
+// side stream + events of the model (LcnAux); nullptr when disabled (LCN_DISABLE_AUX_STREAM=1) or creation failed
+static LcnAux* lcn_aux_get(const lcn_model* m) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("LCN_DISABLE_AUX_STREAM");
+    enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  LcnAux& a = m->aux;
+  if (a.failed) return nullptr;
+  if (!a.ready) {
+    bool ok = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[6] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1]};
+    for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      (void)cudaGetLastError();
+      a.failed = true;
+      return nullptr;
+    }
+    a.ready = true;
+  }
+  return &a;
+}
+
 int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
                        bool recompute_norm, cudaStream_t st) {
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
@@ -220,20 +244,34 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
   lcn_launch(k_mask_scalars, dim3(1), dim3(320), 0, st, params, m->mask_off, m->sup, cmask, m->n_lin, m->d.max_norm, sc, mask);
   LCN_CHECK_LAUNCH();
   int last = m->n_lin - 1;
-  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
+  int n_mid = m->n_lin - 2;
+  const bool use_tc = m->d.path == LCN_PATH_BF16 && lcn_tc_enabled();
+  // the edge-layer packs (four small dependent launches) run on the model's side stream next to the mid-layer pack
+  std::unique_lock<std::mutex> aux_lock;
+  LcnAux* ax = nullptr;
+  if (use_tc && n_mid > 0) {
+    aux_lock = std::unique_lock<std::mutex>(m->aux.mu);
+    ax = lcn_aux_get(m);
+    if (ax == nullptr) aux_lock.unlock();
+  }
+  cudaStream_t est = ax ? ax->st : st;
+  if (ax) {
+    LCN_CHECK_CUDA(cudaEventRecord(ax->ev_go, st));
+    LCN_CHECK_CUDA(cudaStreamWaitEvent(est, ax->ev_go, 0));
+  }
+  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_first));
-  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
+  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_last));
   if (m->d.path == LCN_PATH_BF16) {
-    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_last),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
     if (m->L[0].Kin <= 64)
-      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
+      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
                                                     m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
   }
-  int n_mid = m->n_lin - 2;
-  const bool use_tc = m->d.path == LCN_PATH_BF16 && lcn_tc_enabled();
+  if (ax) LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, est));
   if (n_mid > 0) {
     lcn_launch(k_pack_mid, dim3(dim3(m->nnz * m->FC * m->FC, n_mid)), dim3(256), 0, st, 
         params, lt, make_pairs(m), m->sup, sc, mask, m->d.F, m->FC, m->nnz,
@@ -241,6 +279,7 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
         reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b), use_tc ? 0 : 1, use_tc ? 1 : 0);
   }
   LCN_CHECK_LAUNCH();
+  if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   return LCN_OK;
 }
 
@@ -1653,30 +1692,6 @@ int lcn_launch_forward(const FwdArgs& a) {
   return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<float>(a);
 }
 
-// side stream + events of the model (LcnAux); nullptr when disabled (LCN_DISABLE_AUX_STREAM=1) or creation failed
-static LcnAux* lcn_aux_get(const lcn_model* m) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("LCN_DISABLE_AUX_STREAM");
-    enabled = (e && e[0] == '1') ? 0 : 1;
-  }
-  if (!enabled) return nullptr;
-  LcnAux& a = m->aux;
-  if (a.failed) return nullptr;
-  if (!a.ready) {
-    bool ok = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[6] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1]};
-    for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) {
-      (void)cudaGetLastError();
-      a.failed = true;
-      return nullptr;
-    }
-    a.ready = true;
-  }
-  return &a;
-}
-
 template <typename T>
 static int backward_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, const float* x,
                          const float* labels, float rate, uint64_t seed, uint64_t step, float* loss,
@@ -1842,10 +1857,6 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     (void)keep;
     cur = nxt;
   }
-  if (ax) {                          // join: the caller's stream continues after the last weight gradient
-    LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, wst));
-    LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
-  }
   {
     LinTable lb;
     lb.n = m->n_bn;
@@ -1853,6 +1864,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     lcn_launch(k_db_reduce, dim3(dim3((P + 63) / 64, m->n_bn)), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_dbpart),
                                                               (int)eg, P, graw, lb);
     LCN_CHECK_LAUNCH();
+  }
+  if (ax) {                          // join: the caller's stream continues after the last weight gradient
+    LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, wst));
+    LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   }
   return LCN_OK;
 }
