@@ -198,6 +198,8 @@ extern "C" void lcn_model_destroy(lcn_model* m) {
     cudaStreamDestroy(m->aux.st);
     cudaEventDestroy(m->aux.ev_go);
     cudaEventDestroy(m->aux.ev_done);
+    cudaEventDestroy(m->aux.ev_ms);
+    cudaEventDestroy(m->aux.ev_loss);
     for (int i = 0; i < 2; ++i) {
       cudaEventDestroy(m->aux.ev_dz[i]);
       cudaEventDestroy(m->aux.ev_wg[i]);

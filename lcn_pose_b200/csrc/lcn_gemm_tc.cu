@@ -803,3 +803,5 @@ int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloa
   p.ldw = m->P;
   return launch_tc_wgrad(p, X16, dZ, dWpad, lay.tiles, m->sm_count, st);
 }
+
+LCN_KTRACE_EXPORT(gemm)

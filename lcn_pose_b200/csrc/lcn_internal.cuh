@@ -71,7 +71,8 @@ struct LcnAux {
   std::mutex mu;
   bool ready = false, failed = false;
   cudaStream_t st = nullptr;
-  cudaEvent_t ev_go = nullptr, ev_done = nullptr, ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
+  cudaEvent_t ev_go = nullptr, ev_done = nullptr, ev_ms = nullptr, ev_loss = nullptr;
+  cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
 };
 
 struct lcn_model {
@@ -150,11 +151,49 @@ void lcn_set_error(const char* fmt, ...);
 // the per-kernel launch latency and block ramp-up (measured: DESIGN.md section 6).  LCN_DISABLE_PDL=1 turns the
 // attribute off (the device-side instructions are then no-ops).
 // ---------------------------------------------------------------------------------------------------------------
+// -DLCN_KTRACE (profiling build only): block (0,0) of every kernel stamps %globaltimer right after its
+// griddepcontrol.wait, i.e. when its predecessor has completed -- the start-to-start distances are the effective
+// per-kernel costs of the step as replayed from the CUDA graph (profiles/ktrace_step.py).  One buffer per
+// translation unit, read back through lcn_ktrace_read_<tu>().
+#ifdef LCN_KTRACE
+#define LCN_KTRACE_MAX 8192
+static __device__ unsigned long long g_ktrace[2 * LCN_KTRACE_MAX];
+static __device__ unsigned g_ktrace_n;
+__device__ __forceinline__ void lcn_ktrace_stamp() {
+#if defined(__CUDA_ARCH__)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned i = atomicAdd(&g_ktrace_n, 1u);
+    if (i < LCN_KTRACE_MAX) {
+      g_ktrace[2 * i] = t;
+      g_ktrace[2 * i + 1] = ((unsigned long long)gridDim.x << 32) | ((unsigned long long)gridDim.y << 20) |
+                            ((unsigned long long)blockDim.x << 8) | (unsigned long long)blockDim.y;
+    }
+  }
+#endif
+}
+#define LCN_KTRACE_EXPORT(tu)                                                                        \
+  extern "C" int lcn_ktrace_read_##tu(unsigned long long* h_out, unsigned* h_n, int reset) {        \
+    cudaDeviceSynchronize();                                                                         \
+    if (cudaMemcpyFromSymbol(h_n, g_ktrace_n, sizeof(unsigned)) != cudaSuccess) return -2;           \
+    if (cudaMemcpyFromSymbol(h_out, g_ktrace, sizeof(g_ktrace)) != cudaSuccess) return -2;           \
+    if (reset) {                                                                                     \
+      unsigned z = 0;                                                                                \
+      cudaMemcpyToSymbol(g_ktrace_n, &z, sizeof(z));                                                 \
+    }                                                                                                \
+    return 0;                                                                                        \
+  }
+#else
+__device__ __forceinline__ void lcn_ktrace_stamp() {}
+#define LCN_KTRACE_EXPORT(tu)
+#endif
 __device__ __forceinline__ void lcn_pdl_prologue() {
 #if defined(__CUDA_ARCH__)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+  lcn_ktrace_stamp();
 }
 // split form: trigger at kernel start, wait after the kernel's own setup (barrier init, TMEM allocation)
 __device__ __forceinline__ void lcn_pdl_trigger() {
@@ -166,6 +205,7 @@ __device__ __forceinline__ void lcn_pdl_wait() {
 #if defined(__CUDA_ARCH__)
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+  lcn_ktrace_stamp();
 }
 bool lcn_pdl_enabled();
 // LCN_TRACE=1 (profiling scripts only, eager launches): CUDA events around every lcn_launch; lcn_debug_trace_dump()

@@ -184,8 +184,9 @@ __global__ void k_pack_last16(const float* __restrict__ wm_last, __nv_bfloat16* 
                               __nv_bfloat16* __restrict__ wl16b) {
   lcn_pdl_prologue();
   int kc = blockIdx.x;
-  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
-    int n = e >> 6, k = e & 63;      // n: output column jc, k: channel within chunk
+  // grid (chunks, 4): a CTA converts 16 channel rows; consecutive threads read consecutive output columns
+  for (int e = blockIdx.y * 1024 + threadIdx.x; e < (int)(blockIdx.y + 1) * 1024; e += blockDim.x) {
+    int k = e >> 6, n = e & 63;      // n: output column jc, k: channel within chunk
     float v = n < 51 ? wm_last[(size_t)(kc * 64 + k) * 51 + n] : 0.f;
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     wl16f[(size_t)kc * 4096 + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = h;
@@ -198,8 +199,8 @@ __global__ void k_pack_last16(const float* __restrict__ wm_last, __nv_bfloat16* 
 __global__ void k_pack_first16(const float* __restrict__ wm_first, int Kin, int P, __nv_bfloat16* __restrict__ wf16) {
   lcn_pdl_prologue();
   int oc = blockIdx.x;
-  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
-    int n = e >> 6, k = e & 63;
+  for (int e = blockIdx.y * 1024 + threadIdx.x; e < (int)(blockIdx.y + 1) * 1024; e += blockDim.x) {
+    int k = e >> 6, n = e & 63;      // consecutive threads read consecutive output columns of input feature k
     float v = k < Kin ? wm_first[(size_t)k * P + oc * 64 + n] : 0.f;
     wf16[(size_t)oc * 4096 + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
   }
@@ -217,8 +218,8 @@ static LcnAux* lcn_aux_get(const lcn_model* m) {
   if (a.failed) return nullptr;
   if (!a.ready) {
     bool ok = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[6] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1]};
-    for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
+    cudaEvent_t* evs[8] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1], &a.ev_ms, &a.ev_loss};
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       (void)cudaGetLastError();
       a.failed = true;
@@ -264,11 +265,11 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
   lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_last));
   if (m->d.path == LCN_PATH_BF16) {
-    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_last),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
                                                  reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
     if (m->L[0].Kin <= 64)
-      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
+      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
                                                     m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
   }
   if (ax) LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, est));
@@ -842,7 +843,7 @@ __global__ void __launch_bounds__(128) k_last_layer(const T* __restrict__ A, con
 __global__ void __launch_bounds__(256) k_loss_dout(const float* __restrict__ out_ws, const float* __restrict__ labels,
                                                    int64_t n_rows, float* __restrict__ dout,
                                                    __nv_bfloat16* __restrict__ dout16, float* __restrict__ db,
-                                                   double* loss_acc) {
+                                                   double* loss_acc, float* __restrict__ loss_out) {
   lcn_pdl_prologue();
   __shared__ double sh[32];
   __shared__ float csum[4][64];
@@ -850,8 +851,8 @@ __global__ void __launch_bounds__(256) k_loss_dout(const float* __restrict__ out
   float inv = 2.0f / ((float)n_rows * 51.f);
   double s = 0.0;
   float cs = 0.f;
-  int64_t pr0 = (int64_t)blockIdx.x * 64;
-  for (int r = rs; r < 64; r += 4) {
+  int64_t pr0 = (int64_t)blockIdx.x * 16;              // 16 rows per block (rows_pad is a multiple of 128)
+  for (int r = rs; r < 16; r += 4) {
     int64_t pr = pr0 + r;
     float gsc = 0.f;
     if (c < 51) {
@@ -868,14 +869,20 @@ __global__ void __launch_bounds__(256) k_loss_dout(const float* __restrict__ out
   }
   csum[rs][c] = cs;
   s = block_reduce_sum_d(s, sh);
-  if (threadIdx.x == 0) atomicAdd(loss_acc, s);
   __syncthreads();
   if (db != nullptr && threadIdx.x < 51)
     atomicAdd(&db[threadIdx.x], csum[0][threadIdx.x] + csum[1][threadIdx.x] + csum[2][threadIdx.x] + csum[3][threadIdx.x]);
-}
-__global__ void k_loss_final(const double* loss_acc, int64_t n_rows, float* loss_out) {
-  lcn_pdl_prologue();
-  loss_out[0] = (float)(loss_acc[0] / ((double)n_rows * 51.0));
+  // loss = mean((out - y)^2) (models_att.py:356): the block that arrives last divides the fp64 sum
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_acc, s);
+    __threadfence();
+    unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(loss_acc + 1), 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      double tot = *reinterpret_cast<volatile double*>(loss_acc);
+      loss_out[0] = (float)(tot / ((double)n_rows * 51.0));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1418,12 +1425,17 @@ __global__ void k_maskgrad(const float* __restrict__ params, int64_t mask_off, S
   __shared__ float dM[LCN_J * LCN_J];
   __shared__ float soft[LCN_J * LCN_J];
   int t = threadIdx.x;
-  if (t < n_lin) {
+  for (int l = t >> 5; l < n_lin; l += (int)(blockDim.x >> 5)) {      // one warp per layer, lanes over the pairs
     double s = 0.0;
-    for (int p = 0; p < nnz; ++p) s += (double)mask[pt.pi[p] * LCN_J + pt.pj[p]] * (double)pairdot[t * LCN_J * LCN_J + p];
-    sc[t].sdot = s;
-    double inv = sc[t].inv_norm;
-    sc[t].coef = sc[t].clipped > 0.f ? (float)(s * inv * inv * inv) : 0.f;
+    for (int p = t & 31; p < nnz; p += 32)
+      s += (double)mask[pt.pi[p] * LCN_J + pt.pj[p]] * (double)pairdot[l * LCN_J * LCN_J + p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((t & 31) == 0) {
+      sc[l].sdot = s;
+      double inv = sc[l].inv_norm;
+      sc[l].coef = sc[l].clipped > 0.f ? (float)(s * inv * inv * inv) : 0.f;
+    }
   }
   if (t < LCN_J * LCN_J) {
     int i = t / LCN_J, j = t % LCN_J;
@@ -1709,16 +1721,30 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   cudaStream_t wst = ax ? ax->st : st;
   bool wg_pending[2] = {false, false};
   size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
-  LCN_CHECK_CUDA(cudaMemsetAsync(graw, 0, sizeof(float) * m->n_params, st));
+  const int64_t blast = m->L[m->n_lin - 1].b_off;     // last-layer bias gradient: accumulated by k_loss_dout (caller's stream)
+  if (ax) {
+    // fork at the very start: the 4 B/parameter clear of the gradient bucket (the weight-gradient GEMMs reduce-add
+    // into it) leaves the critical path; the caller's stream only clears what its own first kernels accumulate into
+    LCN_CHECK_CUDA(cudaEventRecord(ax->ev_go, st));
+    LCN_CHECK_CUDA(cudaStreamWaitEvent(wst, ax->ev_go, 0));
+    LCN_CHECK_CUDA(cudaMemsetAsync(graw, 0, sizeof(float) * blast, wst));
+    if (blast + 51 < m->n_params)
+      LCN_CHECK_CUDA(cudaMemsetAsync(graw + blast + 51, 0, sizeof(float) * (m->n_params - blast - 51), wst));
+    LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_dw_last, 0, sizeof(float) * P * 64, wst));
+    LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_dw_first, 0, sizeof(float) * 64 * P, wst));
+    LCN_CHECK_CUDA(cudaEventRecord(ax->ev_ms, wst));
+    LCN_CHECK_CUDA(cudaMemsetAsync(graw + blast, 0, sizeof(float) * 51, st));
+  } else {
+    LCN_CHECK_CUDA(cudaMemsetAsync(graw, 0, sizeof(float) * m->n_params, st));
+  }
   LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_loss, 0, 2 * sizeof(double), st));
   LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_bnsum, 0, sizeof(float) * m->n_bn * (F * 2 + 1), st));   // sums + grid-barrier counters
   float* dout = reinterpret_cast<float*>(ws + lay.off_dout);
   double* lacc = reinterpret_cast<double*>(ws + lay.off_loss);
   __nv_bfloat16* dout16 = tc ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dout16) : nullptr;
-  lcn_launch(k_loss_dout, dim3((unsigned)(lay.rows_pad / 64)), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_out), labels,
+  lcn_launch(k_loss_dout, dim3((unsigned)(lay.rows_pad / 16)), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_out), labels,
                                                              lay.n_rows, dout, dout16,
-                                                             tc ? graw + m->L[m->n_lin - 1].b_off : nullptr, lacc);
-  lcn_launch(k_loss_final, dim3(1), dim3(1), 0, st, lacc, lay.n_rows, loss);
+                                                             tc ? graw + m->L[m->n_lin - 1].b_off : nullptr, lacc, loss);
   LCN_CHECK_LAUNCH();
 
   auto D = [&](int i) { return reinterpret_cast<T*>(ws + lay.off_d + (size_t)i * lay.d_stride); };
@@ -1730,11 +1756,12 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   if (tc) {
     const __nv_bfloat16* Ain = reinterpret_cast<const __nv_bfloat16*>(a_buf(ws, lay, m->n_bn - 1));
     float* dwl = reinterpret_cast<float*>(ws + lay.off_dw_last);
-    LCN_CHECK_CUDA(cudaMemsetAsync(dwl, 0, sizeof(float) * P * 64, st));
-    LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_dw_first, 0, sizeof(float) * 64 * P, st));
-    if (ax) {                       // fork: everything enqueued so far (memsets, loss gradient) precedes the side stream
-      LCN_CHECK_CUDA(cudaEventRecord(ax->ev_go, st));
-      LCN_CHECK_CUDA(cudaStreamWaitEvent(wst, ax->ev_go, 0));
+    if (ax) {                       // the loss gradient (caller's stream) precedes the last layer's weight gradient
+      LCN_CHECK_CUDA(cudaEventRecord(ax->ev_loss, st));
+      LCN_CHECK_CUDA(cudaStreamWaitEvent(wst, ax->ev_loss, 0));
+    } else {
+      LCN_CHECK_CUDA(cudaMemsetAsync(dwl, 0, sizeof(float) * P * 64, st));
+      LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_dw_first, 0, sizeof(float) * 64 * P, st));
     }
     int rc = lcn_tc_head_dgrad(m, lay, dout16, ws + lay.off_wl16b, reinterpret_cast<__nv_bfloat16*>(D(cur)), st);
     if (rc) return rc;
@@ -1775,6 +1802,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     fused_bwd = ok == 1;
   }
   PairTable pt = make_pairs(m);
+  if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_ms, 0));   // the bucket is clear before this stream stores into it
   for (int l = m->n_bn - 1; l >= 0; --l) {
     const LayerInfo& L = m->L[l];
     const T* Z = reinterpret_cast<const T*>(z_buf(ws, lay, l));
@@ -1993,3 +2021,5 @@ extern "C" int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
+
+LCN_KTRACE_EXPORT(kernels)
