@@ -23,16 +23,23 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "lcn_internal.cuh"
 
-#define TC_G 4                      // max output chunks (of 64 columns) per CTA -> 256 TMEM columns
-#define TC_STAGES 2
+#define TC_G 4                      // wgrad: max output chunks per unit
+#define TC_GMAX 6                   // forward / dgrad: max N-side chunks (of 64 columns) per CTA -> <= 384 of 512 TMEM columns
 #define TC_A_BYTES 16384            // 128 rows x 64 bf16
 #define TC_B_BYTES 8192             // one 64x64 bf16 block
-#define TC_STAGE_BYTES (TC_A_BYTES + TC_G * TC_B_BYTES)
-#define TC_THREADS 192
+#define TC_RING_UNITS 23            // operand ring: 23 x 8 KB; one K-chunk iteration takes 2 (A tile) + #blocks units
+#define TC_RING_BYTES (TC_RING_UNITS * TC_B_BYTES)
+#define TC_EPI_WARPS 8              // epilogue warps of k_tc_gemm: two per TMEM lane quarter (32 columns of a chunk each)
+#define TC_SMEM_BYTES (1024 + TC_RING_BYTES + 2 * TC_A_BYTES + TC_EPI_WARPS * 64 * 2 * 4)   // + 2 output staging tiles + BN partial scratch
+#define TC_THREADS 192              // wgrad kernel
+#define TC_MMA_WARPS 2               // MMA-issuing warps of k_tc_gemm (iteration it is issued by warp it % 2)
+#define TC_EPI_T0 (32 + 32 * TC_MMA_WARPS)                  // first epilogue thread
+#define TC_GEMM_THREADS (TC_EPI_T0 + 32 * TC_EPI_WARPS)
 #define TC_MAX_CHUNKS 34            // 17 joints x (F/64 <= 2) chunks on either side
 
 // optional per-CTA timeline (clock64) for block (0,0): enabled with -DLCN_TC_PROFILE
@@ -48,6 +55,16 @@ extern "C" int lcn_debug_read_prof(unsigned long long* h_out) {
 
 enum { TC_MODE_FWD = 0, TC_MODE_DGRAD = 1, TC_MODE_HEAD = 2 };
 
+// One entry of a CTA's schedule (built by the host, tc_fill_schedule): the K chunk of iteration `it`, which of the
+// group's N-side chunks have a block under it, where the iteration's operands sit in the shared-memory ring, which
+// earlier iteration must have been consumed before that ring space may be overwritten, and which accumulators are
+// complete once this iteration's MMAs have retired.
+#define TC_S_KC(s) ((s) & 63u)
+#define TC_S_BITS(s) (((s) >> 6) & 63u)
+#define TC_S_OFF(s) (((s) >> 12) & 31u)
+#define TC_S_WAIT(s) ((int)(((s) >> 17) & 127u) - 1)
+#define TC_S_DONE(s) (((s) >> 24) & 63u)
+
 struct TcParams {
   uint32_t kmask[LCN_J];            // K-side joint -> bitmask of N-side joints with a block
   int FCK, FCN;                     // 64-chunks per joint on the K side / N side
@@ -62,186 +79,216 @@ struct TcParams {
   int64_t n_rows;
   float* out_user;
   float* out_ws;
-  // per (N-side chunk group, K chunk) schedule, filled by the host (tc_fill_schedule): which chunks of the group have
-  // a block under this K chunk, and the slot of the first one in the packed panel.  Lives in the kernel parameters
-  // (constant bank) so that the producer / MMA warps index it with uniform loads and keep descriptors in uniform
-  // registers (a schedule in shared memory forces an R2UR per tcgen05.mma operand: measured 80-100 cycles per MMA).
-  uint8_t gbits[TC_MAX_CHUNKS][TC_MAX_CHUNKS];
-  uint16_t gslot[TC_MAX_CHUNKS][TC_MAX_CHUNKS];
+  // Per (N-side chunk group, iteration) schedule.  Lives in the kernel parameters (constant bank) so that the producer /
+  // MMA warps index it with uniform loads and keep descriptors in uniform registers (a schedule in shared memory forces
+  // an R2UR per tcgen05.mma operand: measured 80-100 cycles per MMA).
+  uint32_t sched[TC_MAX_CHUNKS][TC_MAX_CHUNKS];
+  // the MMAs of the iteration as runs of adjacent present chunks with equal accumulate state (one tcgen05.mma of
+  // N = 64 * len per K = 16 step): 6 bits per run = chunk q (3) | len - 1 (2) | accumulate (1), count in bits 60..63.
+  // Precomputed so that the single issuing warp spends its instructions on tcgen05.mma, not on bit scans.
+  uint64_t runs[TC_MAX_CHUNKS][TC_MAX_CHUNKS];
+  uint16_t gslot[TC_MAX_CHUNKS][TC_MAX_CHUNKS];   // [group][K chunk]: slot of the first present block in the packed panel
+  uint8_t gnit[TC_MAX_CHUNKS];                    // iterations of the group (K chunks with a block into it)
   uint8_t gwritten[TC_MAX_CHUNKS];
+  uint8_t gdcnt[TC_MAX_CHUNKS][TC_GMAX];          // per chunk of the group: MMA warps that issue into it (arrivals on done[q])
+  uint8_t gorder[TC_MAX_CHUNKS][TC_GMAX];         // the group's chunks in the order their accumulators complete
   uint8_t goc0[TC_MAX_CHUNKS + 1];  // group g owns N-side chunks [goc0[g], goc0[g+1]): contiguous, balanced by block count
 };
 
 #include "lcn_tc_ptx.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// forward / dgrad / head GEMM.  GMAX = max N-side chunks per CTA (64*GMAX TMEM columns).
+// forward / dgrad / head GEMM.
+//   Operand pipeline: a ring of 8 KB units in shared memory; iteration `it` (one K chunk) owns 2 + #blocks units and
+//   its own pair of single-use mbarriers (full[it]: bulk copies landed, empty[it]: MMAs retired), so there is no phase
+//   bookkeeping and the number of iterations in flight adapts to their size (about five for the knn=3 mask instead of
+//   three fixed 64 KB stages: the loop is bound by the L2 -> shared-memory copy rate, profiles/micro/bulk_bw2.csv).
+//   Two MMA warps: a tcgen05.mma of N = 64..256 executes in 48..128 cycles but costs the issuing warp about as much in
+//   barrier polls, descriptor moves to uniform registers and election (profiles/r1/timeline_tc_gemm.log), and the
+//   tensor pipe does not queue far ahead, so one issuer leaves it idle half of the time.  Warp 1 issues the even
+//   iterations, warp 2 the odd ones; the accumulators are zeroed by the epilogue warps first (tcgen05.st) so every MMA
+//   accumulates and the order in which the two warps reach the tensor pipe does not matter.
+//   Epilogue overlap: the host orders each group's K chunks so that its N-side chunks complete one after the other
+//   (tc_fill_schedule); the MMA warp commits to done[q] right after the last MMA into chunk q and the four epilogue
+//   warps convert / store / reduce that chunk while the remaining MMAs run.  Two 16 KB staging tiles alternate.
 // ---------------------------------------------------------------------------------------------
-template <int GMAX, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __restrict__ A,
+__global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16* __restrict__ A,
                                                         const __nv_bfloat16* __restrict__ Wp,
                                                         const float* __restrict__ bias,
                                                         const __nv_bfloat16* __restrict__ addend,
                                                         __nv_bfloat16* __restrict__ Y, float* __restrict__ part,
                                                         const __grid_constant__ TcParams p) {
   lcn_pdl_trigger();
-  constexpr int STAGE_BYTES = TC_A_BYTES + GMAX * TC_B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_CHUNKS + TC_GMAX];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[GMAX * 64];
+  __shared__ __align__(16) float bias_s[TC_GMAX * 64];
 
   uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x, tile = blockIdx.y;
   const int oc0 = p.goc0[g], G = p.goc0[g + 1] - oc0;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+  const int n_it = p.gnit[g];
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_CHUNKS]), done0 = smem_u32(&bars[2 * TC_MAX_CHUNKS]);
   const uint32_t tmem_cols = G <= 1 ? 64u : (G == 2 ? 128u : (G <= 4 ? 256u : 512u));
   TC_STAMP(0);
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    mbar_init(tfull, 1);
+  if (threadIdx.x < 2 * TC_MAX_CHUNKS + TC_GMAX) {
+    // every barrier is single use: one init each, in parallel.  done[q] collects one commit per MMA warp issuing into q
+    const int i = threadIdx.x;
+    const uint32_t cnt = i < 2 * TC_MAX_CHUNKS ? 1u : (uint32_t)max(1, (int)p.gdcnt[g][i - 2 * TC_MAX_CHUNKS]);
+    mbar_init(full0 + 8 * i, cnt);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
   const uint32_t tmem_base = tmem_base_s;
+  if (warp > TC_MMA_WARPS) {
+    // zero the accumulators: epilogue warp (lane quarter lq, half hh) clears its 32 lanes x half of the G*64 columns
+    const int ew0 = warp - 1 - TC_MMA_WARPS;
+    for (int c = (ew0 >> 2) * G; c < ((ew0 >> 2) + 1) * G; ++c)
+      tmem_st32_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c * 32);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+  }
+  if (warp >= 1) asm volatile("bar.sync 3, %0;" ::"n"(TC_GEMM_THREADS - 32) : "memory");   // MMA + epilogue warps
+  lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
   TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform; one elected lane issues) =====
     const __nv_bfloat16* a_tile = A + (size_t)tile * p.NCK * 8192;
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int kc = 0; kc < p.NCK; ++kc) {
-      const uint32_t bits = p.gbits[g][kc];
-      if (!bits) continue;
-      const uint32_t cnt = (uint32_t)__popc(bits);
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t s = p.sched[g][it];
+      const uint32_t kc = TC_S_KC(s), cnt = (uint32_t)__popc(TC_S_BITS(s));
+      const int wait = TC_S_WAIT(s);
       const __nv_bfloat16* wsrc = Wp + (size_t)p.gslot[g][kc] * 4096;
-      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      if (wait >= 0) {                                   // the iterations that occupied this ring space have been consumed:
+        mbar_wait(empty0 + 8 * wait, 0u);                // MMAs retire in order per issuing warp, so the newest iteration
+        if (wait >= 1) mbar_wait(empty0 + 8 * (wait - 1), 0u);   // of either parity covers all older ones
+      }
       if (elect_one()) {
         TC_STAMP(16 + 4 * it);
-        const uint32_t sa = sbase + s * STAGE_BYTES;
-        mbar_expect_tx(full0 + 8 * s, TC_A_BYTES + cnt * TC_B_BYTES);
-        bulk_g2s(sa, a_tile + (size_t)kc * 8192, TC_A_BYTES, full0 + 8 * s);
-        bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * s);
+        const uint32_t sa = sbase + TC_S_OFF(s) * TC_B_BYTES;
+        mbar_expect_tx(full0 + 8 * it, TC_A_BYTES + cnt * TC_B_BYTES);
+        bulk_g2s(sa, a_tile + (size_t)kc * 8192, TC_A_BYTES, full0 + 8 * it);
+        bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * it);
         TC_STAMP(17 + 4 * it);
       }
       __syncwarp();
-      ++it;
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform control flow and operands; one elected lane issues) =====
-    uint32_t written = 0;
+  } else if (warp <= TC_MMA_WARPS) {
+    // ===== MMA issuers (warp-uniform control flow and operands; one elected lane issues): warp w takes it % 2 == w - 1 =====
+    tc_fence_after();
     const uint64_t desc_hi = (uint64_t)((1024u >> 4) & 0x3FFF) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int kc = 0; kc < p.NCK; ++kc) {
-      const uint32_t bits = p.gbits[g][kc];
-      if (!bits) continue;
-      mbar_wait(full0 + 8 * s, ph);
+    const uint32_t idesc0 = umma_idesc(0, 0, 0);
+    for (int it = warp - 1; it < n_it; it += TC_MMA_WARPS) {
+      const uint32_t s = p.sched[g][it];
+      const uint64_t rw = p.runs[g][it];
+      const uint32_t bits = TC_S_BITS(s);
+      const int nr = (int)(rw >> 60);
+      mbar_wait(full0 + 8 * it, 0u);
       tc_fence_after();
-      const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+      const uint32_t sa = sbase + TC_S_OFF(s) * TC_B_BYTES, sb = sa + TC_A_BYTES;
       const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
       if (lane == 0) TC_STAMP(18 + 4 * it);
-      // run detection is warp-uniform (uniform registers); only the tcgen05 instructions sit under elect_one
-      int rank = 0, q = 0;
-      while (q < G) {
-        if (!((bits >> q) & 1u)) { ++q; continue; }
-        const uint32_t acc = (written >> q) & 1u;      // maximal run of present chunks with equal accumulate state
-        int len = 1;
-        while (len < 4 && q + len < G && ((bits >> (q + len)) & 1u) && (((written >> (q + len)) & 1u) == acc)) ++len;
-        const uint32_t idesc = umma_idesc(64 * len, 0, 0);
+#pragma unroll
+      for (int r = 0; r < TC_GMAX; ++r) {
+        if (r >= nr) break;
+        const uint32_t e = (uint32_t)(rw >> (6 * r)) & 63u;
+        const uint32_t q = e & 7u, len = ((e >> 3) & 3u) + 1u;
+        const uint32_t rank = (uint32_t)__popc(bits & ((1u << q) - 1u));   // blocks of the panel in front of chunk q
+        const uint32_t idesc = idesc0 | ((len * 8u) << 17);               // N = 64 * len
         const uint64_t bd0 = desc_hi | (uint64_t)(((sb + rank * TC_B_BYTES) >> 4) & 0x3FFF);
         const uint32_t d = tmem_base + q * 64;
         if (elect_one()) {
-          umma_f16(d, ad0, bd0, idesc, acc);       // K = 64 -> 4 instructions of K = 16 (32 bytes each)
+          umma_f16(d, ad0, bd0, idesc, 1u);        // K = 64 -> 4 instructions of K = 16 (32 bytes each)
           umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
           umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
           umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
         }
-        rank += len;
-        q += len;
       }
-      if (elect_one()) umma_commit(empty0 + 8 * s);     // frees the smem stage when these MMAs have read it
+      uint32_t done = TC_S_DONE(s);
+      if (elect_one()) {
+        umma_commit(empty0 + 8 * it);              // frees the ring space when these MMAs have read it
+        while (done) {                             // accumulators that received their last block in this iteration
+          const int dq = __ffs(done) - 1;
+          done &= done - 1;
+          umma_commit(done0 + 8 * dq);
+        }
+      }
       if (lane == 0) TC_STAMP(19 + 4 * it);
       __syncwarp();
-      written |= bits;
-      ++it;
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
-    if (elect_one()) umma_commit(tfull);  // accumulators complete
-    __syncwarp();
   } else {
-    // ===== epilogue: 4 warps, warp's TMEM lane quarter = warp id % 4 =====
+    // ===== epilogue: 8 warps; TMEM lane quarter = warp id % 4, column half of the chunk = epilogue warp / 4 =====
     const int lq = warp & 3;
+    const int ew = warp - 1 - TC_MMA_WARPS;          // 0..7
+    const int hh = ew >> 2;                          // 0: columns 0..31 of a chunk, 1: columns 32..63
     const int row = lq * 32 + lane;
+    const int et = threadIdx.x - TC_EPI_T0;          // 0..255
+    constexpr int ET = 32 * TC_EPI_WARPS;
     const uint32_t written = p.gwritten[g];
+    uint8_t* stage = sgen + TC_RING_BYTES;           // 2 x 16 KB output tiles (head mode: one fp32 tile)
     if (p.mode != TC_MODE_DGRAD) {
-      for (int c = threadIdx.x - 64; c < G * 64; c += 128) {
+      for (int c = et; c < G * 64; c += ET) {
         int col = oc0 * 64 + c;
         bias_s[c] = (p.mode == TC_MODE_HEAD && col >= 51) ? 0.f : bias[col];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 4, 256;" ::: "memory");
     }
-    // head mode (last layer, models_att.py:765-773): row geometry and the row's xy inputs are fetched while the main
-    // loop runs (independent loads, all in flight before the accumulators are read)
-    int64_t src = -1;
-    bool valid = false;
-    float xr[2 * LCN_J];
     if (p.mode == TC_MODE_HEAD) {
+      // head mode (last layer, models_att.py:765-773): row geometry and the row's xy inputs are fetched while the main
+      // loop runs (independent loads, all in flight before the accumulators are read)
       const int64_t pr = (int64_t)tile * LCN_TILE + row;
       const int64_t grp = pr / p.gstride;
       const int rin = (int)(pr - grp * p.gstride);
-      src = grp * p.bn_group + rin;
-      valid = rin < p.bn_group;
+      int64_t src = grp * p.bn_group + rin;
+      const bool valid = rin < p.bn_group;
       if (!(valid && src < p.n_rows)) src = -1;
+      float xr[2 * LCN_J];
 #pragma unroll
       for (int j = 0; j < LCN_J; ++j) {
         xr[2 * j] = src >= 0 ? p.x[src * (LCN_J * p.in_F) + j * p.in_F] : 0.f;
         xr[2 * j + 1] = src >= 0 ? p.x[src * (LCN_J * p.in_F) + j * p.in_F + 1] : 0.f;
       }
-    }
-    mbar_wait(tfull, 0);
-    if (threadIdx.x == 64) TC_STAMP(2);
-    tc_fence_after();
-    if (p.mode == TC_MODE_HEAD) {
+      if (written & 1u) mbar_wait(done0, 0u);
+      if (et == 0) TC_STAMP(2);
+      tc_fence_after();
       // 51 valid columns of one chunk -> fp32 prediction rows: through a shared-memory tile (pitch 51 words: conflict
       // free for thread = row), then coalesced stores
-      float* stg = reinterpret_cast<float*>(sgen);                          // [128][51]
-      int64_t* src_s = reinterpret_cast<int64_t*>(sgen + 128 * 51 * 4);     // [128]
-      src_s[row] = valid ? src : -2;                                        // -2: tile padding row (out_ws gets zeros)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      float* stg = reinterpret_cast<float*>(stage);                          // [128][51]
+      int64_t* src_s = reinterpret_cast<int64_t*>(stage + 128 * 51 * 4);     // [128]
+      if (hh == 0) src_s[row] = valid ? src : -2;                            // -2: tile padding row (out_ws gets zeros)
+      {
         uint32_t v[32];
         if (written & 1u) {
-          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + h * 32, v);
+          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + hh * 32, v);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
+        // (two compile-time instances of the column loop: xr[] must be indexed with constants to stay in registers)
+        auto emit = [&](auto half) {
+          constexpr int H = decltype(half)::value;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = h * 32 + i;
-          if (c < 51) {
-            float val = __uint_as_float(v[i]) + bias_s[c];
-            const int j = c / 3, cc = c - j * 3;
-            if (cc < 2) val += xr[2 * j + cc];
-            stg[row * 51 + c] = val;
+          for (int i = 0; i < 32; ++i) {
+            const int c = H * 32 + i;
+            if (c < 51) {
+              float val = __uint_as_float(v[i]) + bias_s[c];
+              const int j = c / 3, cc = c - j * 3;
+              if (cc < 2) val += xr[2 * j + cc];
+              stg[row * 51 + c] = val;
+            }
           }
-        }
+        };
+        if (hh == 0) emit(std::integral_constant<int, 0>{}); else emit(std::integral_constant<int, 1>{});
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int e = threadIdx.x - 64; e < 128 * 51; e += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = et; e < 128 * 51; e += ET) {
         const int r = e / 51, c = e - r * 51;
         const int64_t sr = src_s[r];
         const float val = stg[e];
@@ -249,19 +296,47 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
         if (sr >= 0) p.out_user[sr * 51 + c] = val;
       }
     } else {
-      for (int q = 0; q < G; ++q) {
-        uint8_t* tile_s = sgen + q * TC_A_BYTES;
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          if ((written >> q) & 1u) {
-            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + q * 64 + h * 32, v);
-          } else {
+      // Two teams of four warps (one warp per TMEM lane quarter) take alternate chunks of the completion order, each
+      // with its own staging tile, named barrier and reduction scratch: a chunk's epilogue is a chain of latencies
+      // (commit -> mbarrier, tcgen05.ld, shared-memory round trips, barriers: ~2.5 k cycles measured whether four or
+      // eight warps share it), so two chunks in flight halve the time the accumulators wait for their epilogue.
+      const int team = ew >> 2;
+      const int tt = et & 127;                                               // thread within the team
+      const uint32_t bar_id = 1u + (uint32_t)team;
+      const int tig = tile % (p.gstride / LCN_TILE);
+      const int nvalid = min(LCN_TILE, p.bn_group - tig * LCN_TILE);
+      const float rn = 1.f / (float)nvalid;
+      uint8_t* tile_s = stage + team * TC_A_BYTES;
+      float* red = reinterpret_cast<float*>(stage + 2 * TC_A_BYTES) + team * (4 * 64 * 2);   // [4 warps][64 columns][s1, s2]
+      for (int e = team; e < G; e += 2) {
+        const int q = p.gorder[g][e];
+        const bool has = (written >> q) & 1u;
+        if (e >= 2) {
+          // the team's previous bulk store has read the staging tile (its BN partials were read before the last barrier)
+          if (tt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
+        if (has) {
+          mbar_wait(done0 + 8 * q, 0u);
+          tc_fence_after();
+        }
+        if (et == 0 && e == 0) TC_STAMP(2);
+        if (tt == 0) TC_STAMP(200 + 8 * e);
+        uint32_t v0[32], v1[32];
+        if (has) {
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(lq * 32) << 16) + q * 64, v0);
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(lq * 32) << 16) + q * 64 + 32, v1);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0u;
-          }
+          for (int i = 0; i < 32; ++i) v0[i] = v1[i] = 0u;
+        }
+        if (tt == 0) TC_STAMP(201 + 8 * e);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(h ? v1[i] : v0[i]);
           if (p.mode == TC_MODE_FWD) {
             const float4* b4 = reinterpret_cast<const float4*>(bias_s + q * 64 + h * 32);
 #pragma unroll
@@ -277,10 +352,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
               uint4 u = *reinterpret_cast<const uint4*>(arow + (((h * 4 + c) ^ (row & 7)) << 4));
               const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 t = __bfloat1622float2(hp[e]);
-                f[c * 8 + 2 * e] += t.x;
-                f[c * 8 + 2 * e + 1] += t.y;
+              for (int k = 0; k < 4; ++k) {
+                float2 t = __bfloat1622float2(hp[k]);
+                f[c * 8 + 2 * k] += t.x;
+                f[c * 8 + 2 * k + 1] += t.y;
               }
             }
           }
@@ -299,69 +374,66 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_gemm(const __nv_bfloat16* __r
             *reinterpret_cast<uint4*>(tile_s + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = u;
           }
         }
-      }
-      if (threadIdx.x == 64) TC_STAMP(3);
-      tc_fence_before();
-      fence_proxy_async();                                   // generic smem writes -> bulk-store (async proxy) reads
-      asm volatile("bar.sync 1, 128;" ::: "memory");         // the 4 epilogue warps
-      if (warp == 2 && lane == 0) {
-        for (int q = 0; q < G; ++q)
-          bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * 8192, sbase + q * TC_A_BYTES, TC_A_BYTES);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    }
-    if (threadIdx.x == 64) TC_STAMP(5);
-  }
-  if (p.mode == TC_MODE_FWD && part != nullptr) {
-    // BatchNorm partials of this tile: per column (mean, M2) over the valid rows, from the bf16 values staged in
-    // shared memory.  All six warps take part (the producer and MMA warps are idle by now): warp w handles chunks
-    // w, w+6, ...; a lane owns two columns and walks the rows with a shifted sum / sum of squares.
-    __syncwarp();
-    asm volatile("bar.sync 2, 192;" ::: "memory");
-    // rows r = warp, warp + 6, ... of every chunk; a lane owns two columns.  Sums are shifted by the chunk's row-0
-    // value (the same shift in every warp, so the partial sums of the six warps simply add).
-    const int tig = tile % (p.gstride / LCN_TILE);
-    const int nvalid = min(LCN_TILE, p.bn_group - tig * LCN_TILE);
-    float* red = reinterpret_cast<float*>(sgen + GMAX * TC_A_BYTES);       // [6 warps][G][64 columns][s1, s2]
-    const uint32_t coff = (uint32_t)(lane & 3) * 4;
-    const int chunk = lane >> 2;
-    for (int q = 0; q < G; ++q) {
-      const uint8_t* tile_s = sgen + q * TC_A_BYTES;
-      float sh0, sh1, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-      {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + (chunk << 4) + coff);
-        float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-        sh0 = t.x; sh1 = t.y;
-      }
-#pragma unroll 4
-      for (int r = warp; r < nvalid; r += 6) {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
-        float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-        float d0 = t.x - sh0, d1 = t.y - sh1;
-        s1a += d0; s2a = fmaf(d0, d0, s2a);
-        s1b += d1; s2b = fmaf(d1, d1, s2b);
-      }
-      *reinterpret_cast<float4*>(red + ((size_t)(warp * G + q) * 64 + lane * 2) * 2) = make_float4(s1a, s2a, s1b, s2b);
-    }
-    asm volatile("bar.sync 2, 192;" ::: "memory");
-    const float n = (float)nvalid;
-    for (int c = threadIdx.x; c < G * 64; c += TC_THREADS) {
-      const int q = c >> 6, col = c & 63;
-      float s1 = 0.f, s2 = 0.f;
+        if (tt == 0) TC_STAMP(202 + 8 * e);
+        tc_fence_before();
+        fence_proxy_async();                                   // generic smem writes -> bulk-store (async proxy) reads
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the 4 warps of the team
+        if (tt == 0) {
+          TC_STAMP(203 + 8 * e);
+          bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * 8192, smem_u32(tile_s), TC_A_BYTES);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.mode == TC_MODE_FWD && part != nullptr) {
+          // BatchNorm partials of this tile and chunk: per column (mean, M2) over the valid rows, from the bf16 values
+          // staged in shared memory (what k_bn_act will read).  Warp w walks rows w, w+4, ...; a lane owns two columns;
+          // sums are shifted by the chunk's row-0 value (the same shift in every warp, so the four partial sums add).
+          // Constant trip count: all 32 loads of the lane are in flight before the first add.
+          const uint32_t coff = (uint32_t)(lane & 3) * 4;
+          const int chunk = lane >> 2;
+          uint32_t w[32];
 #pragma unroll
-      for (int w = 0; w < 6; ++w) {
-        const float2 v = *reinterpret_cast<const float2*>(red + ((size_t)(w * G + q) * 64 + col) * 2);
-        s1 += v.x; s2 += v.y;
+          for (int i = 0; i < 32; ++i) {
+            const int r = lq + 4 * i;
+            w[i] = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
+          }
+          const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile_s + (chunk << 4) + coff);
+          const float2 sh2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (lq + 4 * i < nvalid) {
+              float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              float d0 = t.x - sh2.x, d1 = t.y - sh2.y;
+              s1a += d0; s2a = fmaf(d0, d0, s2a);
+              s1b += d1; s2b = fmaf(d1, d1, s2b);
+            }
+          }
+          *reinterpret_cast<float4*>(red + ((size_t)lq * 64 + lane * 2) * 2) = make_float4(s1a, s2a, s1b, s2b);
+          if (tt == 0) TC_STAMP(204 + 8 * e);
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (tt == 0) TC_STAMP(205 + 8 * e);
+          if (tt < 64) {
+            const int col = tt;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 4; ++ww) {
+              const float2 v = *reinterpret_cast<const float2*>(red + ((size_t)ww * 64 + col) * 2);
+              s1 += v.x; s2 += v.y;
+            }
+            const float sh = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile_s + ((col >> 3) << 4) + (col & 7) * 2));
+            *reinterpret_cast<float2*>(part + ((size_t)tile * p.P + (oc0 + q) * 64 + col) * 2) =
+                make_float2(fmaf(s1, rn, sh), fmaxf(s2 - s1 * s1 * rn, 0.f));
+          }
+          if (tt == 0) TC_STAMP(206 + 8 * e);
+        }
       }
-      const uint8_t* tile_s = sgen + q * TC_A_BYTES;
-      const float sh = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile_s + (((col >> 3)) << 4) + (col & 7) * 2));
-      *reinterpret_cast<float2*>(part + ((size_t)tile * p.P + (oc0 + q) * 64 + col) * 2) =
-          make_float2(sh + s1 / n, fmaxf(s2 - s1 * s1 / n, 0.f));
+      if (tt == 0) {
+        if (et == 0) TC_STAMP(3);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; writes land by grid end
+        if (et == 0) TC_STAMP(4);
+      }
     }
-  }
-  if (warp == 2 && lane == 0 && p.mode != TC_MODE_HEAD) {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; writes land by grid end
-    TC_STAMP(4);
+    if (et == 0) TC_STAMP(5);
   }
   tc_fence_before();
   __syncthreads();
@@ -381,17 +453,14 @@ bool lcn_tc_enabled() {
   return v == 1;
 }
 
-template <int GMAX, int STAGES>
-static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
-                          const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, const TcParams& p, int tiles,
-                          cudaStream_t st) {
-  size_t smem = (size_t)STAGES * (TC_A_BYTES + GMAX * TC_B_BYTES) + 1024;
+static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* addend,
+                          __nv_bfloat16* Y, float* part, const TcParams& p, int tiles, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm<GMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr = true;
   }
-  lcn_launch(k_tc_gemm<GMAX, STAGES>, dim3(dim3(p.n_groups, tiles)), dim3(TC_THREADS), smem, st, A, W, bias, addend, Y, part, p);
+  lcn_launch(k_tc_gemm, dim3(dim3(p.n_groups, tiles)), dim3(TC_GEMM_THREADS), (size_t)TC_SMEM_BYTES, st, A, W, bias, addend, Y, part, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
@@ -404,7 +473,7 @@ static int tc_col_blocks(const TcParams& p, int oc) {
   return n;
 }
 
-// contiguous split of the N-side chunks into ng groups of <= 6 chunks minimising the largest block count
+// contiguous split of the N-side chunks into ng groups of <= TC_GMAX chunks minimising the largest block count
 // (a CTA's main-loop time is proportional to its blocks); returns that maximum.  DP over (groups, chunks).
 static int tc_partition(const TcParams& p, int ng, uint8_t* goc0) {
   const int NC = p.NCN, INF = 1 << 28;
@@ -417,7 +486,7 @@ static int tc_partition(const TcParams& p, int ng, uint8_t* goc0) {
   best[0][0] = 0;
   for (int k = 1; k <= ng; ++k)
     for (int c = k; c <= NC; ++c)
-      for (int a = 1; a <= 6 && a <= c; ++a) {
+      for (int a = 1; a <= TC_GMAX && a <= c; ++a) {
         if (best[k - 1][c - a] >= INF) continue;
         int load = pre[c] - pre[c - a];
         int v = best[k - 1][c - a] > load ? best[k - 1][c - a] : load;
@@ -433,20 +502,31 @@ static int tc_partition(const TcParams& p, int ng, uint8_t* goc0) {
   return best[ng][NC];
 }
 
-// per (group, K chunk): present bits of the group's chunks and the slot of the first present block (k_pack_mid order)
+// Per group: the K-chunk order, the ring placement of every iteration and the completion order of the accumulators.
+//   order: greedy -- repeatedly take the N-side chunk with the fewest K chunks still missing and schedule those, so
+//          the chunks of a group finish one after the other and their epilogues overlap the remaining MMAs;
+//   ring : iteration `it` takes 2 + #blocks units at the running head (wrapping when it does not fit before the end);
+//          `wait` = the newest earlier iteration whose units it overwrites (MMAs retire in order, so waiting for that
+//          one's empty barrier covers all older ones);
+//   slot : position of the iteration's first block in the packed panel (k_pack_mid order).
 static void tc_fill_schedule(TcParams& p) {
-  memset(p.gbits, 0, sizeof(p.gbits));
+  memset(p.sched, 0, sizeof(p.sched));
+  memset(p.runs, 0, sizeof(p.runs));
   memset(p.gslot, 0, sizeof(p.gslot));
+  memset(p.gnit, 0, sizeof(p.gnit));
   memset(p.gwritten, 0, sizeof(p.gwritten));
+  memset(p.gorder, 0, sizeof(p.gorder));
+  memset(p.gdcnt, 0, sizeof(p.gdcnt));
   for (int g = 0; g < p.n_groups; ++g) {
     const int oc0 = p.goc0[g], G = p.goc0[g + 1] - oc0;
+    uint32_t kbits[TC_MAX_CHUNKS];                    // per K chunk: present chunks of the group
     for (int kc = 0; kc < p.NCK; ++kc) {
       const int ka = kc / p.FCK, hk = kc - ka * p.FCK;
       const uint32_t km = p.kmask[ka];
       uint32_t bits = 0;
       for (int q = 0; q < G; ++q)
         if ((km >> ((oc0 + q) / p.FCN)) & 1u) bits |= 1u << q;
-      p.gbits[g][kc] = (uint8_t)bits;
+      kbits[kc] = bits;
       p.gwritten[g] |= (uint8_t)bits;
       if (bits) {
         const int oc = oc0 + __builtin_ctz(bits);
@@ -457,31 +537,125 @@ static void tc_fill_schedule(TcParams& p) {
                                     __builtin_popcount(km & ((1u << nb) - 1u)) * p.FCN + hn);
       }
     }
+    // greedy completion order
+    int order[TC_MAX_CHUNKS], n_it = 0, n_done = 0;
+    uint32_t done_after[TC_MAX_CHUNKS];               // per iteration: chunks complete after it
+    memset(done_after, 0, sizeof(done_after));
+    bool used[TC_MAX_CHUNKS] = {false};
+    uint32_t finished = 0;
+    for (int q = 0; q < G; ++q)
+      if (!((p.gwritten[g] >> q) & 1u)) {             // no block at all: nothing to wait for, zeros are stored
+        finished |= 1u << q;
+        p.gorder[g][n_done++] = (uint8_t)q;
+      }
+    while (n_done < G) {
+      int bq = -1, bmiss = 1 << 30;
+      for (int q = 0; q < G; ++q) {
+        if ((finished >> q) & 1u) continue;
+        int miss = 0;
+        for (int kc = 0; kc < p.NCK; ++kc)
+          if (!used[kc] && ((kbits[kc] >> q) & 1u)) ++miss;
+        if (miss < bmiss) { bmiss = miss; bq = q; }
+      }
+      for (int kc = 0; kc < p.NCK; ++kc)
+        if (!used[kc] && ((kbits[kc] >> bq) & 1u)) {
+          used[kc] = true;
+          order[n_it++] = kc;
+        }
+      // every chunk whose K chunks are now all scheduled completes with the last iteration added
+      for (int q = 0; q < G; ++q) {
+        if ((finished >> q) & 1u) continue;
+        bool all = true;
+        for (int kc = 0; kc < p.NCK; ++kc)
+          if (!used[kc] && ((kbits[kc] >> q) & 1u)) { all = false; break; }
+        if (all) {
+          finished |= 1u << q;
+          p.gorder[g][n_done++] = (uint8_t)q;
+        }
+      }
+    }
+    // Completion: MMA warp w issues the iterations it % TC_MMA_WARPS == w and commits to done[q] after its own last
+    // iteration touching chunk q; done[q] expects one arrival per warp that touches q.  The epilogue visits the chunks
+    // in the order of their overall last iteration.
+    {
+      int comp[TC_GMAX];
+      for (int q = 0; q < G; ++q) {
+        comp[q] = -1;
+        int cnt = 0;
+        for (int w = 0; w < TC_MMA_WARPS; ++w) {
+          int last = -1;
+          for (int i = w; i < n_it; i += TC_MMA_WARPS)
+            if ((kbits[order[i]] >> q) & 1u) last = i;
+          if (last >= 0) {
+            done_after[last] |= 1u << q;
+            ++cnt;
+            if (last > comp[q]) comp[q] = last;
+          }
+        }
+        p.gdcnt[g][q] = (uint8_t)cnt;
+      }
+      int ce[TC_GMAX];
+      for (int e = 0; e < G; ++e) ce[e] = comp[p.gorder[g][e]];
+      for (int a = 1; a < G; ++a)                     // insertion sort, stable
+        for (int b = a; b > 0 && ce[b - 1] > ce[b]; --b) {
+          int t = ce[b]; ce[b] = ce[b - 1]; ce[b - 1] = t;
+          uint8_t u = p.gorder[g][b]; p.gorder[g][b] = p.gorder[g][b - 1]; p.gorder[g][b - 1] = u;
+        }
+    }
+    p.gnit[g] = (uint8_t)n_it;
+    // MMA runs: maximal runs (<= 4 chunks = N 256) of adjacent present chunks (every MMA accumulates: the accumulators
+    // are zeroed at kernel start)
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t bits = kbits[order[it]];
+      uint64_t rw = 0;
+      int nr = 0, q = 0;
+      while (q < G) {
+        if (!((bits >> q) & 1u)) { ++q; continue; }
+        int len = 1;
+        while (len < 4 && q + len < G && ((bits >> (q + len)) & 1u)) ++len;
+        rw |= (uint64_t)((uint32_t)q | ((uint32_t)(len - 1) << 3) | (1u << 5)) << (6 * nr);
+        ++nr;
+        q += len;
+      }
+      p.runs[g][it] = rw | ((uint64_t)nr << 60);
+    }
+    // ring placement
+    int head = 0, first_live = 0;
+    int off[TC_MAX_CHUNKS], need[TC_MAX_CHUNKS];
+    for (int it = 0; it < n_it; ++it) {
+      need[it] = 2 + __builtin_popcount(kbits[order[it]]);
+      if (head + need[it] > TC_RING_UNITS) head = 0;
+      off[it] = head;
+      int wait = -1;
+      for (int j = first_live; j < it; ++j)
+        if (off[j] < off[it] + need[it] && off[it] < off[j] + need[j]) wait = j;
+      if (wait >= 0) first_live = wait + 1;
+      head += need[it];
+      p.sched[g][it] = (uint32_t)order[it] | (kbits[order[it]] << 6) | ((uint32_t)off[it] << 12) |
+                       ((uint32_t)(wait + 1) << 17) | (done_after[it] << 24);
+    }
   }
 }
 
 // choose the number of groups (whole waves of sm_count CTAs, minimal waves x per-CTA time), partition, fill the schedule
-static int tc_make_schedule(TcParams& p, int tiles, int sm_count, int force) {
+static void tc_make_schedule(TcParams& p, int tiles, int sm_count, int force) {
   int best_ng = p.NCN;
   double best = 1e30;
   uint8_t goc0[TC_MAX_CHUNKS + 1];
-  for (int ng = (p.NCN + 5) / 6; ng <= p.NCN; ++ng) {
+  for (int ng = (p.NCN + TC_GMAX - 1) / TC_GMAX; ng <= p.NCN; ++ng) {
     const int maxblk = tc_partition(p, ng, goc0);
     int gmax = 0;
     for (int g = 0; g < ng; ++g) gmax = goc0[g + 1] - goc0[g] > gmax ? goc0[g + 1] - goc0[g] : gmax;
     long ctas = (long)tiles * ng;
     long waves = (ctas + sm_count - 1) / sm_count;
-    // per-CTA time ~ main loop (blocks) + epilogue (chunks) + fixed cost, in units of one block's MMA time
-    double c = (double)waves * (maxblk + 3.0 * gmax + 8.0);
+    // per-CTA time ~ main loop (blocks) + the epilogue tail (the last chunks) + fixed cost, in units of one block's MMA time
+    double c = (double)waves * (maxblk + 1.5 * gmax + 8.0);
     if (c < best - 1e-9) { best = c; best_ng = ng; }
   }
-  if (force > 0 && (p.NCN + force - 1) / force <= 6) best_ng = force < p.NCN ? force : p.NCN;
+  if (force > 0 && (p.NCN + force - 1) / force <= TC_GMAX) best_ng = force < p.NCN ? force : p.NCN;
   p.n_groups = best_ng;
   tc_partition(p, best_ng, p.goc0);
-  int gmax = 0;
-  for (int g = 0; g < best_ng; ++g) gmax = p.goc0[g + 1] - p.goc0[g] > gmax ? p.goc0[g + 1] - p.goc0[g] : gmax;
   tc_fill_schedule(p);
-  return gmax;
 }
 
 // Pick the N-side grouping.  One CTA is resident per SM (TMEM kernels), so the grid should be whole waves of
@@ -496,10 +670,9 @@ static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const
   }
   // The grouping and its schedule depend only on (mask, chunk geometry, tiles, SM count): computed once, then
   // served from a small cache (the launch path must stay cheap: it runs ~20 times per train step).
-  struct Entry { uint32_t kmask[LCN_J]; int FCK, FCN, NCK, NCN, tiles, sm, force; TcParams sched; int gmax; };
+  struct Entry { uint32_t kmask[LCN_J]; int FCK, FCN, NCK, NCN, tiles, sm, force; TcParams sched; };
   static std::mutex mu;
   static std::vector<Entry> cache;
-  int gmax = 0;
   {
     std::lock_guard<std::mutex> lock(mu);
     const Entry* hit = nullptr;
@@ -511,20 +684,41 @@ static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const
       memcpy(e.kmask, p.kmask, sizeof(e.kmask));
       e.FCK = p.FCK; e.FCN = p.FCN; e.NCK = p.NCK; e.NCN = p.NCN; e.tiles = tiles; e.sm = sm_count; e.force = force;
       e.sched = p;
-      e.gmax = tc_make_schedule(e.sched, tiles, sm_count, force);
+      tc_make_schedule(e.sched, tiles, sm_count, force);
       cache.push_back(e);
       hit = &cache.back();
     }
     p.n_groups = hit->sched.n_groups;
-    memcpy(p.gbits, hit->sched.gbits, sizeof(p.gbits));
+    memcpy(p.sched, hit->sched.sched, sizeof(p.sched));
+    memcpy(p.runs, hit->sched.runs, sizeof(p.runs));
     memcpy(p.gslot, hit->sched.gslot, sizeof(p.gslot));
+    memcpy(p.gnit, hit->sched.gnit, sizeof(p.gnit));
     memcpy(p.gwritten, hit->sched.gwritten, sizeof(p.gwritten));
+    memcpy(p.gorder, hit->sched.gorder, sizeof(p.gorder));
+    memcpy(p.gdcnt, hit->sched.gdcnt, sizeof(p.gdcnt));
     memcpy(p.goc0, hit->sched.goc0, sizeof(p.goc0));
-    gmax = hit->gmax;
   }
-  if (gmax <= 2) return launch_tc_gemm<2, 4>(A, W, bias, addend, Y, part, p, tiles, st);
-  if (gmax <= 4) return launch_tc_gemm<4, 4>(A, W, bias, addend, Y, part, p, tiles, st);
-  return launch_tc_gemm<6, 3>(A, W, bias, addend, Y, part, p, tiles, st);
+  return launch_tc_gemm(A, W, bias, addend, Y, part, p, tiles, st);
+}
+
+// schedule of the knn-masked mid layer for inspection / tests (host only): returns the number of groups and fills, per
+// group, the iteration count; sched_out[g * 34 + it] is the packed entry (TC_S_* fields)
+extern "C" int lcn_debug_tc_schedule(const uint32_t* kmask17, int FC, int tiles, int sm_count, uint32_t* sched_out,
+                                     uint8_t* nit_out, uint8_t* goc0_out, uint8_t* order_out, uint64_t* runs_out,
+                                     uint8_t* dcnt_out) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  for (int a = 0; a < LCN_J; ++a) p.kmask[a] = kmask17[a];
+  p.FCK = p.FCN = FC;
+  p.NCK = p.NCN = LCN_J * FC;
+  tc_make_schedule(p, tiles, sm_count, 0);
+  memcpy(sched_out, p.sched, sizeof(p.sched));
+  memcpy(nit_out, p.gnit, sizeof(p.gnit));
+  memcpy(goc0_out, p.goc0, sizeof(p.goc0));
+  memcpy(order_out, p.gorder, sizeof(p.gorder));
+  if (runs_out) memcpy(runs_out, p.runs, sizeof(p.runs));
+  if (dcnt_out) memcpy(dcnt_out, p.gdcnt, sizeof(p.gdcnt));
+  return p.n_groups;
 }
 
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed, const __nv_bfloat16* A,
