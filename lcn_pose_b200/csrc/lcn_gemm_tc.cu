@@ -782,15 +782,29 @@ int lcn_tc_head_dgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient of the nonzero blocks: dWm[(i,hi) chunk, (j,ho) chunk] += A[rows, ic]^T dZ[rows, oc]
-//   D[M=64 input channels, N=64*len output channels] = sum_k A_op[m][k] * B_op[n][k], k = batch row.
-//   Both operands are MN-major SW128 tiles exactly as stored in HBM (K = the 128 rows of a tile).
-//   unit = (input chunk, group of <=4 of its present output chunks); grid.y splits the batch rows.
-//   M=64 accumulators use the half-subpartition TMEM layout: row m -> lane 32*(m/16) + m%16.
+//   D[M = 128 = two input chunks x 64 channels, N = 64*len output channels] = sum_k A_op[m][k] * B_op[n][k], k = batch row.
+//   Both operands are MN-major SW128 tiles exactly as stored in HBM (K = the rows of a tile); the two input chunks of a
+//   unit sit 8 KB apart in shared memory, which is the descriptor's leading-dimension stride, like the <=4 output chunks.
+//   unit = (pair of input chunks, group of <=4 output chunks out of the union of their neighbourhoods): M = 128 runs the
+//   tensor pipe at full rate (M = 64 at half) and halves the number of units; the pairs are matched on the host so that
+//   the union wastes as few blocks as possible (knn=3: 218 computed for 175 stored; F=128: the two halves of a joint,
+//   no waste).  Blocks of the union that are not in the mask are computed and dropped.  grid.y splits the batch rows.
+//   Two MMA-issuing warps (even / odd half tiles) on accumulators zeroed by the epilogue warps, as in k_tc_gemm.
 // ---------------------------------------------------------------------------------------------
 #define TCW_HALF_BYTES 8192                       // 64 rows x 64 bf16: half of an activation tile
-#define TCW_STAGE_BYTES ((1 + TC_G) * TCW_HALF_BYTES)
-#define TCW_STAGES 2
+#define TCW_STAGE_BYTES ((2 + TC_G) * TCW_HALF_BYTES)
+#define TCW_STAGES 4     // even: a stage is always consumed by the same MMA warp (it % 2 == stage % 2), so each warp sees
+                         // the phases of its full barriers in sequence
 #define TCW_PITCH 260   // floats per staged output row (1040 B: 16-byte aligned, bank-conflict free)
+#define TCW_THREADS (32 + 32 * TC_MMA_WARPS + 128)
+#define TCW_MAX_UNITS 160
+
+struct TcwUnit {
+  uint8_t ic0, ic1;        // input chunks (ic1 = 0xff: single)
+  uint8_t len, pad;
+  uint8_t oc[TC_G];        // output chunks
+  uint8_t keep[TC_G];      // bit 0: (ic0, oc) is a block of the mask, bit 1: (ic1, oc)
+};
 
 struct TcwParams {
   uint32_t row[LCN_J];     // outputs (N-side joints) of input (M-side) joint i
@@ -798,6 +812,8 @@ struct TcwParams {
   int NCK, NCN;            // chunks per row tile of A / dZ
   int ldw;                 // row pitch of dW in floats
   int tiles, tiles_per_cta;
+  int n_units;
+  TcwUnit unit[TCW_MAX_UNITS];
 };
 
 __device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src, uint32_t bytes) {
@@ -806,39 +822,20 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src, ui
                : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __restrict__ A,
-                                                         const __nv_bfloat16* __restrict__ dZ,
-                                                         float* __restrict__ dW, TcwParams p) {
+__global__ void __launch_bounds__(TCW_THREADS) k_tc_wgrad(const __nv_bfloat16* __restrict__ A,
+                                                          const __nv_bfloat16* __restrict__ dZ,
+                                                          float* __restrict__ dW, const __grid_constant__ TcwParams p) {
   lcn_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TCW_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * TCW_STAGES + TC_MMA_WARPS];
   __shared__ uint32_t tmem_base_s;
   uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // decode the unit: input chunk ic and its gi-th group of present output chunks
-  int ic = 0, gi = 0;
-  {
-    int u = blockIdx.x;
-    for (ic = 0; ic < p.NCK; ++ic) {
-      int cnt = __popc(p.row[ic / p.FCK]) * p.FCN;
-      int ng = (cnt + TC_G - 1) / TC_G;
-      if (u < ng) { gi = u; break; }
-      u -= ng;
-    }
-  }
-  int ocs[TC_G];
-  int len = 0;
-  {
-    uint32_t bits = p.row[ic / p.FCK];
-    int e = 0;
-    for (int j = 0; j < LCN_J; ++j) {
-      if (!((bits >> j) & 1u)) continue;
-      for (int ho = 0; ho < p.FCN; ++ho, ++e)
-        if (e >= gi * TC_G && e < gi * TC_G + TC_G) ocs[len++] = j * p.FCN + ho;
-    }
-  }
+  const TcwUnit& u = p.unit[blockIdx.x];
+  const int ic0 = u.ic0, ic1 = u.ic1, len = u.len;
+  const int na = ic1 != 0xff ? 2 : 1;              // input half tiles per stage
   const int t0 = blockIdx.y * p.tiles_per_cta;
   const int t1 = min(t0 + p.tiles_per_cta, p.tiles);
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TCW_STAGES]), tfull = smem_u32(&bars[2 * TCW_STAGES]);
@@ -849,15 +846,22 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tfull, 1);
+    mbar_init(tfull, TC_MMA_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
   const uint32_t tmem_base = tmem_base_s;
+  if (warp > TC_MMA_WARPS) {
+    // zero the accumulators (the two MMA warps only accumulate): warp's lane quarter x all columns
+    for (int c = 0; c < (int)tmem_cols / 32; ++c) tmem_st32_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c * 32);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+  }
+  if (warp >= 1) asm volatile("bar.sync 3, %0;" ::"n"(TCW_THREADS - 32) : "memory");
+  lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
 
   const int n_it = 2 * (t1 - t0);                  // two 64-row half tiles per 128-row tile
   if (warp == 0) {
@@ -868,29 +872,33 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
         int t = t0 + (it >> 1), half = it & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         uint32_t sa = sbase + s * TCW_STAGE_BYTES;
-        mbar_expect_tx(full0 + 8 * s, (1 + len) * TCW_HALF_BYTES);
-        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic) * 8192 + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
+        mbar_expect_tx(full0 + 8 * s, (na + len) * TCW_HALF_BYTES);
+        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic0) * 8192 + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
+        if (na == 2)
+          bulk_g2s(sa + TCW_HALF_BYTES, A + ((size_t)t * p.NCK + ic1) * 8192 + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
         for (int q = 0; q < len; ++q)
-          bulk_g2s(sa + (1 + q) * TCW_HALF_BYTES, dZ + ((size_t)t * p.NCN + ocs[q]) * 8192 + half * 4096,
+          bulk_g2s(sa + (2 + q) * TCW_HALF_BYTES, dZ + ((size_t)t * p.NCN + u.oc[q]) * 8192 + half * 4096,
                    TCW_HALF_BYTES, full0 + 8 * s);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= TC_MMA_WARPS) {
+    tc_fence_after();
     if (lane == 0) {
-      // M = 64, N = 64*len, both operands MN-major
+      // M = 128, N = 64*len, both operands MN-major.  The stage's empty barrier takes ONE arrival: consecutive
+      // iterations alternate between the two warps, and a stage is released by the warp that consumed it.
       uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((64 * len) >> 3) << 17) |
-                       ((uint32_t)(64 >> 4) << 24);
-      for (int it = 0; it < n_it; ++it) {
+                       ((uint32_t)(128 >> 4) << 24);
+      for (int it = warp - 1; it < n_it; it += TC_MMA_WARPS) {
         int s = it % TCW_STAGES;
         uint32_t ph = (uint32_t)(it / TCW_STAGES) & 1u;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
-        uint32_t sa = sbase + s * TCW_STAGE_BYTES, sb = sa + TCW_HALF_BYTES;
+        uint32_t sa = sbase + s * TCW_STAGE_BYTES, sb = sa + 2 * TCW_HALF_BYTES;
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {          // 64 rows = 4 MMAs of K = 16
           uint64_t ad = umma_desc_sw128(sa + k16 * 2048, TCW_HALF_BYTES, 1024);
           uint64_t bd = umma_desc_sw128(sb + k16 * 2048, TCW_HALF_BYTES, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (uint32_t)(it > 0 || k16 > 0));
+          umma_f16(tmem_base, ad, bd, idesc, 1u);
         }
         umma_commit(empty0 + 8 * s);
       }
@@ -898,53 +906,109 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_wgrad(const __nv_bfloat16* __
     }
   } else {
     const int lq = warp & 3;
+    const int et = threadIdx.x - 32 - 32 * TC_MMA_WARPS;          // 0..127
     mbar_wait(tfull, 0);
     tc_fence_after();
     float* out_s = reinterpret_cast<float*>(sgen);
-    const int m = lq * 16 + lane;                    // valid for lane < 16
+    const int m = lq * 32 + lane;                    // accumulator row: channel m % 64 of input chunk ic0 (m < 64) / ic1
+    const int hi = m >> 6;
     for (int q = 0; q < len; ++q)
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + q * 64 + h * 32, v);
-        if (lane < 16) {
-          float* dst = out_s + m * TCW_PITCH + q * 64 + h * 32;
+        float* dst = out_s + m * TCW_PITCH + q * 64 + h * 32;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(dst + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
-        }
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(dst + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
       }
     tc_fence_before();
     fence_proxy_async();
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (lane < 16) {
+    (void)et;
+    if (hi < na) {
+      const int ic = hi ? ic1 : ic0;
       for (int q = 0; q < len; ++q)
-        bulk_reduce_add_f32(dW + (size_t)(ic * 64 + m) * p.ldw + ocs[q] * 64, smem_u32(out_s + m * TCW_PITCH + q * 64), 256);
-      bulk_commit_wait_read();
+        if ((u.keep[q] >> hi) & 1u)
+          bulk_reduce_add_f32(dW + (size_t)(ic * 64 + (m & 63)) * p.ldw + u.oc[q] * 64, smem_u32(out_s + m * TCW_PITCH + q * 64), 256);
     }
+    bulk_commit_wait_read();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// units of the weight-gradient kernel: input chunks matched in pairs (smallest union of neighbourhoods first), then
+// groups of <= TC_G output chunks of the union
+static void tcw_build_units(TcwParams& p) {
+  const int NI = p.NCK;
+  auto outs = [&](int ic, uint8_t* list) {          // output chunks of input chunk ic, ascending
+    int n = 0;
+    const uint32_t bits = p.row[ic / p.FCK];
+    for (int j = 0; j < LCN_J; ++j)
+      if ((bits >> j) & 1u)
+        for (int ho = 0; ho < p.FCN; ++ho) list[n++] = (uint8_t)(j * p.FCN + ho);
+    return n;
+  };
+  bool used[TC_MAX_CHUNKS] = {false};
+  int pa[TC_MAX_CHUNKS], pb[TC_MAX_CHUNKS], np = 0;
+  int left = NI;
+  while (left > 1) {
+    int bi = -1, bk = -1;
+    long best = 1L << 60;
+    for (int i = 0; i < NI; ++i) {
+      if (used[i]) continue;
+      for (int k = i + 1; k < NI; ++k) {
+        if (used[k]) continue;
+        const uint32_t a = p.row[i / p.FCK], b = p.row[k / p.FCK];
+        const int un = __builtin_popcount(a | b), waste = 2 * un - __builtin_popcount(a) - __builtin_popcount(b);
+        const long key = ((long)waste << 20) | ((long)un << 8) | (long)(k - i);   // least waste, then smallest union, then nearest
+        if (key < best) { best = key; bi = i; bk = k; }
+      }
+    }
+    used[bi] = used[bk] = true;
+    pa[np] = bi; pb[np] = bk; ++np;
+    left -= 2;
+  }
+  for (int i = 0; i < NI; ++i)
+    if (!used[i]) { pa[np] = i; pb[np] = -1; ++np; }
+  p.n_units = 0;
+  for (int e = 0; e < np; ++e) {
+    uint8_t la[TC_MAX_CHUNKS], lb[TC_MAX_CHUNKS], un[2 * TC_MAX_CHUNKS];
+    const int na = outs(pa[e], la), nb = pb[e] >= 0 ? outs(pb[e], lb) : 0;
+    bool ina[TC_MAX_CHUNKS] = {false}, inb[TC_MAX_CHUNKS] = {false};
+    for (int i = 0; i < na; ++i) ina[la[i]] = true;
+    for (int i = 0; i < nb; ++i) inb[lb[i]] = true;
+    int nu = 0;
+    for (int oc = 0; oc < p.NCN; ++oc)
+      if (ina[oc] || inb[oc]) un[nu++] = (uint8_t)oc;
+    for (int g0 = 0; g0 < nu; g0 += TC_G) {
+      TcwUnit& u = p.unit[p.n_units++];
+      memset(&u, 0, sizeof(u));
+      u.ic0 = (uint8_t)pa[e];
+      u.ic1 = pb[e] >= 0 ? (uint8_t)pb[e] : (uint8_t)0xff;
+      u.len = (uint8_t)(nu - g0 < TC_G ? nu - g0 : TC_G);
+      for (int q = 0; q < u.len; ++q) {
+        u.oc[q] = un[g0 + q];
+        u.keep[q] = (uint8_t)((ina[un[g0 + q]] ? 1 : 0) | (inb[un[g0 + q]] ? 2 : 0));
+      }
+    }
+  }
+}
+
 static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW, int tiles,
                            int sm_count, cudaStream_t st) {
-  int units = 0;
-  for (int ic = 0; ic < p.NCK; ++ic) {
-    int cnt = __builtin_popcount(p.row[ic / p.FCK]) * p.FCN;
-    units += (cnt + TC_G - 1) / TC_G;
-  }
+  tcw_build_units(p);
+  const int units = p.n_units;
   p.tiles = tiles;
-  // One CTA is resident per SM (TMEM kernels: profiles/micro/occ.cu).  The row range per CTA is the smallest for
-  // which the grid has at most 2 x SMs CTAs: two waves of ~7-tile CTAs measured faster than one wave of 16-tile CTAs
-  // (0.820 vs 0.854 ms per train step) because ~54 units x 2 row splits fill only 108 of the 148 SMs.
-  // LCN_TCW_SLOTS overrides the slot count for experiments.
+  // One CTA is resident per SM (TMEM kernels: profiles/micro/occ.cu): the row range per CTA is the smallest for which
+  // the grid is a single wave.  LCN_TCW_SLOTS overrides the slot count for experiments.
   static int slots_env = -1;
   if (slots_env < 0) {
     const char* e = getenv("LCN_TCW_SLOTS");
     slots_env = e ? atoi(e) : 0;
   }
-  int slots = slots_env > 0 ? slots_env : 2 * sm_count;
+  int slots = slots_env > 0 ? slots_env : sm_count;
   int tpc = 1;
   while (tpc < tiles && (long)units * ((tiles + tpc - 1) / tpc) > slots) ++tpc;
   p.tiles_per_cta = tpc;
@@ -955,7 +1019,7 @@ static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bflo
     LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  lcn_launch(k_tc_wgrad, dim3(dim3(units, splits)), dim3(TC_THREADS), smem, st, A, dZ, dW, p);
+  lcn_launch(k_tc_wgrad, dim3(dim3(units, splits)), dim3(TCW_THREADS), smem, st, A, dZ, dW, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
