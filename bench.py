@@ -169,9 +169,13 @@ def run_reference(args, rank, world):
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def launches_per_step(n_bn):
-    fwd = 3 * n_bn + 1                      # (gemm | first layer) + bn_finalize + bn_act per BN layer, last layer
-    bwd = 2 + 1 + 2 * n_bn + 2 * (n_bn - 1) + 1   # loss(2), last bwd, bn bwd x2, wgrad+dgrad mid, first wgrad
-    opt = 2 + 2 + 4                         # pairdot, maskgrad, zero, adam, prepare (mask, edge x2, pack)
+    """Kernels of this library per train step on the bf16 path (counted from the launch list, profiles/r1):
+    forward: (GEMM | first layer) + bn_act per BN layer (the BatchNorm statistics are accumulated by the GEMM itself),
+    head GEMM; backward: loss, head dgrad, last-layer wgrad, fused BN backward per BN layer, dgrad + wgrad per mid layer,
+    first-layer wgrad, bias-gradient reduce; optimizer: pairdot, mask gradient (2), Adam, mask scalars, 5 weight packs."""
+    fwd = 2 * n_bn + 1
+    bwd = 3 + n_bn + 2 * (n_bn - 1) + 2
+    opt = 10
     return fwd + bwd + opt
 
 

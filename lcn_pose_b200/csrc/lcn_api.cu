@@ -258,6 +258,8 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_part = take(w.fused ? 0 : sizeof(float) * (size_t)w.tiles * P * 2);
   w.off_bnstat = take(w.fused ? 0 : sizeof(float) * (size_t)m->n_bn * w.n_groups * F * 2);
   w.off_bnsum = take(sizeof(float) * (size_t)m->n_bn * (F * 2 + 1));    // + one grid-barrier counter per BN layer
+  w.gacc_stride = sizeof(double) * LCN_GACC_REP * F * 2 + 256;
+  w.off_gacc = take(training ? w.gacc_stride * (size_t)m->n_bn : 0);
   w.off_out = take(training ? sizeof(float) * (size_t)w.rows_pad * 51 : 0);
   w.off_dout = take(training ? sizeof(float) * (size_t)w.rows_pad * 51 : 0);
   w.off_x16 = take(training ? (size_t)w.rows_pad * 64 * 2 : 0);

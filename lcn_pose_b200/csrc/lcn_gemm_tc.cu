@@ -93,6 +93,8 @@ struct TcParams {
   uint8_t gdcnt[TC_MAX_CHUNKS][TC_GMAX];          // per chunk of the group: MMA warps that issue into it (arrivals on done[q])
   uint8_t gorder[TC_MAX_CHUNKS][TC_GMAX];         // the group's chunks in the order their accumulators complete
   uint8_t goc0[TC_MAX_CHUNKS + 1];  // group g owns N-side chunks [goc0[g], goc0[g+1]): contiguous, balanced by block count
+  int fuse_on;                      // forward only: BatchNorm statistics by fp64 atomics into fuse.gacc (no partials, no k_bn_finalize)
+  TcFuse fuse;
 };
 
 #include "lcn_tc_ptx.cuh"
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
           bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * 8192, smem_u32(tile_s), TC_A_BYTES);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (p.mode == TC_MODE_FWD && part != nullptr) {
+        if (p.mode == TC_MODE_FWD && (part != nullptr || p.fuse_on)) {
           // BatchNorm partials of this tile and chunk: per column (mean, M2) over the valid rows, from the bf16 values
           // staged in shared memory (what k_bn_act will read).  Warp w walks rows w, w+4, ...; a lane owns two columns;
           // sums are shifted by the chunk's row-0 value (the same shift in every warp, so the four partial sums add).
@@ -421,8 +423,18 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
               s1 += v.x; s2 += v.y;
             }
             const float sh = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile_s + ((col >> 3) << 4) + (col & 7) * 2));
-            *reinterpret_cast<float2*>(part + ((size_t)tile * p.P + (oc0 + q) * 64 + col) * 2) =
-                make_float2(fmaf(s1, rn, sh), fmaxf(s2 - s1 * s1 * rn, 0.f));
+            if (p.fuse_on) {
+              // unshifted moments in fp64 (sum x = n sh + s1, sum x^2 = s2 + 2 sh s1 + n sh^2) added to this tile's
+              // replica of the per-channel accumulators; channel = column within the joint
+              const double n = (double)nvalid, shd = (double)sh, d1 = (double)s1;
+              const int f = ((oc0 + q) % p.FCN) * 64 + col;
+              double* dst = p.fuse.gacc + ((size_t)(tile & (LCN_GACC_REP - 1)) * p.fuse.F + f) * 2;
+              atomicAdd(dst, n * shd + d1);
+              atomicAdd(dst + 1, (double)s2 + 2.0 * shd * d1 + n * shd * shd);
+            } else {
+              *reinterpret_cast<float2*>(part + ((size_t)tile * p.P + (oc0 + q) * 64 + col) * 2) =
+                  make_float2(fmaf(s1, rn, sh), fmaxf(s2 - s1 * s1 * rn, 0.f));
+            }
           }
           if (tt == 0) TC_STAMP(206 + 8 * e);
         }
@@ -723,7 +735,7 @@ extern "C" int lcn_debug_tc_schedule(const uint32_t* kmask17, int FC, int tiles,
 
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed, const __nv_bfloat16* A,
                 const char* wpacked, const float* bias, const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part,
-                cudaStream_t st) {
+                cudaStream_t st, const TcFuse* fuse, int* fused) {
   (void)mid_index;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -734,8 +746,20 @@ int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int tran
   p.bn_group = lay.bn_group;
   p.gstride = lay.gstride;
   p.mode = transposed ? TC_MODE_DGRAD : TC_MODE_FWD;
-  return pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, addend, Y, part, p, lay.tiles,
-                         m->sm_count, st);
+  if (fused) *fused = 0;
+  if (fuse != nullptr && !transposed && lay.n_groups == 1) {
+    static int on = -1;                // LCN_FUSED_BNSTATS=0: per-tile partials + k_bn_finalize as on the other paths
+    if (on < 0) {
+      const char* e = getenv("LCN_FUSED_BNSTATS");
+      on = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.fuse = *fuse;
+    p.fuse_on = on;
+  }
+  int rc = pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, addend, Y, part, p, lay.tiles,
+                           m->sm_count, st);
+  if (fused) *fused = p.fuse_on;
+  return rc;
 }
 
 // last layer (17*F -> 51) + output head on the tensor cores: one N-side chunk (51 columns padded to 64),

@@ -117,6 +117,7 @@ struct WsLayout {
   size_t off_part;                   // float[tiles][P][2] BN partials (mean, M2)
   size_t off_bnstat;                 // float[n_bn][n_groups][F][2]  (mean, rstd)
   size_t off_bnsum;                  // float[n_bn][F][2]  backward sums (sum dy, sum dy*xhat)
+  size_t off_gacc, gacc_stride;      // per BN layer: double[LCN_GACC_REP][F][2] (sum x, sum x^2) + grid-barrier counter (training)
   size_t off_out;                    // float[rows_pad][51] copy of the prediction (training)
   size_t off_dout;                   // float[rows_pad][51]
   size_t off_z, z_stride; int n_z;   // Z buffers
@@ -268,11 +269,20 @@ int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, con
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,
                            float* dst, cudaStream_t st);
 
+// BatchNorm statistics of the forward tensor-core GEMM without a second launch (one BatchNorm group): every CTA adds
+// its per-channel (sum x, sum x^2) to fp64 accumulators (LCN_GACC_REP replicas indexed by row tile spread the atomics),
+// and k_bn_act_pre derives (mean, rstd) from them in its prologue -- k_bn_finalize is not launched for the layer.
+#define LCN_GACC_REP 8
+struct TcFuse {
+  double* gacc;                      // [LCN_GACC_REP][F][2], zeroed by the caller once per forward pass
+  int F;
+};
 // tcgen05 (bf16) mid-layer kernels, lcn_gemm_tc.cu.  transposed=0: Y = A*Wm (+bias, BN partials);
-// transposed=1: dA = dZ*Wm^T (+addend).
+// transposed=1: dA = dZ*Wm^T (+addend).  fuse != nullptr (forward, one BatchNorm group): *fused = 1 if the statistics
+// went to fuse->gacc (the caller skips k_bn_finalize and hands gacc to k_bn_act_pre), 0: per-tile partials as usual.
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed,
                 const __nv_bfloat16* A, const char* wpacked, const float* bias, const __nv_bfloat16* addend,
-                __nv_bfloat16* Y, float* part, cudaStream_t st);
+                __nv_bfloat16* Y, float* part, cudaStream_t st, const TcFuse* fuse = nullptr, int* fused = nullptr);
 int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ,
                  float* dW /* dense [P,P] */, cudaStream_t st);
 int lcn_tc_head(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const char* wpacked,

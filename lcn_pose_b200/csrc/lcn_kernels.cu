@@ -313,7 +313,7 @@ template <typename T, int IN_F>
 __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x, RowGeom g,
                                                      const float* __restrict__ wm, const float* __restrict__ bias,
                                                      T* __restrict__ Z, float* __restrict__ part, int P,
-                                                     __nv_bfloat16* __restrict__ x16) {
+                                                     __nv_bfloat16* __restrict__ x16, double* __restrict__ gacc, int F) {
   lcn_pdl_prologue();
   constexpr int KIN = LCN_J * IN_F;
   __shared__ __align__(16) float xs[KIN][LCN_TILE];
@@ -407,8 +407,17 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
     }
     const float nf = (float)max(n, 1);
     const int c = col0 + threadIdx.x;
-    *reinterpret_cast<float2*>(part + ((size_t)tile * P + c) * 2) =
-        make_float2(bias[c] + t1 / nf, fmaxf(t2 - t1 * t1 / nf, 0.f));
+    if (gacc != nullptr) {
+      // per-channel fp64 accumulators instead of partials + k_bn_finalize (TcFuse, lcn_internal.cuh): the sums are
+      // shifted by the bias, sum x = n b + t1, sum x^2 = t2 + 2 b t1 + n b^2
+      const double nd = (double)n, bd = (double)bias[c], d1 = (double)t1;
+      double* dst = gacc + ((size_t)(tile & (LCN_GACC_REP - 1)) * F + c % F) * 2;
+      atomicAdd(dst, nd * bd + d1);
+      atomicAdd(dst + 1, (double)t2 + 2.0 * bd * d1 + nd * bd * bd);
+    } else {
+      *reinterpret_cast<float2*>(part + ((size_t)tile * P + c) * 2) =
+          make_float2(bias[c] + t1 / nf, fmaxf(t2 - t1 * t1 / nf, 0.f));
+    }
   }
 }
 
@@ -705,7 +714,9 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act_pre(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ Aout,
                                                            uint8_t* __restrict__ keepbits, int P, int F, int rows_pad,
                                                            int bn_group, float rate, uint64_t seed, uint64_t step,
-                                                           int layer, const lcn_step_scalars* __restrict__ dyn) {
+                                                           int layer, const lcn_step_scalars* __restrict__ dyn,
+                                                           const double* __restrict__ gacc, float* __restrict__ stat_out,
+                                                           double inv_n) {
   lcn_pdl_prologue();
   __shared__ __align__(16) float s_sc[256], s_sh[256];
   if (dyn != nullptr) step = dyn->step;
@@ -727,7 +738,30 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_act_pre(const __nv_bfloat16* 
     }
   }
   if (tid < F) {
-    const float mean = stat[tid * 2], rstd = stat[tid * 2 + 1];
+    float mean, rstd;
+    if (gacc != nullptr) {
+      // statistics straight from the GEMM's per-channel fp64 accumulators (sum x, sum x^2 over batch x joints,
+      // LCN_GACC_REP replicas): what k_bn_finalize would have produced, without the launch
+      double S1 = 0.0, S2 = 0.0;
+#pragma unroll
+      for (int rep = 0; rep < LCN_GACC_REP; ++rep) {
+        S1 += gacc[((size_t)rep * F + tid) * 2];
+        S2 += gacc[((size_t)rep * F + tid) * 2 + 1];
+      }
+      // (fp64 only where the cancellation is; no fp64 division or square root on every block's critical path)
+      const double md = S1 * inv_n;
+      const double var = fmax(S2 * inv_n - md * md, 0.0);
+      mean = (float)md;
+      rstd = rsqrtf((float)var + LCN_BN_EPS);
+      rstd = rstd * (1.5f - 0.5f * ((float)var + LCN_BN_EPS) * rstd * rstd);    // one Newton step: full fp32 accuracy
+      if (blockIdx.x == 0) {            // for the backward pass
+        stat_out[tid * 2] = mean;
+        stat_out[tid * 2 + 1] = rstd;
+      }
+    } else {
+      mean = stat[tid * 2];
+      rstd = stat[tid * 2 + 1];
+    }
     const float a = gamma[tid] * rstd;
     s_sc[tid] = a;
     s_sh[tid] = beta[tid] - mean * a;
@@ -1630,25 +1664,50 @@ static int forward_impl(const FwdArgs& a) {
     attr_done = true;
   }
   int n_bn = m->n_bn;
+  // training at one BatchNorm group on the tensor-core path: the mid-layer GEMMs accumulate the BatchNorm statistics
+  // themselves (TcFuse, lcn_gemm_tc.cu) and k_bn_act_pre finalises them; the accumulators are cleared here, once per pass
+  bool pre_ok = false;                 // k_bn_act_pre eligible (same test as below): it is the kernel that accepts gacc
+  if constexpr (sizeof(T) == 2) {
+    const int ewy0 = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
+    const int grid0 = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy0);
+    const int per0 = (int)(((lay.rows_pad / ewy0 + grid0 - 1) / grid0) * ewy0);
+    pre_ok = lay.n_groups == 1 && per0 <= BA_R * ewy0 && !getenv("LCN_DISABLE_BNACT_PRE");
+  }
+  const bool try_fuse = tc && lay.training && lay.n_groups == 1 && pre_ok;
+  if (try_fuse) LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_gacc, 0, lay.gacc_stride * (size_t)n_bn, st));
   for (int l = 0; l < n_bn; ++l) {
     const LayerInfo& L = m->L[l];
     T* Z = reinterpret_cast<T*>(z_buf(ws, lay, l));
     T* Aout = reinterpret_cast<T*>(a_buf(ws, lay, l));
+    int fused_bn = 0;
     if (l == 0) {
       dim3 grid(lay.tiles, P / 64);
       const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
       __nv_bfloat16* x16 = (tc && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
+      static int stats_on = -1;
+      if (stats_on < 0) {
+        const char* e = getenv("LCN_FUSED_BNSTATS");
+        stats_on = (e && e[0] == '0') ? 0 : 1;
+      }
+      double* gacc0 = (try_fuse && stats_on) ? reinterpret_cast<double*>(ws + lay.off_gacc) : nullptr;
+      fused_bn = gacc0 != nullptr;
       switch (m->d.in_F) {
-        case 2: lcn_launch(k_first_layer<T, 2>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
-        case 3: lcn_launch(k_first_layer<T, 3>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16); break;
+        case 2: lcn_launch(k_first_layer<T, 2>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16, gacc0, F); break;
+        case 3: lcn_launch(k_first_layer<T, 3>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16, gacc0, F); break;
         default: lcn_set_error("in_F=%d not supported (2 or 3)", m->d.in_F); return LCN_EINVAL;
       }
     } else {
       const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, l - 1));
       if (tc) {
         const char* wp = ws + lay.off_wp16f + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+        TcFuse fu;
+        memset(&fu, 0, sizeof(fu));
+        if (try_fuse) {
+          fu.gacc = reinterpret_cast<double*>(ws + lay.off_gacc + (size_t)l * lay.gacc_stride);
+          fu.F = F;
+        }
         int rc = lcn_tc_gemm(m, lay, l - 1, 0, reinterpret_cast<const __nv_bfloat16*>(Ain), wp, a.params + L.b_off,
-                             nullptr, reinterpret_cast<__nv_bfloat16*>(Z), part, st);
+                             nullptr, reinterpret_cast<__nv_bfloat16*>(Z), part, st, try_fuse ? &fu : nullptr, &fused_bn);
         if (rc) return rc;
       } else {
         const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
@@ -1658,6 +1717,8 @@ static int forward_impl(const FwdArgs& a) {
     }
     LCN_CHECK_LAUNCH();
     float* stat = bn_stat(ws, lay, m, l);
+    const double* gacc = fused_bn ? reinterpret_cast<const double*>(ws + lay.off_gacc + (size_t)l * lay.gacc_stride) : nullptr;
+    if (fused_bn == 0)
     lcn_launch(k_bn_finalize, dim3(dim3(lay.n_groups, F / 2)), dim3(256), 0, st, part, stat, P, F, lay.tiles_per_group, lay.bn_group);
     const T* res = L.res_from >= 0 ? reinterpret_cast<const T*>(a_buf(ws, lay, L.res_from)) : nullptr;
     const int ewy = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
@@ -1674,8 +1735,12 @@ static int forward_impl(const FwdArgs& a) {
         lcn_launch(k_bn_act_pre, dim3(ew_grid), dim3(P / 8, ewy), 0, st, reinterpret_cast<const __nv_bfloat16*>(Z), stat,
                    a.params + L.gamma_off, a.params + L.beta_off, reinterpret_cast<const __nv_bfloat16*>(res),
                    reinterpret_cast<__nv_bfloat16*>(Aout), keepbits, P, F, (int)lay.rows_pad, lay.bn_group, a.dropout_rate,
-                   a.seed, a.step, l, a.dyn);
+                   a.seed, a.step, l, a.dyn, gacc, stat, 1.0 / ((double)lay.bn_group * LCN_J));
       }
+    }
+    if (!pre && fused_bn) {
+      lcn_set_error("internal: BatchNorm statistics were accumulated for k_bn_act_pre, which is not eligible here");
+      return LCN_EINVAL;
     }
     if (!pre)
       lcn_launch(k_bn_act<T>, dim3(ew_grid), dim3(dim3(P / 8, ewy)), 0, st, Z, stat, a.params + L.gamma_off, a.params + L.beta_off, res, Aout,
