@@ -1442,10 +1442,24 @@ __global__ void k_pairdot(const float* __restrict__ params, const float* __restr
   const float* w = params + lt.w_off[l];
   const float* g = graw + lt.w_off[l];
   double s = 0.0;
-  for (int e = threadIdx.x; e < Fi * Fo; e += blockDim.x) {
-    int fi = e / Fo, fo = e - fi * Fo;
-    size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
-    s += (double)g[o] * (double)w[o];
+  // 8 elements per thread and pass, all 16 loads issued before the first use (W comes from HBM: the latency is paid
+  // once per pass instead of once per element)
+  const int n = Fi * Fo;
+  for (int e0 = threadIdx.x; e0 < n; e0 += 8 * (int)blockDim.x) {
+    float gv[8], wv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = e0 + k * (int)blockDim.x;
+      gv[k] = wv[k] = 0.f;
+      if (e < n) {
+        int fi = e / Fo, fo = e - fi * Fo;
+        size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
+        gv[k] = g[o];
+        wv[k] = w[o];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += (double)gv[k] * (double)wv[k];
   }
   s = block_reduce_sum_d(s, sh);
   if (threadIdx.x == 0) pairdot[l * LCN_J * LCN_J + p] = (float)s;
