@@ -1522,86 +1522,104 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
   lcn_pdl_prologue();
   __shared__ double sh[32];
   if (dyn != nullptr) lr_t = dyn->lr_t;        // CUDA-graph replay: the step size lives in device memory
-  int chunk = blockIdx.x;
-  int s = 0;
-  while (s + 1 < segs.n && segs.s[s + 1].chunk_start <= chunk) ++s;
-  const SegInfo sg = segs.s[s];
-  int64_t e0 = (int64_t)(chunk - sg.chunk_start) * LCN_ADAM_CHUNK;
-  int64_t e1 = min(e0 + (int64_t)LCN_ADAM_CHUNK, sg.size);
-  int l = sg.layer;
-  int Fi = 1, Fo = 1, Kout = 1;
-  float inv = 1.f, coef = 0.f;
-  if (sg.kind == SEG_W) {
-    Fi = lt.Fi[l]; Fo = lt.Fo[l]; Kout = LCN_J * Fo;
-    inv = sc[l].inv_norm; coef = sc[l].coef;
-  }
-  double nrm = 0.0;
+  // Persistent: gridDim.x blocks (8 per SM) walk the parameter vector in quarter chunks of 1024 elements with a grid
+  // stride, so the last wave is 1/6 of the work instead of half of it and the per-block prologue / norm reduction is
+  // paid once per block and layer, not once per 4096 elements.
+  constexpr int SUB = LCN_ADAM_CHUNK / 1024;
+  const int nsub = segs.total_chunks * SUB;
   const float omb1 = 1.f - b1, omb2 = 1.f - b2;
-  if (sg.kind == SEG_W && (Fo & 3) == 0) {
-    // fast path: 4 consecutive elements share the row and the joint pair; 28 B/parameter of HBM traffic
-    for (int64_t e = e0 + 4 * threadIdx.x; e < e1; e += 1024) {
-      int64_t o = sg.off + e;
-      uint32_t r = (uint32_t)e / (uint32_t)Kout, c = (uint32_t)e - r * (uint32_t)Kout;
-      uint32_t i = r / (uint32_t)Fi, j = c / (uint32_t)Fo;
-      float4 w4 = *reinterpret_cast<const float4*>(params + o);
-      float w[4] = {w4.x, w4.y, w4.z, w4.w}, g[4];
-      bool on = (sup.row[i] >> j) & 1u;
-      float ms = on ? mask[i * LCN_J + j] * inv : 0.f;
-      float4 gr = on ? *reinterpret_cast<const float4*>(graw + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float grr[4] = {gr.x, gr.y, gr.z, gr.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) g[q] = fmaf(reg, w[q], fmaf(grr[q], ms, -coef * w[q]));
-      if (WRITE_G) {
-        *reinterpret_cast<float4*>(gout + o) = make_float4(g[0], g[1], g[2], g[3]);
-      } else {
-        float4 m4 = *reinterpret_cast<const float4*>(mm + o), v4 = *reinterpret_cast<const float4*>(vv + o);
-        float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          m[q] = b1 * m[q] + omb1 * g[q];
-          v[q] = b2 * v[q] + omb2 * g[q] * g[q];
-          w[q] -= lr_t * m[q] / (sqrtf(v[q]) + eps);
-          nrm += (double)w[q] * w[q];
+  double nrm = 0.0;
+  int nrm_layer = -1;
+  int s = 0;
+  for (int sub = blockIdx.x; sub < nsub; sub += gridDim.x) {
+    const int chunk = sub / SUB, part = sub - chunk * SUB;
+    while (s + 1 < segs.n && segs.s[s + 1].chunk_start <= chunk) ++s;
+    const SegInfo sg = segs.s[s];
+    const int64_t e0 = (int64_t)(chunk - sg.chunk_start) * LCN_ADAM_CHUNK + part * 1024;
+    const int64_t e1 = min(e0 + (int64_t)1024, sg.size);
+    const int l = sg.layer;
+    int Fi = 1, Fo = 1, Kout = 1;
+    float inv = 1.f, coef = 0.f;
+    if (sg.kind == SEG_W) {
+      if (!WRITE_G && l != nrm_layer) {          // block-uniform: flush the previous layer's ||W_new||^2
+        if (nrm_layer >= 0) {
+          nrm = block_reduce_sum_d(nrm, sh);
+          if (threadIdx.x == 0) atomicAdd(&sc[nrm_layer].norm2, nrm);
+          __syncthreads();
         }
-        *reinterpret_cast<float4*>(mm + o) = make_float4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<float4*>(vv + o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(params + o) = make_float4(w[0], w[1], w[2], w[3]);
+        nrm = 0.0;
+        nrm_layer = l;
       }
+      Fi = lt.Fi[l]; Fo = lt.Fo[l]; Kout = LCN_J * Fo;
+      inv = sc[l].inv_norm; coef = sc[l].coef;
     }
-  } else {
-    for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
-      int64_t o = sg.off + e;
-      float w = params[o];
-      float g;
-      if (sg.kind == SEG_W) {
-        int r = (int)(e / Kout), c = (int)(e - (int64_t)r * Kout);
-        int i = r / Fi, j = c / Fo;
-        g = -coef * w;
-        if ((sup.row[i] >> j) & 1u) g = fmaf(graw[o], mask[i * LCN_J + j] * inv, g);
-        g = fmaf(reg, w, g);
-      } else if (sg.kind == SEG_B) {
-        g = fmaf(reg, w, graw[o]);
-      } else if (sg.kind == SEG_MASK) {
-        g = maskgrad[e];
-      } else {
-        g = graw[o];
+    if (sg.kind == SEG_W && (Fo & 3) == 0) {
+      // fast path: 4 consecutive elements share the row and the joint pair; 28 B/parameter of HBM traffic
+      const int64_t e = e0 + 4 * threadIdx.x;
+      if (e < e1) {
+        int64_t o = sg.off + e;
+        uint32_t r = (uint32_t)e / (uint32_t)Kout, c = (uint32_t)e - r * (uint32_t)Kout;
+        uint32_t i = r / (uint32_t)Fi, j = c / (uint32_t)Fo;
+        float4 w4 = *reinterpret_cast<const float4*>(params + o);
+        float w[4] = {w4.x, w4.y, w4.z, w4.w}, g[4];
+        bool on = (sup.row[i] >> j) & 1u;
+        float ms = on ? mask[i * LCN_J + j] * inv : 0.f;
+        float4 gr = on ? *reinterpret_cast<const float4*>(graw + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float grr[4] = {gr.x, gr.y, gr.z, gr.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = fmaf(reg, w[q], fmaf(grr[q], ms, -coef * w[q]));
+        if (WRITE_G) {
+          *reinterpret_cast<float4*>(gout + o) = make_float4(g[0], g[1], g[2], g[3]);
+        } else {
+          float4 m4 = *reinterpret_cast<const float4*>(mm + o), v4 = *reinterpret_cast<const float4*>(vv + o);
+          float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            m[q] = b1 * m[q] + omb1 * g[q];
+            v[q] = b2 * v[q] + omb2 * g[q] * g[q];
+            w[q] -= lr_t * m[q] / (sqrtf(v[q]) + eps);
+            nrm += (double)w[q] * w[q];
+          }
+          *reinterpret_cast<float4*>(mm + o) = make_float4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<float4*>(vv + o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(params + o) = make_float4(w[0], w[1], w[2], w[3]);
+        }
       }
-      if (WRITE_G) {
-        gout[o] = g;
-      } else {
-        float m = b1 * mm[o] + omb1 * g;
-        float v = b2 * vv[o] + omb2 * g * g;
-        mm[o] = m;
-        vv[o] = v;
-        w -= lr_t * m / (sqrtf(v) + eps);
-        params[o] = w;
-        nrm += (double)w * w;
+    } else {
+      for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+        int64_t o = sg.off + e;
+        float w = params[o];
+        float g;
+        if (sg.kind == SEG_W) {
+          int r = (int)(e / Kout), c = (int)(e - (int64_t)r * Kout);
+          int i = r / Fi, j = c / Fo;
+          g = -coef * w;
+          if ((sup.row[i] >> j) & 1u) g = fmaf(graw[o], mask[i * LCN_J + j] * inv, g);
+          g = fmaf(reg, w, g);
+        } else if (sg.kind == SEG_B) {
+          g = fmaf(reg, w, graw[o]);
+        } else if (sg.kind == SEG_MASK) {
+          g = maskgrad[e];
+        } else {
+          g = graw[o];
+        }
+        if (WRITE_G) {
+          gout[o] = g;
+        } else {
+          float m = b1 * mm[o] + omb1 * g;
+          float v = b2 * vv[o] + omb2 * g * g;
+          mm[o] = m;
+          vv[o] = v;
+          w -= lr_t * m / (sqrtf(v) + eps);
+          params[o] = w;
+          if (sg.kind == SEG_W) nrm += (double)w * w;
+        }
       }
     }
   }
-  if (!WRITE_G && sg.kind == SEG_W) {
+  if (!WRITE_G && nrm_layer >= 0) {
     nrm = block_reduce_sum_d(nrm, sh);
-    if (threadIdx.x == 0) atomicAdd(&sc[l].norm2, nrm);
+    if (threadIdx.x == 0) atomicAdd(&sc[nrm_layer].norm2, nrm);
   }
 }
 
@@ -1624,7 +1642,7 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
   if (rc) return rc;
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
-  lcn_launch(k_adam<true>, dim3(m->segs.total_chunks), dim3(256), 0, st, const_cast<float*>(params), nullptr, nullptr, grads_raw,
+  lcn_launch(k_adam<true>, dim3(std::min(m->segs.total_chunks * (LCN_ADAM_CHUNK / 1024), 8 * m->sm_count)), dim3(256), 0, st, const_cast<float*>(params), nullptr, nullptr, grads_raw,
                                                      grads_out, m->segs, make_lin(m), m->sup, mask,
                                                      mask + 2 * LCN_J * LCN_J, sc, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr);
   LCN_CHECK_LAUNCH();
@@ -1639,7 +1657,7 @@ int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, cha
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
   lcn_launch(k_zero_norm2, dim3(1), dim3(32), 0, st, sc, m->n_lin);
-  lcn_launch(k_adam<false>, dim3(m->segs.total_chunks), dim3(256), 0, st, params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
+  lcn_launch(k_adam<false>, dim3(std::min(m->segs.total_chunks * (LCN_ADAM_CHUNK / 1024), 8 * m->sm_count)), dim3(256), 0, st, params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
                                                       m->sup, mask, mask + 2 * LCN_J * LCN_J, sc, lr_t, b1, b2, eps,
                                                       reg, dyn);
   LCN_CHECK_LAUNCH();
