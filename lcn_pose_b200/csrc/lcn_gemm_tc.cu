@@ -136,16 +136,23 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
   const uint32_t tmem_cols = G <= 1 ? 64u : (G == 2 ? 128u : (G <= 4 ? 256u : 512u));
   TC_STAMP(0);
 
+  // Cluster of CT row tiles of the same chunk group (cluster dims (1, CT, 1), CT = 1: no cluster): the CTAs run the same
+  // schedule, so the weight panel of an iteration is fetched once per cluster -- every CTA loads 1/CT of it and
+  // multicasts that share into the same ring offset of all CTAs (L2 -> shared-memory traffic of the weights / CT).  A ring
+  // region may be overwritten when the MMAs of ALL CTAs have consumed it: empty[] takes CT multicast commits.
+  const uint32_t CT = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << CT) - 1u);
   if (threadIdx.x < 2 * TC_MAX_CHUNKS + TC_GMAX) {
     // every barrier is single use: one init each, in parallel.  done[q] collects one commit per MMA warp issuing into q
     const int i = threadIdx.x;
-    const uint32_t cnt = i < 2 * TC_MAX_CHUNKS ? 1u : (uint32_t)max(1, (int)p.gdcnt[g][i - 2 * TC_MAX_CHUNKS]);
+    const uint32_t cnt = i < TC_MAX_CHUNKS ? 1u : (i < 2 * TC_MAX_CHUNKS ? CT : (uint32_t)max(1, (int)p.gdcnt[g][i - 2 * TC_MAX_CHUNKS]));
     mbar_init(full0 + 8 * i, cnt);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (CT > 1) cluster_sync_all();          // every CTA's barriers are initialised before remote bytes / arrivals land
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (warp > TC_MMA_WARPS) {
@@ -177,7 +184,13 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
         const uint32_t sa = sbase + TC_S_OFF(s) * TC_B_BYTES;
         mbar_expect_tx(full0 + 8 * it, TC_A_BYTES + cnt * TC_B_BYTES);
         bulk_g2s(sa, a_tile + (size_t)kc * 8192, TC_A_BYTES, full0 + 8 * it);
-        bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * it);
+        if (CT == 1) {
+          bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * it);
+        } else {
+          const uint32_t share = cnt * TC_B_BYTES / CT;       // CT in {2, 4}: a multiple of 2 KB
+          bulk_g2s_mc(sa + TC_A_BYTES + crank * share, reinterpret_cast<const uint8_t*>(wsrc) + crank * share, share,
+                      full0 + 8 * it, cmask);
+        }
         TC_STAMP(17 + 4 * it);
       }
       __syncwarp();
@@ -215,7 +228,8 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
       }
       uint32_t done = TC_S_DONE(s);
       if (elect_one()) {
-        umma_commit(empty0 + 8 * it);              // frees the ring space when these MMAs have read it
+        if (CT == 1) umma_commit(empty0 + 8 * it);  // frees the ring space when these MMAs have read it
+        else umma_commit_mc(empty0 + 8 * it, cmask);
         while (done) {                             // accumulators that received their last block in this iteration
           const int dq = __ffs(done) - 1;
           done &= done - 1;
@@ -449,6 +463,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
   }
   tc_fence_before();
   __syncthreads();
+  if (CT > 1) cluster_sync_all();          // no CTA leaves while peers may still multicast into it or arrive on its barriers
   if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
@@ -468,11 +483,36 @@ bool lcn_tc_enabled() {
 static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* addend,
                           __nv_bfloat16* Y, float* part, const TcParams& p, int tiles, cudaStream_t st) {
   static bool attr = false;
+  static int ct_env = 1;
   if (!attr) {
     LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    const char* e = getenv("LCN_TC_CLUSTER");              // row tiles per cluster sharing the weight panels: 1, 2 or 4
+    ct_env = e ? atoi(e) : 1;
+    if (ct_env != 2 && ct_env != 4) ct_env = 1;
     attr = true;
   }
-  lcn_launch(k_tc_gemm, dim3(dim3(p.n_groups, tiles)), dim3(TC_GEMM_THREADS), (size_t)TC_SMEM_BYTES, st, A, W, bias, addend, Y, part, p);
+  int ct = ct_env;
+  while (ct > 1 && tiles % ct) ct >>= 1;
+  if (ct == 1) {
+    lcn_launch(k_tc_gemm, dim3(dim3(p.n_groups, tiles)), dim3(TC_GEMM_THREADS), (size_t)TC_SMEM_BYTES, st, A, W, bias, addend, Y, part, p);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(p.n_groups, tiles);
+    cfg.blockDim = dim3(TC_GEMM_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = (unsigned)ct;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = lcn_pdl_enabled() ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, k_tc_gemm, A, W, bias, addend, Y, part, p);
+  }
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
