@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
                              "sample": f"{args.steps} train steps at batch {batch} (dense fp32 restatement of the "
                                        f"TF graph, torch-CPU autograd; TensorFlow 2.13 not installable offline)"},
             "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -354,12 +354,22 @@ def run_gpu(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": cb * cs / dt, "unit": "poses/s", "cores": threads, "kind": "port",
                                     "sample": f"{cs} train steps at batch {cb}: dense fp32 restatement of the TF graph "
                                               f"(torch-CPU autograd + TF1 Adam); TensorFlow 2.13 not installable offline"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+JSON_OUT = sys.stdout
+
+
 def main():
+    # The contract is ONE JSON line on stdout.  NCCL prints its version banner with a C-level printf to stdout when the
+    # first communicator is created (seen on the GPU boxes: "NCCL version 2.28.9+cuda12.9" in front of the line), so the
+    # process's fd 1 is pointed at stderr and the JSON line goes to a duplicate of the original stdout.
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
