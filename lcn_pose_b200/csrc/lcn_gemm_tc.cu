@@ -1047,6 +1047,7 @@ static void tcw_build_units(TcwParams& p) {
     for (int oc = 0; oc < p.NCN; ++oc)
       if (ina[oc] || inb[oc]) un[nu++] = (uint8_t)oc;
     for (int g0 = 0; g0 < nu; g0 += TC_G) {
+      if (p.n_units >= TCW_MAX_UNITS) return;       // cannot happen: 17 pairs x ceil(34 / 4) = 153 units at most
       TcwUnit& u = p.unit[p.n_units++];
       memset(&u, 0, sizeof(u));
       u.ic0 = (uint8_t)pa[e];
@@ -1058,6 +1059,18 @@ static void tcw_build_units(TcwParams& p) {
       }
     }
   }
+}
+
+// unit table of the weight-gradient kernel for inspection / tests (host only): per unit 12 bytes
+// {ic0, ic1, len, 0, oc[4], keep[4]}; returns the number of units
+extern "C" int lcn_debug_tcw_units(const uint32_t* row17, int FCK, int FCN, int NCK, int NCN, uint8_t* units_out, int max_units) {
+  TcwParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < LCN_J; ++i) p.row[i] = row17[i];
+  p.FCK = FCK; p.FCN = FCN; p.NCK = NCK; p.NCN = NCN;
+  tcw_build_units(p);
+  for (int u = 0; u < p.n_units && u < max_units; ++u) memcpy(units_out + 12 * u, &p.unit[u], 12);
+  return p.n_units;
 }
 
 static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW, int tiles,

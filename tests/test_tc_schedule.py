@@ -101,3 +101,61 @@ def test_knn3_chunks_complete_staggered():
             if first_done is None and (s >> 24) & 63:
                 first_done = blocks
         assert first_done <= 0.6 * blocks, (g, first_done, blocks)
+
+
+def _wgrad_units(support, FCK, FCN, NCK, NCN):
+    lib = L.load()
+    row = (C.c_uint32 * 17)(*[int(sum(1 << j for j in range(17) if support[i, j])) for i in range(17)])
+    buf = (C.c_uint8 * (12 * 160))()
+    lib.lcn_debug_tcw_units.restype = C.c_int
+    n = lib.lcn_debug_tcw_units(row, FCK, FCN, NCK, NCN, buf, 160)
+    return np.array(buf[:12 * n], dtype=np.uint8).reshape(n, 12)
+
+
+@pytest.mark.parametrize("knn,FC", [(1, 1), (2, 1), (3, 1), (3, 2), (0, 1), (0, 2)])
+def test_wgrad_units_cover_exactly_the_mask_blocks(knn, FC):
+    """Weight-gradient units (pairs of input chunks x groups of <= 4 output chunks of the union of their neighbourhoods,
+    lcn_gemm_tc.cu: tcw_build_units): every nonzero (input chunk, output chunk) block is stored by exactly one unit and
+    row half, nothing outside the mask is stored, every input chunk sits in exactly one pair."""
+    sup = (O.get_neighbour_matrix_by_hand(knn=knn).T != 0) if knn > 0 else np.ones((17, 17), bool)
+    NC = 17 * FC
+    units = _wgrad_units(sup, FC, FC, NC, NC)
+    assert 0 < len(units) <= 160
+    stored = np.zeros((NC, NC), int)
+    partner = {}
+    computed = 0
+    for ic0, ic1, ln, _, *rest in units.tolist():
+        ocs, keep = rest[:4], rest[4:]
+        assert 1 <= ln <= 4 and ic0 < NC and (ic1 == 0xFF or ic1 < NC)
+        partner.setdefault(ic0, ic1)
+        assert partner[ic0] == ic1                      # an input chunk always appears with the same partner
+        assert len(set(ocs[:ln])) == ln
+        computed += ln * 2                              # M = 128 MMAs: both row halves run, single or not
+        for q in range(ln):
+            assert keep[q] & 3 and not keep[q] & ~3
+            if keep[q] & 1:
+                stored[ic0, ocs[q]] += 1
+            if keep[q] & 2:
+                assert ic1 != 0xFF
+                stored[ic1, ocs[q]] += 1
+    want = np.kron(sup, np.ones((FC, FC), int))
+    assert np.array_equal(stored, want)
+    firsts, seconds = set(partner), {v for v in partner.values() if v != 0xFF}
+    assert not firsts & seconds and firsts | seconds == set(range(NC))
+    if knn == 3 and FC == 1:
+        assert len(units) == 31 and computed == 218     # the figures DESIGN.md quotes
+    if FC == 2:
+        assert computed == int(want.sum())              # the two halves of a joint share their neighbourhood: no waste
+
+
+def test_wgrad_units_edge_layers():
+    """Last layer (every input chunk -> the one padded output chunk) and first layer (one padded input chunk -> all)."""
+    row1 = np.zeros((17, 17), bool)
+    row1[:, 0] = True
+    units = _wgrad_units(row1, 1, 1, 17, 1)
+    assert len(units) == 9 and all(u[2] == 1 and u[4] == 0 for u in units.tolist())
+    first = np.zeros((17, 17), bool)
+    first[0, :] = True
+    units = _wgrad_units(first, 1, 1, 1, 17)
+    assert len(units) == 5 and all(u[0] == 0 and u[1] == 0xFF for u in units.tolist())
+    assert sorted(oc for u in units.tolist() for oc in u[4:4 + u[2]]) == list(range(17))
