@@ -260,18 +260,13 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
     LCN_CHECK_CUDA(cudaEventRecord(ax->ev_go, st));
     LCN_CHECK_CUDA(cudaStreamWaitEvent(est, ax->ev_go, 0));
   }
+  // two dependent pairs of small launches (dense masked weights, then their bf16 tiles): the first layer's pair on the
+  // side stream, the last layer's pair behind the mid-layer pack on the caller's stream -- the tail is one pair long
   lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_first));
-  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
-                                  reinterpret_cast<float*>(ws + lay.off_wm_last));
-  if (m->d.path == LCN_PATH_BF16) {
-    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_last),
-                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
-                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
-    if (m->L[0].Kin <= 64)
-      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
-                                                    m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
-  }
+  if (m->d.path == LCN_PATH_BF16 && m->L[0].Kin <= 64)
+    lcn_launch(k_pack_first16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
+                                                  m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
   if (ax) LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, est));
   if (n_mid > 0) {
     lcn_launch(k_pack_mid, dim3(dim3(m->nnz * m->FC * m->FC, n_mid)), dim3(256), 0, st, 
@@ -279,6 +274,12 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
         reinterpret_cast<float*>(ws + lay.off_wp32), reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f),
         reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b), use_tc ? 0 : 1, use_tc ? 1 : 0);
   }
+  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
+                                  reinterpret_cast<float*>(ws + lay.off_wm_last));
+  if (m->d.path == LCN_PATH_BF16)
+    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC, 4), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
+                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
   LCN_CHECK_LAUNCH();
   if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   return LCN_OK;
@@ -1459,9 +1460,10 @@ __global__ void k_pairdot(const float* __restrict__ params, const float* __restr
 // per-layer <dWc,W> -> clip coefficient; mask gradient through the column softmax
 __global__ void k_maskgrad(const float* __restrict__ params, int64_t mask_off, SupportBits sup, PairTable pt,
                            int nnz, int n_lin, const float* __restrict__ pairdot, const float* __restrict__ mask,
-                           LayerScalars* sc, float* __restrict__ maskgrad /*[289]*/) {
+                           LayerScalars* sc, float* __restrict__ maskgrad /*[289]*/, int zero_norm2) {
   lcn_pdl_prologue();
   __shared__ float dM[LCN_J * LCN_J];
+  if (zero_norm2 && threadIdx.x < n_lin) sc[threadIdx.x].norm2 = 0.0;   // the Adam kernel that follows accumulates ||W_new||^2
   __shared__ float soft[LCN_J * LCN_J];
   int t = threadIdx.x;
   for (int l = t >> 5; l < n_lin; l += (int)(blockDim.x >> 5)) {      // one warp per layer, lanes over the pairs
@@ -1615,21 +1617,21 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
 }
 
 static int launch_grad_chain(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
-                             const float* graw, cudaStream_t st) {
+                             const float* graw, cudaStream_t st, int zero_norm2) {
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
   float* pairdot = reinterpret_cast<float*>(ws + lay.off_pairdot);
   float* maskgrad = mask + 2 * LCN_J * LCN_J;
   lcn_launch(k_pairdot, dim3(dim3(m->nnz, m->n_lin)), dim3(256), 0, st, params, graw, make_lin(m), make_pairs(m), pairdot);
   lcn_launch(k_maskgrad, dim3(1), dim3(320), 0, st, params, m->mask_off, m->sup, make_pairs(m), m->nnz, m->n_lin, pairdot, mask, sc,
-                                maskgrad);
+                                maskgrad, zero_norm2);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
 
 int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
                              const float* grads_raw, float* grads_out, cudaStream_t st) {
-  int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st);
+  int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st, /*zero_norm2=*/0);
   if (rc) return rc;
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
@@ -1643,11 +1645,10 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
 int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
                     const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg,
                     const lcn_step_scalars* dyn, cudaStream_t st) {
-  int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st);
+  int rc = launch_grad_chain(m, params, ws, lay, grads_raw, st, /*zero_norm2=*/1);
   if (rc) return rc;
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);
   float* mask = reinterpret_cast<float*>(ws + lay.off_mask);
-  lcn_launch(k_zero_norm2, dim3(1), dim3(32), 0, st, sc, m->n_lin);
   lcn_launch(k_adam<false>, dim3(std::min(m->segs.total_chunks * (LCN_ADAM_CHUNK / 1024), 8 * m->sm_count)), dim3(256), 0, st, params, mm, vv, grads_raw, nullptr, m->segs, make_lin(m),
                                                       m->sup, mask, mask + 2 * LCN_J * LCN_J, sc, lr_t, b1, b2, eps,
                                                       reg, dyn);
