@@ -198,18 +198,24 @@ def run_gpu(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     n_bn = 1 + 2 * LAYERS
 
-    from lcn_pose_b200.dist import average_gradient_bucket as allreduce   # one bucket: raw gradient of every tensor
+    # one bucket: the raw gradients, packed to the nonzero joint-pair blocks (LCN_DP_PACKED=0: the full parameter-layout vector)
+    from lcn_pose_b200.dist import average_gradient_bucket as allreduce
+    packed = os.environ.get("LCN_DP_PACKED", "1") != "0"
 
     def step(xx, yy):
         if args.no_graph:
             eng.forward(xx, bn_group=BATCH, training=True, dropout=args.dropout)
             eng.backward(xx, yy, args.dropout)
             if world > 1:
-                allreduce(eng.grads_raw)
+                if packed:
+                    allreduce(eng.pack_grads())
+                    eng.unpack_grads()
+                else:
+                    allreduce(eng.grads_raw)
             eng.adam()
         else:
             # the same launches, replayed from a CUDA graph (LcnEngine.train_step_graph)
-            eng.train_step_graph(xx, yy, args.dropout, allreduce if world > 1 else None)
+            eng.train_step_graph(xx, yy, args.dropout, allreduce if world > 1 else None, packed=packed)
 
     def barrier():
         torch.cuda.synchronize()
@@ -329,7 +335,7 @@ def run_gpu(args, rank, world, local_rank):
                 "dtype": "bf16" if args.path == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "flushed between steps (256 MiB memset)",
                            "dropout": args.dropout, "path": args.path, "launch": "eager" if args.no_graph else "cuda-graph replay",
-                           "parallelism": f"dp{world}: per-GPU BatchNorm statistics, NCCL allreduce of the gradient bucket"},
+                           "parallelism": f"dp{world}: per-GPU BatchNorm statistics, NCCL allreduce of the " + ("packed nonzero-block" if packed else "parameter-layout") + " gradient bucket"},
                 "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "poses/s",
                         "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4},
                 "gpu_launches": launches_per_step(n_bn) * args.steps,

@@ -142,6 +142,16 @@ int lcn_model_backward(lcn_model* m, const float* d_params, void* d_ws, size_t w
 int lcn_model_finalize_grads(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes,
                              const float* d_grads_raw, float* d_grads_out, void* stream);
 
+/* Data-parallel exchange ("allreduce of the packed nonzero-block gradient"; the reference has no
+ * distributed code, models_att.py:155-158).  The raw-gradient bucket has the parameter layout, so 40 % of it (knn=3) are
+ * the never-written zero entries of masked-out joint-pair blocks.  lcn_model_pack_grads gathers what backward actually
+ * produces -- the nonzero Fi x Fo blocks of every weight matrix, then every other tensor whole -- into
+ * lcn_model_grad_compact_count(m) contiguous floats; the host all-reduces that buffer and lcn_model_unpack_grads
+ * scatters it back before lcn_model_adam_step.  Both only enqueue on `stream`. */
+int64_t lcn_model_grad_compact_count(const lcn_model* m);
+int lcn_model_pack_grads(lcn_model* m, const float* d_grads_raw, float* d_compact, void* stream);
+int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_raw, void* stream);
+
 /* (a10) ... or applies TF1 Adam directly from the raw gradients in one fused pass (models_att.py:404-409):
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (host scalar); theta -= lr_t*m/(sqrt(v)+eps).
  * `regularization` adds reg*theta to the gradient of w* / b* (models_att.py:362-365).  Also re-runs the

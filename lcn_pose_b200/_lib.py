@@ -41,6 +41,9 @@ PROTOTYPES = {
     "lcn_model_forward_taps": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "lcn_model_backward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _i64, _f, _u64, _u64, _vp, _vp, _vp]),
     "lcn_model_finalize_grads": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "lcn_model_grad_compact_count": (_i64, [_vp]),
+    "lcn_model_pack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "lcn_model_unpack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lcn_model_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _vp, _vp]),
     "lcn_layer_gemm": (C.c_int, [_vp, _vp, _vp, _sz, _i64, _i32, C.c_int, C.c_int, _vp]),
     "lcn_model_read_tensor": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _i64, _i32, _vp, _vp]),

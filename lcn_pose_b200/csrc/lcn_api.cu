@@ -455,6 +455,16 @@ extern "C" int lcn_model_adam_step(lcn_model* m, float* d_params, float* d_m, fl
                          d_dyn, (cudaStream_t)stream);
 }
 
+extern "C" int64_t lcn_model_grad_compact_count(const lcn_model* m) { return m ? lcn_grad_compact_count(m) : 0; }
+extern "C" int lcn_model_pack_grads(lcn_model* m, const float* d_grads_raw, float* d_compact, void* stream) {
+  LCN_REQUIRE(m != nullptr && d_grads_raw != nullptr && d_compact != nullptr, "null argument");
+  return lcn_launch_grad_compact(m, const_cast<float*>(d_grads_raw), d_compact, false, (cudaStream_t)stream);
+}
+extern "C" int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_raw, void* stream) {
+  LCN_REQUIRE(m != nullptr && d_grads_raw != nullptr && d_compact != nullptr, "null argument");
+  return lcn_launch_grad_compact(m, d_grads_raw, const_cast<float*>(d_compact), true, (cudaStream_t)stream);
+}
+
 extern "C" int lcn_layer_gemm(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, int64_t n_rows,
                               int32_t bn_group, int layer, int transposed, void* stream) {
   int rc = check_geom(m, n_rows, bn_group);

@@ -264,6 +264,8 @@ int lcn_launch_grad_finalize(const lcn_model* m, const float* params, char* ws, 
 int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, char* ws, const WsLayout& lay,
                     const float* grads_raw, float lr_t, float b1, float b2, float eps, float reg,
                     const lcn_step_scalars* dyn, cudaStream_t st);
+int64_t lcn_grad_compact_count(const lcn_model* m);
+int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, bool unpack, cudaStream_t st);
 int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
                           int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,

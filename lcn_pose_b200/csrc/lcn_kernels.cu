@@ -1616,6 +1616,70 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// packed gradient exchange (include/lcn_b200.h: lcn_model_pack_grads / lcn_model_unpack_grads)
+// blocks [0, nnz * n_lin): one Fi x Fo block of one weight matrix; the remaining blocks: one non-weight tensor each
+// ------------------------------------------------------------------------------------------------
+struct CompactTable {
+  int64_t w_coff[LCN_MAX_LIN];          // compact offset of layer l's first block
+  int n_other;
+  int64_t o_off[LCN_MAX_TENSORS], o_size[LCN_MAX_TENSORS], o_coff[LCN_MAX_TENSORS];
+  int64_t total;
+};
+static CompactTable make_compact(const lcn_model* m) {
+  CompactTable c;
+  memset(&c, 0, sizeof(c));
+  int64_t off = 0;
+  for (int l = 0; l < m->n_lin; ++l) {
+    c.w_coff[l] = off;
+    off += (int64_t)m->nnz * m->L[l].Fi * m->L[l].Fo;
+  }
+  for (int s = 0; s < m->segs.n; ++s) {
+    if (m->segs.s[s].kind == SEG_W) continue;
+    c.o_off[c.n_other] = m->segs.s[s].off;
+    c.o_size[c.n_other] = m->segs.s[s].size;
+    c.o_coff[c.n_other] = off;
+    off += m->segs.s[s].size;
+    ++c.n_other;
+  }
+  c.total = off;
+  return c;
+}
+template <bool UNPACK>
+__global__ void __launch_bounds__(256) k_grad_compact(float* __restrict__ graw, float* __restrict__ compact, LinTable lt,
+                                                      PairTable pt, CompactTable ct, int nnz, int n_lin) {
+  lcn_pdl_prologue();
+  const int b = blockIdx.x;
+  if (b < nnz * n_lin) {
+    const int l = b / nnz, p = b - l * nnz;
+    const int Fi = lt.Fi[l], Fo = lt.Fo[l], Kout = LCN_J * Fo;
+    const int i = pt.pi[p], j = pt.pj[p];
+    float* g = graw + lt.w_off[l];
+    float* c = compact + ct.w_coff[l] + (int64_t)p * Fi * Fo;
+    for (int e = threadIdx.x; e < Fi * Fo; e += 256) {
+      const int fi = e / Fo, fo = e - fi * Fo;
+      const size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
+      if (UNPACK) g[o] = c[e]; else c[e] = g[o];
+    }
+  } else {
+    const int k = b - nnz * n_lin;
+    float* g = graw + ct.o_off[k];
+    float* c = compact + ct.o_coff[k];
+    for (int64_t e = threadIdx.x; e < ct.o_size[k]; e += 256) {
+      if (UNPACK) g[e] = c[e]; else c[e] = g[e];
+    }
+  }
+}
+int64_t lcn_grad_compact_count(const lcn_model* m) { return make_compact(m).total; }
+int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, bool unpack, cudaStream_t st) {
+  const CompactTable ct = make_compact(m);
+  const dim3 grid((unsigned)(m->nnz * m->n_lin + ct.n_other));
+  if (unpack) lcn_launch(k_grad_compact<true>, grid, dim3(256), 0, st, graw, compact, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
+  else lcn_launch(k_grad_compact<false>, grid, dim3(256), 0, st, graw, compact, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
 static int launch_grad_chain(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
                              const float* graw, cudaStream_t st, int zero_norm2) {
   LayerScalars* sc = reinterpret_cast<LayerScalars*>(ws + lay.off_scalars);

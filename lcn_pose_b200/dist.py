@@ -3,7 +3,8 @@
 * Inference / evaluation shard the pose set at BatchNorm-group granularity (the reference's BN uses batch statistics at
   inference too, models_att.py:588-612 + SURVEY 9-Q2, so a batch of `batch_size` consecutive poses is the unit of
   independence): no collective on the data path, one small all-reduce of the per-joint error sums at the end.
-* Data-parallel training all-reduces ONE bucket (the flat raw-gradient vector, parameter layout) between backward
+* Data-parallel training all-reduces ONE bucket (the raw gradients, packed to the nonzero weight blocks + the small
+  tensors: average_gradients_packed; or the flat parameter-layout vector: average_gradient_bucket) between backward
   and the fused Adam step; BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
 Everything here is backend agnostic (nccl on GPUs, gloo in the CPU tests)."""
 import torch
@@ -38,6 +39,16 @@ def average_gradient_bucket(bucket, group=None):
             dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
             bucket.div_(dist.get_world_size(group))
     return bucket
+
+
+def average_gradients_packed(engine, group=None):
+    """The same exchange on the packed bucket: LcnEngine.pack_grads() leaves out the never-written entries of the
+    masked-out joint-pair blocks (40 % of the parameter-layout bucket for knn=3), one collective, unpack.  No-op (and no
+    pack / unpack launches) in a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        average_gradient_bucket(engine.pack_grads(), group)
+        engine.unpack_grads()
+    return engine.grads_raw
 
 
 def broadcast_parameters(flat_params, src=0, group=None):

@@ -220,6 +220,20 @@ class LcnEngine:
                                             _ptr(self.loss_dev), _ptr(self.grads_raw), self._stream()))
         return self.loss_dev
 
+    # ---- data-parallel exchange: only what backward produces travels (lcn_model_pack_grads) ----
+    def pack_grads(self):
+        """Gather the nonzero weight blocks + every other tensor of the raw-gradient bucket into self.grads_compact."""
+        if getattr(self, "grads_compact", None) is None:
+            n = int(self.lib.lcn_model_grad_compact_count(self.h))
+            self.grads_compact = torch.empty(n, dtype=torch.float32, device=self.device)
+        L.check(self.lib.lcn_model_pack_grads(self.h, _ptr(self.grads_raw), _ptr(self.grads_compact), self._stream()))
+        return self.grads_compact
+
+    def unpack_grads(self):
+        """Scatter self.grads_compact (all-reduced by the caller) back into the raw-gradient bucket."""
+        L.check(self.lib.lcn_model_unpack_grads(self.h, _ptr(self.grads_compact), _ptr(self.grads_raw), self._stream()))
+        return self.grads_raw
+
     def true_grads(self):
         g = torch.empty_like(self.params)
         L.check(self.lib.lcn_model_finalize_grads(self.h, _ptr(self.params), _ptr(self.ws), self.ws.numel(),
@@ -258,20 +272,24 @@ class LcnEngine:
         self._dyn_ev[slot] = ev
         return lr
 
-    def train_step_graph(self, x, labels, dropout=0.0, allreduce=None):
+    def train_step_graph(self, x, labels, dropout=0.0, allreduce=None, packed=False):
         """train_step() as CUDA-graph replays: the ~60 launches of one step (forward, loss, backward, chain rule,
         Adam, weight re-preparation) are captured once per (batch shape, dropout, buffers) and replayed; the
         per-step scalars (dropout counter, Adam step size) travel through 16 bytes of device memory.
         `x` / `labels` must be the SAME device tensors every call (copy new batches into them).
         allreduce: optional callable run between backward and Adam on the gradient bucket (data parallel);
-        then two graphs are replayed around it.  Returns (loss device scalar, learning rate used)."""
-        key = (x.data_ptr(), labels.data_ptr(), tuple(x.shape), float(dropout), allreduce is not None)
+        then two graphs are replayed around it.  packed=True: the callable receives the packed bucket
+        (self.grads_compact: nonzero weight blocks + small tensors); the pack / unpack launches are part of the two
+        graphs.  Returns (loss device scalar, learning rate used)."""
+        key = (x.data_ptr(), labels.data_ptr(), tuple(x.shape), float(dropout), allreduce is not None, bool(packed))
         n = x.shape[0]
         if key not in self._graphs:
             self._ensure_ws(n, n, True)
             if not self._prepared:
                 self.prepare()
             out = torch.empty((n, J * 3), dtype=torch.float32, device=self.device)
+            if packed:
+                self.pack_grads()                    # allocates self.grads_compact outside the capture
             self._stage_scalars(self.step + 1)
             # warm-up on a side stream (first-call attribute setup must not happen under capture)
             side = torch.cuda.Stream(device=self.device)
@@ -291,17 +309,21 @@ class LcnEngine:
                 self.backward(x, labels, dropout)
                 if allreduce is None:
                     self.adam(dyn=True)
+                elif packed:
+                    self.pack_grads()
             g2 = None
             if allreduce is not None:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2):
+                    if packed:
+                        self.unpack_grads()
                     self.adam(dyn=True)
             self._graphs[key] = (g1, g2, out)
         g1, g2, _ = self._graphs[key]
         lr = self._stage_scalars(self.step + 1)
         g1.replay()
         if g2 is not None:
-            allreduce(self.grads_raw)
+            allreduce(self.grads_compact if packed else self.grads_raw)
             g2.replay()
         self.step += 1
         self._prepared = True

@@ -255,3 +255,39 @@ def test_graph_replayed_train_steps_equal_eager_steps():
         assert float(d.max()) < 1e-4, (path, float(d.max()))
         dv = (eng_a.adam_v - eng_b.adam_v).abs()
         assert int((dv > 1e-12 + 1e-3 * eng_b.adam_v.abs()).sum()) <= 8
+
+
+@pytest.mark.parametrize("mask_type,knn,F", [("locally_connected", 3, 64), ("exponential", 1, 64), ("locally_connected", 2, 128)])
+def test_packed_gradient_bucket_round_trip(mask_type, knn, F):
+    """lcn_model_pack_grads / lcn_model_unpack_grads (the data-parallel exchange buffer): the packed buffer holds
+    exactly the nonzero joint-pair blocks of every weight matrix plus the other tensors, and scattering it back
+    reproduces every entry backward wrote (the masked-out entries of the bucket are zero and stay untouched)."""
+    import torch
+    eng, cfg, p = make_pair(F=F, L=1, knn=knn, mask_type=mask_type, path="bf16")
+    n = 128
+    x, y = synth_xy(n)
+    eng.forward(dev(x), bn_group=n, training=True)
+    eng.backward(dev(x), dev(y), 0.0)
+    raw = eng.grads_raw.clone()
+    g0 = eng.unflatten(eng.true_grads())            # per tensor: the alignment gaps of the flat vector are never written
+    packed = eng.pack_grads().clone()
+    sup = cfg.support() != 0
+    want = 0
+    for name in O.weight_names(cfg):
+        fi, fo = p[name].shape[0] // 17, p[name].shape[1] // 17
+        want += int(sup.sum()) * fi * fo
+    want += sum(v.size for k, v in p.items() if k not in O.weight_names(cfg))
+    assert packed.numel() == want
+    assert float(packed.abs().sum()) > 0
+    # everything the chain rule / Adam read from the bucket survives the round trip: poison the bucket, scatter the
+    # packed copy back, and the true gradients come out bit-identical (entries outside the support -- e.g. the dense
+    # edge-layer products -- are never read, so they may keep the poison)
+    eng.grads_raw.fill_(12345.0)
+    eng.unpack_grads()
+    back = eng.grads_raw
+    written = back != 12345.0
+    assert int(written.sum()) <= want and int(written.sum()) > 0.99 * want      # (an entry may equal the poison by chance)
+    assert torch.equal(back[written], raw[written])
+    g1 = eng.unflatten(eng.true_grads())
+    for k in g0:
+        assert np.array_equal(g0[k], g1[k]), k
