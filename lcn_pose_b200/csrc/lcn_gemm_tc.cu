@@ -1,24 +1,25 @@
-// bf16 tensor-core kernels of the LCN mid layers for sm_100a: tcgen05.mma with TMEM accumulators,
-// operands staged by 1-D bulk TMA (cp.async.bulk) through an mbarrier pipeline.
+// bf16 tensor-core kernels of the LCN layers for sm_100a: tcgen05.mma with TMEM accumulators, operands staged by
+// 1-D bulk TMA (cp.async.bulk) through mbarrier pipelines.
 //
-//   lcn_tc_gemm  : Y[128-row tile, group of <=4 output chunks] = sum over the input chunks that have a
-//                  nonzero 64x64 block into the group of  A[tile, chunk] (128x64, K-major SW128)  x
-//                  Wp(panel of present blocks) -- all-zero joint-pair blocks of the mask are never
-//                  loaded nor multiplied (network/models_att.py:576-586 multiplies them densely).
-//                  Forward: + bias, BatchNorm (mean, M2) partials per column (models_att.py:588-612),
-//                  transposed (dgrad): + residual gradient addend.
-//   lcn_tc_wgrad : dWm block(i,j) = A[:, i]^T dZ[:, j] for the nonzero blocks only, K = batch rows,
-//                  both operands MN-major straight out of the tile-major activation layout.
+//   k_tc_gemm  : Y[128-row tile, group of <=6 output chunks] = sum over the input chunks that have a nonzero 64x64
+//                block into the group of  A[tile, chunk] (128x64, K-major SW128)  x  Wp(panel of present blocks) --
+//                all-zero joint-pair blocks of the mask are never loaded nor multiplied (network/models_att.py:576-586
+//                multiplies them densely).  Forward: + bias, BatchNorm statistics per column (models_att.py:588-612;
+//                fp64 atomics or per-tile (mean, M2) partials); transposed (dgrad): + residual gradient addend; head
+//                mode: the last layer with the xy skip (models_att.py:765-773).
+//   k_tc_wgrad : dWm block(i,j) = A[:, i]^T dZ[:, j] for the nonzero blocks only, K = batch rows, both operands MN-major
+//                straight out of the tile-major activation layout, M = 128 from pairs of input chunks.
 //
-// Data layout contracts: activations are tile-major SW128 (lcn_internal.cuh, lcn_off<bf16>), packed
-// weights are per-64x64-block SW128 K-major images written by k_pack_mid (lcn_kernels.cu) in the order
-// the panels are consumed, so every operand is one contiguous bulk copy -- no tensor maps needed.
+// Data layout contracts: activations are tile-major SW128 (lcn_internal.cuh, lcn_off<bf16>), packed weights are
+// per-64x64-block SW128 K-major images written by k_pack_mid (lcn_kernels.cu) in the order the panels are consumed, so
+// every operand is one contiguous bulk copy -- no tensor maps needed.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem tile -> bulk store); all six warps compute the
-// BatchNorm partials.  A kernel that allocates TMEM gets ONE resident CTA per SM (cudaOccupancyMaxActiveBlocksPer-
-// Multiprocessor reports 1 for any kernel containing tcgen05.alloc, profiles/micro/occ.cu), so grids are sized as
-// single waves of <= SM-count CTAs and a CTA may use the whole shared memory and all 512 TMEM columns.
+// Warp roles of k_tc_gemm (352 threads): warp 0 = TMA producer, warps 1-2 = MMA issuers (even / odd iterations; warp 1
+// also owns the TMEM allocation), warps 3-10 = epilogue in two teams of four (TMEM -> registers -> swizzled smem tile ->
+// bulk store, BatchNorm sums).  k_tc_wgrad (224 threads): producer, two MMA issuers, four epilogue warps.  A kernel
+// that allocates TMEM gets ONE resident CTA per SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for any
+// kernel containing tcgen05.alloc, profiles/micro/occ.cu), so grids are sized as single waves of <= SM-count CTAs and a
+// CTA may use the whole shared memory and all 512 TMEM columns.  What bounds these kernels: DESIGN.md section 4.1.
 #include <stdlib.h>
 #include <string.h>
 
