@@ -291,3 +291,18 @@ def test_packed_gradient_bucket_round_trip(mask_type, knn, F):
     g1 = eng.unflatten(eng.true_grads())
     for k in g0:
         assert np.array_equal(g0[k], g1[k]), k
+
+
+def test_forward_and_train_step_multi_wave_bf16():
+    """More CTAs than SMs in the tensor-core GEMMs (40 row tiles x 4 chunk groups = 160 > 148) and a ragged last tile
+    (5000 = 39 * 128 + 8): per-layer parity of the forward pass, and one train step against the oracle's loss."""
+    eng, cfg, p = make_pair(L=1, knn=3, path="bf16")
+    n = 5000
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    out = eng.forward(xd, bn_group=n, training=True).cpu().numpy()
+    _per_layer_check(eng, cfg, p, x.astype(np.float64), n, n, 0.0, TOL["bf16"])
+    assert rel_err(out, O.forward(cfg, p, x.astype(np.float64))[0]) < 5e-2
+    loss, _ = eng.train_step(xd, yd)
+    ref_loss, _ = O.loss_and_grads(cfg, p, x.astype(np.float64), y.astype(np.float64))
+    assert abs(loss.item() - ref_loss) < 2e-2 * ref_loss
