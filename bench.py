@@ -171,10 +171,10 @@ def run_reference(args, rank, world):
 def launches_per_step(n_bn):
     """Kernels of this library per train step on the bf16 path (counted from the launch list, profiles/r1):
     forward: (GEMM | first layer) + bn_act per BN layer (the BatchNorm statistics are accumulated by the GEMM itself),
-    head GEMM; backward: loss, head dgrad, last-layer wgrad, fused BN backward per BN layer, dgrad + wgrad per mid layer,
+    head GEMM; backward: loss, head dgrad, last-layer wgrad, BN backward (reduce + apply) per BN layer, dgrad + wgrad per mid layer,
     first-layer wgrad, bias-gradient reduce; optimizer: pairdot, mask gradient, Adam, mask scalars, 5 weight packs."""
     fwd = 2 * n_bn + 1
-    bwd = 3 + n_bn + 2 * (n_bn - 1) + 2
+    bwd = 3 + 2 * n_bn + 2 * (n_bn - 1) + 2
     opt = 9
     return fwd + bwd + opt
 

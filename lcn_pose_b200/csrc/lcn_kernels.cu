@@ -1952,7 +1952,15 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
       const char* e = getenv("LCN_DISABLE_FUSED_BNBWD");
       if (e && e[0] == '1') ok = 0;
     }
-    fused_bwd = ok == 1;
+    // With the weight gradients on the side stream the grid-barrier kernel is the slower choice: it cannot start
+    // before the weight-gradient CTAs of the previous layer have drained (all of its blocks must be resident), while the
+    // two plain launches interleave with them (0.577 against 0.583 ms per step).  LCN_FORCE_FUSED_BNBWD=1 keeps it.
+    static int force = -1;
+    if (force < 0) {
+      const char* e = getenv("LCN_FORCE_FUSED_BNBWD");
+      force = (e && e[0] == '1') ? 1 : 0;
+    }
+    fused_bwd = ok == 1 && (ax == nullptr || force == 1);
   }
   PairTable pt = make_pairs(m);
   if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_ms, 0));   // the bucket is clear before this stream stores into it
