@@ -72,6 +72,10 @@ typedef struct lcn_model lcn_model; /* opaque */
 const char* lcn_version(void);
 const char* lcn_last_error(void);
 
+/* CRC32C (Castagnoli) of HOST memory, continuing from `crc` (0 to start): the checksum TensorFlow's Saver V2 files carry
+ * (tools/tf_checkpoint.py reads and writes the reference's checkpoints, models_att.py:256-260,445-463). */
+uint32_t lcn_crc32c(const void* h_data, size_t n, uint32_t crc);
+
 /* ---- mask construction on the host, bit exact (tools/params_help.py:8-20, tools/filter_hub.py:4-20,
  *      network/models_att.py:14-69) ---- */
 int lcn_neighbour_matrix(int knn, float* h_out /* [17*17] float32 0/1 */);
@@ -119,6 +123,18 @@ int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws, size_t ws
                       float dropout_rate, uint64_t seed, uint64_t step, float* d_out,
                       const lcn_step_scalars* d_dyn, void* stream);
 
+/* A sub-range of the stack, for the reference's method-level layer API: runs the linear layers [layer_begin, layer_end)
+ * (0 = w1 ... 2*num_layers+1 = w4; each of the first 2*num_layers+1 is followed by its BatchNorm / LeakyReLU / dropout
+ * and, where the reference has one, the residual add) on the TRAINING workspace layout, where every layer keeps its
+ * own buffers.  The input of layer_begin > 0 is the activation A_{layer_begin-1} already in the workspace (left there
+ * by a previous forward, or injected with lcn_model_write_tensor); the output A_{layer_end-1} is read with
+ * lcn_model_read_tensor(kind 1).  cgcnn.two_linear(xin, dropout, idx) (models_att.py:630-705) is
+ * write_tensor(A_{2 idx}) + forward_layers(2 idx + 1, 2 idx + 3) + read_tensor(A_{2 idx + 2}).  d_x is needed when the
+ * range contains the first or the last layer, d_out when it contains the last. */
+int lcn_model_forward_layers(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,
+                             int64_t n_rows, int32_t bn_group, float dropout_rate, uint64_t seed, uint64_t step,
+                             int layer_begin, int layer_end, float* d_out, void* stream);
+
 /* Same arithmetic, with a parity tap: valid only where inference runs as the fused cluster kernel (bf16 path,
  * F = 64, bn_group <= 256; LCN_EINVAL otherwise).  d_taps receives every layer output A_l (after
  * BN / LeakyReLU / residual) as bf16 in the kernel's tile-major layout: [n_bn][tile][17 chunks][128 rows][64]
@@ -152,6 +168,21 @@ int64_t lcn_model_grad_compact_count(const lcn_model* m);
 int lcn_model_pack_grads(lcn_model* m, const float* d_grads_raw, float* d_compact, void* stream);
 int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_raw, void* stream);
 
+/* Data-parallel training with the exchange INSIDE the backward pass (csrc/lcn_dp.cu).  One process per GPU; rank 0 makes
+ * an id with lcn_dp_unique_id (128 bytes, ncclUniqueId) and hands it to the other ranks by any means (torch.distributed
+ * store, MPI, a file); every rank then calls lcn_dp_init -- a COLLECTIVE call that creates the model's NCCL communicator,
+ * communication stream and events.  Afterwards lcn_model_backward averages d_grads_raw over the ranks itself: each mid
+ * layer's weight gradient is all-reduced (ncclAvg, in place) right behind its weight-gradient GEMM, overlapped with the
+ * rest of the backward pass, the small tensors go out as one grouped launch at the end, and the caller's stream waits
+ * for the communication stream before the call's work is considered done -- so lcn_model_adam_step needs no change and
+ * the whole step is capturable as one CUDA graph.  BatchNorm statistics stay per GPU (== the reference at batch B per
+ * GPU).  lcn_dp_enable(m, 0) switches the exchange off for calls that want the local gradient (tests, the packed-bucket
+ * path above).  libnccl.so.2 is resolved with dlopen at the first call; LCN_ECUDA + message if it is missing. */
+int lcn_dp_unique_id(void* h_id128);
+int lcn_dp_init(lcn_model* m, const void* h_id128, int rank, int world);
+int lcn_dp_world(const lcn_model* m);
+int lcn_dp_enable(lcn_model* m, int on);
+
 /* (a10) ... or applies TF1 Adam directly from the raw gradients in one fused pass (models_att.py:404-409):
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (host scalar); theta -= lr_t*m/(sqrt(v)+eps).
  * `regularization` adds reg*theta to the gradient of w* / b* (models_att.py:362-365).  Also re-runs the
@@ -173,6 +204,44 @@ int lcn_layer_gemm(lcn_model* m, const float* d_params, void* d_ws, size_t ws_by
  *       4 = BN mean [groups,F], 5 = BN rstd [groups,F], 6 = dZ_l. */
 int lcn_model_read_tensor(lcn_model* m, void* d_ws, size_t ws_bytes, int kind, int layer,
                           int64_t n_rows, int32_t bn_group, float* d_dst, void* stream);
+
+/* Inverse of the kind-1 tap: d_src dense fp32 [groups*bn_group, 17*F] becomes the layer output A_layer of the
+ * training-layout workspace (the input of lcn_model_forward_layers(layer + 1, ...)). */
+int lcn_model_write_tensor(lcn_model* m, void* d_ws, size_t ws_bytes, int kind, int layer, int64_t n_rows,
+                           int32_t bn_group, const float* d_src, void* stream);
+
+/* ---- the reference's method-level layer API as stand-alone device ops (csrc/lcn_layers.cu) ---- */
+/* cgcnn.mask_weights(weights), models_att.py:576-586: d_out = reshape(d_w, [17,Fi,17,Fo]) * d_mask[17,1,17,1];
+ * d_w / d_out [rows, cols] with rows, cols multiples of 17; d_mask [17,17] = [in joint, out joint]. */
+int lcn_mask_weights(const float* d_w, int32_t rows, int32_t cols, const float* d_mask, float* d_out, void* stream);
+/* cgcnn.batch_normalization_warp(y, training, name), models_att.py:588-612: Keras BatchNormalization(axis=-1) on
+ * reshape(y, [-1, 17, F]) with BATCH statistics (every entry point of the reference passes
+ * training=True): per channel mean / biased variance over rows x 17, gamma (y - mean) / sqrt(var + eps) + beta.
+ * d_y / d_out [rows, 17*F]; d_stats [F][2] = (mean, variance), may be NULL. */
+int lcn_batch_norm(const float* d_y, int64_t rows, int32_t F, const float* d_gamma, const float* d_beta, float eps,
+                   float* d_out, float* d_stats, void* stream);
+/* base_model.loss, models_att.py:352-366: d_loss[0] = mean((pred - labels)^2) over n_elems (+ reg_scale * d_reg[0]
+ * when d_reg != NULL: the "reg_loss" term, :362-365). */
+int lcn_mse_loss(const float* d_pred, const float* d_labels, int64_t n_elems, const float* d_reg, float reg_scale,
+                 float* d_loss, void* stream);
+/* tf.add_n(self.regularizers), models_att.py:364,465-472: d_out[0] = sum over every w*, b* of sum(v^2)/2.
+ * d_scratch16: 16 bytes of device memory, zeroed once by the caller (the kernel leaves them zero). */
+int lcn_l2_regularizer(const lcn_model* m, const float* d_params, void* d_scratch16, float* d_out, void* stream);
+/* ExponentialMovingAverage(0.9).apply of the loss, run EVERY step by op_loss_average (models_att.py:210-212,370-379):
+ * d_ema[0] = decay * d_ema[0] + (1 - decay) * (d_loss[0] + reg_scale * d_reg[0]); d_ema[1] += 1.  The reader applies
+ * TF's zero-debias: loss_average = d_ema[0] / (1 - decay^d_ema[1]).  d_reg may be NULL. */
+int lcn_loss_ema(const float* d_loss, const float* d_reg, float reg_scale, float decay, float* d_ema, void* stream);
+
+/* ---- data path either side of the stack ---- */
+/* Batch gather of base_model.fit (train_data[idx], train_labels[idx], models_att.py:200) from device-resident sets:
+ * d_dst_a[b,:] = d_src_a[d_idx[b],:] and, when given, the same for the second row set.  Indices are clamped. */
+int lcn_gather_rows(const float* d_src_a, int32_t cols_a, float* d_dst_a, const float* d_src_b, int32_t cols_b,
+                    float* d_dst_b, const int64_t* d_idx, int64_t n_idx, int64_t n_src, void* stream);
+/* DataReader.read_2d / read_3d "scale" normalisation, tools/data.py:338-445: d_joint_3d_image [n,17,3] (pixels, mm),
+ * d_res [n,2] = (res_w, res_h) of each item's camera; d_x2d [n,34] = xy / res_w * 2 - [1, res_h / res_w] (may be
+ * NULL), d_y3d [n,51] = the same xy and z / res_w * 2 (may be NULL).  Inverse of lcn_denormalize. */
+int lcn_normalize(const float* d_joint_3d_image, const float* d_res, int64_t n, float* d_x2d, float* d_y3d,
+                  void* stream);
 
 /* Dropout keep decisions (1 = keep) exactly as the fused kernels draw them: Philox4x32-10 keyed on
  * seed, counter (element/8, layer, step), 16 random bits per element (u = bits/65536, rate rounded up to a
@@ -197,6 +266,13 @@ int lcn_dropout_mask(uint64_t seed, uint64_t step, int layer, int64_t rows, int3
 int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const float* d_box, const float* d_cam,
                    const float* d_root_depth, const int32_t* d_action, int32_t n_actions, int64_t n,
                    int flags, float* d_err, float* d_pose_out, double* d_sums, void* stream);
+
+/* tools.procrustes(A, B, scaling=True, reflection='best') -> (d, Z, tform), tools/tools.py:96-181, for n pose pairs:
+ * d_A / d_B [n,17,3] (A = target); reflection: 0 = 'best' (no determinant fix, what align_to_gt uses), 1 = False,
+ * 2 = True (:149-157).  d_Z [n,17,3] transformed B (may be NULL); d_tform [n,14] = rotation (9, row major),
+ * scale, translation (3), d (may be NULL). */
+int lcn_procrustes(const float* d_A, const float* d_B, int64_t n, int scaling, int reflection, float* d_Z,
+                   float* d_tform, void* stream);
 
 /* (f) DataReader.denormalize arithmetic, tools/data.py:471-472, fused in front of the evaluator:
  * d_pose [n,17,3] in place; d_res [n,2] = (res_w, res_h). */

@@ -28,6 +28,7 @@ _vp, _i32, _i64, _u64, _f, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C
 PROTOTYPES = {
     "lcn_version": (C.c_char_p, []),
     "lcn_last_error": (C.c_char_p, []),
+    "lcn_crc32c": (C.c_uint32, [_vp, _sz, C.c_uint32]),
     "lcn_neighbour_matrix": (C.c_int, [C.c_int, _vp]),
     "lcn_exponential_matrix": (C.c_int, [_vp]),
     "lcn_model_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_vp)]),
@@ -38,17 +39,31 @@ PROTOTYPES = {
     "lcn_model_workspace_bytes": (_sz, [_vp, _i64, _i32, C.c_int]),
     "lcn_model_prepare_weights": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "lcn_model_forward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, C.c_int, _f, _u64, _u64, _vp, _vp, _vp]),
+    "lcn_model_forward_layers": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, _f, _u64, _u64, C.c_int, C.c_int, _vp, _vp]),
+    "lcn_model_write_tensor": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _i64, _i32, _vp, _vp]),
+    "lcn_mask_weights": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "lcn_batch_norm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f, _vp, _vp, _vp]),
+    "lcn_mse_loss": (C.c_int, [_vp, _vp, _i64, _vp, _f, _vp, _vp]),
+    "lcn_l2_regularizer": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "lcn_loss_ema": (C.c_int, [_vp, _vp, _f, _f, _vp, _vp]),
+    "lcn_gather_rows": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _vp]),
+    "lcn_normalize": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "lcn_model_forward_taps": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "lcn_model_backward": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _i64, _f, _u64, _u64, _vp, _vp, _vp]),
     "lcn_model_finalize_grads": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "lcn_model_grad_compact_count": (_i64, [_vp]),
     "lcn_model_pack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lcn_model_unpack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "lcn_dp_unique_id": (C.c_int, [_vp]),
+    "lcn_dp_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "lcn_dp_world": (C.c_int, [_vp]),
+    "lcn_dp_enable": (C.c_int, [_vp, C.c_int]),
     "lcn_model_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _vp, _vp]),
     "lcn_layer_gemm": (C.c_int, [_vp, _vp, _vp, _sz, _i64, _i32, C.c_int, C.c_int, _vp]),
     "lcn_model_read_tensor": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _i64, _i32, _vp, _vp]),
     "lcn_dropout_mask": (C.c_int, [_u64, _u64, C.c_int, _i64, _i32, _f, _vp, _vp]),
     "lcn_eval_mpjpe": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp, _vp]),
+    "lcn_procrustes": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lcn_denormalize": (C.c_int, [_vp, _vp, _i64, _vp]),
     "lcn_augment": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _f, _f, _vp]),
     "lcn_tta_undo": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f, _f, _vp]),

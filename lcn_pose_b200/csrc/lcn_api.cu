@@ -68,6 +68,38 @@ extern "C" int lcn_exponential_matrix(float* h_out) {
   return LCN_OK;
 }
 
+// ---- CRC32C (Castagnoli) of host memory: the checksum of TensorBundle checkpoints (tools/tf_checkpoint.py) ----
+// slicing-by-8; tables built once (thread safe: function-local static initialisation)
+struct Crc32cTables {
+  uint32_t t[8][256];
+  Crc32cTables() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      t[0][i] = c;
+    }
+    for (int k = 1; k < 8; ++k)
+      for (uint32_t i = 0; i < 256; ++i) t[k][i] = (t[k - 1][i] >> 8) ^ t[0][t[k - 1][i] & 0xFFu];
+  }
+};
+extern "C" uint32_t lcn_crc32c(const void* h_data, size_t n, uint32_t crc) {
+  static const Crc32cTables T;
+  const uint8_t* p = static_cast<const uint8_t*>(h_data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = T.t[7][lo & 0xFF] ^ T.t[6][(lo >> 8) & 0xFF] ^ T.t[5][(lo >> 16) & 0xFF] ^ T.t[4][lo >> 24] ^
+        T.t[3][hi & 0xFF] ^ T.t[2][(hi >> 8) & 0xFF] ^ T.t[1][(hi >> 16) & 0xFF] ^ T.t[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = T.t[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
 // ---- model -------------------------------------------------------------------------------------
 static int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 
@@ -194,6 +226,7 @@ extern "C" int lcn_model_create(const lcn_model_desc* desc, lcn_model** out) {
 
 extern "C" void lcn_model_destroy(lcn_model* m) {
   if (m == nullptr) return;
+  lcn_dp_destroy(m);
   if (m->aux.ready) {
     cudaStreamDestroy(m->aux.st);
     cudaEventDestroy(m->aux.ev_go);
@@ -307,12 +340,11 @@ extern "C" int lcn_model_prepare_weights(lcn_model* m, const float* d_params, vo
 }
 
 bool lcn_pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  static const bool v = [] {                       // profiling switch; function-local static: initialised once, thread safe
     const char* e = getenv("LCN_DISABLE_PDL");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
+    return !(e && e[0] == '1');
+  }();
+  return v;
 }
 
 // ---- LCN_TRACE: per-kernel in-stream durations (debug) ----
@@ -324,12 +356,11 @@ std::vector<TraceRec> g_trace;
 std::mutex g_trace_mu;
 }
 bool lcn_trace_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  static const bool v = [] {
     const char* e = getenv("LCN_TRACE");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
+    return e && e[0] == '1';
+  }();
+  return v;
 }
 void lcn_trace_mark(const void* func, cudaStream_t st, int end) {
   std::lock_guard<std::mutex> lock(g_trace_mu);
@@ -396,6 +427,52 @@ extern "C" int lcn_model_forward(lcn_model* m, const float* d_params, void* d_ws
   a.dyn = d_dyn;
   a.st = (cudaStream_t)stream;
   return lcn_launch_forward(a);
+}
+
+extern "C" int lcn_model_forward_layers(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,
+                                        int64_t n_rows, int32_t bn_group, float dropout_rate, uint64_t seed, uint64_t step,
+                                        int layer_begin, int layer_end, float* d_out, void* stream) {
+  int rc = check_geom(m, n_rows, bn_group);
+  if (rc) return rc;
+  LCN_REQUIRE(d_params && d_ws, "null argument");
+  LCN_REQUIRE(layer_begin >= 0 && layer_begin < layer_end && layer_end <= m->n_lin, "layer range [%d, %d) outside [0, %d)",
+              layer_begin, layer_end, m->n_lin);
+  LCN_REQUIRE(d_x != nullptr || (layer_begin > 0 && layer_end < m->n_lin), "the first and the last layer read d_x");
+  LCN_REQUIRE(d_out != nullptr || layer_end < m->n_lin, "the last layer writes d_out");
+  LCN_REQUIRE(dropout_rate >= 0.f && dropout_rate < 1.f, "dropout rate %f outside [0,1)", dropout_rate);
+  FwdArgs a;
+  a.m = m;
+  a.params = d_params;
+  a.ws = (char*)d_ws;
+  a.lay = lcn_ws_layout(m, n_rows, bn_group, 1);     // training layout: every Z_l / A_l has its own buffer
+  if (ws_bytes < a.lay.total) {
+    lcn_set_error("workspace too small: %zu < %zu", ws_bytes, a.lay.total);
+    return LCN_ENOMEM;
+  }
+  a.x = d_x;
+  a.out = d_out;
+  a.dropout_rate = dropout_rate;
+  a.seed = seed;
+  a.step = step;
+  a.dyn = nullptr;
+  a.st = (cudaStream_t)stream;
+  a.layer_begin = layer_begin;
+  a.layer_end = layer_end;
+  return lcn_launch_forward(a);
+}
+
+extern "C" int lcn_model_write_tensor(lcn_model* m, void* d_ws, size_t ws_bytes, int kind, int layer, int64_t n_rows,
+                                      int32_t bn_group, const float* d_src, void* stream) {
+  int rc = check_geom(m, n_rows, bn_group);
+  if (rc) return rc;
+  LCN_REQUIRE(d_ws && d_src, "null argument");
+  LCN_REQUIRE(kind == 1, "only kind 1 (layer output A_l) can be injected");
+  WsLayout lay = lcn_ws_layout(m, n_rows, bn_group, 1);
+  if (ws_bytes < lay.total) {
+    lcn_set_error("workspace too small: %zu < %zu", ws_bytes, lay.total);
+    return LCN_ENOMEM;
+  }
+  return lcn_launch_write_tensor(m, (char*)d_ws, lay, layer, d_src, (cudaStream_t)stream);
 }
 
 extern "C" int lcn_model_forward_taps(lcn_model* m, const float* d_params, void* d_ws, size_t ws_bytes, const float* d_x,

@@ -343,12 +343,13 @@ extern "C" int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const floa
   if (d_action == nullptr) n_actions = 0;
   const int bufs = (flags & 1) ? 1 : 2;
   size_t smem = (size_t)EV_WARPS * bufs * 2 * 32 * EV_POSE * sizeof(float) + (size_t)n_actions * 19 * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr = true;
-  }
+  static std::once_flag once;            // thread-safe one-time attribute setup (include/lcn_b200.h: re-entrancy)
+  static cudaError_t once_rc = cudaSuccess;
+  std::call_once(once, [] {
+    once_rc = cudaFuncSetAttribute(k_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (once_rc == cudaSuccess) once_rc = cudaFuncSetAttribute(k_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  });
+  LCN_CHECK_CUDA(once_rc);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t chunks = (n + 31) / 32;
@@ -360,6 +361,111 @@ extern "C" int lcn_eval_mpjpe(const float* d_pred, const float* d_gt, const floa
   else
     k_eval<2><<<grid, EV_WARPS * 32, smem, (cudaStream_t)stream>>>(d_pred, d_gt, d_box, d_cam, d_root_depth, d_action,
                                                                  n_actions, n, flags, d_err, d_pose_out, d_sums);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+// tools.procrustes(A, B, scaling, reflection) in full (tools/tools.py:96-181): one thread per pose pair, every option
+// of the reference's signature, and the (d, Z, tform) triple it returns.  The evaluator above inlines the
+// scaling=True / reflection='best' case that evaluate.py uses; this entry serves direct callers of tools.procrustes.
+// flags: bit 0 = scaling, bits 1-2 = reflection (0 'best', 1 force none, 2 force one).
+__global__ void __launch_bounds__(128) k_procrustes(const float* __restrict__ A, const float* __restrict__ B, int64_t n,
+                                                    int flags, float* __restrict__ Z, float* __restrict__ tform) {
+  const int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= n) return;
+  const float* a = A + ip * EV_POSE;
+  const float* b = B + ip * EV_POSE;
+  const int scaling = flags & 1, refl = (flags >> 1) & 3;
+  float ab[3] = {0, 0, 0}, bb[3] = {0, 0, 0};
+  for (int j = 0; j < LCN_J; ++j)
+    for (int c = 0; c < 3; ++c) {
+      ab[c] += a[j * 3 + c] - a[c];                          // relative to joint 0: keeps fp32 accuracy at ~1e3-1e4 mm
+      bb[c] += b[j * 3 + c] - b[c];
+    }
+  for (int c = 0; c < 3; ++c) {
+    ab[c] = ab[c] * (1.0f / LCN_J) + a[c];                   // A_bar, B_bar (tools.py:127-128)
+    bb[c] = bb[c] * (1.0f / LCN_J) + b[c];
+  }
+  float ssX = 0.f, ssY = 0.f, M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < LCN_J; ++j) {
+    float x[3], y[3];
+    for (int c = 0; c < 3; ++c) {
+      x[c] = a[j * 3 + c] - ab[c];
+      y[c] = b[j * 3 + c] - bb[c];
+      ssX = fmaf(x[c], x[c], ssX);
+      ssY = fmaf(y[c], y[c], ssY);
+    }
+    for (int p = 0; p < 3; ++p)
+      for (int q = 0; q < 3; ++q) M[p][q] = fmaf(x[p], y[q], M[p][q]);   // A0^T B0 (tools.py:144)
+  }
+  const float nA = sqrtf(ssX), nB = sqrtf(ssY), inv_ab = 1.0f / (nA * nB);
+  float g[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};          // g[s] = column s of M, v[s] = column s of V
+  for (int s2 = 0; s2 < 3; ++s2)
+    for (int p = 0; p < 3; ++p) g[s2][p] = M[p][s2] * inv_ab;
+  for (int sweep = 0; sweep < 8; ++sweep) {
+    bool r = jacobi_rot(g[0], g[1], v[0], v[1]);
+    r |= jacobi_rot(g[0], g[2], v[0], v[2]);
+    r |= jacobi_rot(g[1], g[2], v[1], v[2]);
+    if (!r) break;
+  }
+  float sv[3], inv[3];
+  for (int s2 = 0; s2 < 3; ++s2) {
+    sv[s2] = sqrtf(g[s2][0] * g[s2][0] + g[s2][1] * g[s2][1] + g[s2][2] * g[s2][2]);
+    inv[s2] = sv[s2] > 1e-20f ? 1.f / sv[s2] : 0.f;
+  }
+  float R[3][3];
+  auto make_R = [&]() {
+    for (int p = 0; p < 3; ++p)
+      for (int c = 0; c < 3; ++c)
+        R[p][c] = v[0][p] * g[0][c] * inv[0] + v[1][p] * g[1][c] * inv[1] + v[2][p] * g[2][c] * inv[2];   // V U^T (:146-147)
+  };
+  make_R();
+  if (refl != 0) {                                           // tools.py:149-157
+    const float det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                      R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    const bool have = det < 0.f, want = refl == 2;
+    if (have != want) {
+      int last = 0;                                          // numpy's svd sorts descending: "[-1]" is the smallest
+      if (sv[1] < sv[last]) last = 1;
+      if (sv[2] < sv[last]) last = 2;
+      for (int p = 0; p < 3; ++p) v[last][p] = -v[last][p];
+      make_R();
+      sv[last] = -sv[last];
+    }
+  }
+  const float tr = sv[0] + sv[1] + sv[2];
+  float scale, d, zs;
+  if (scaling) {
+    scale = tr * nA / nB;                                    // :161
+    d = 1.f - tr * tr;                                       // :164
+    zs = nA * tr / nB;                                       // Z = A_norm * S_trace * (B0 / B_norm) R + A_bar (:167)
+  } else {
+    scale = 1.f;
+    d = 1.f + ssY / ssX - 2.f * tr * nB / nA;                // :170
+    zs = 1.f;                                                // Z = B_norm * (B0 / B_norm) R + A_bar (:171)
+  }
+  if (Z != nullptr)
+    for (int j = 0; j < LCN_J; ++j) {
+      float y[3];
+      for (int c = 0; c < 3; ++c) y[c] = b[j * 3 + c] - bb[c];
+      for (int c = 0; c < 3; ++c) Z[ip * EV_POSE + j * 3 + c] = zs * (y[0] * R[0][c] + y[1] * R[1][c] + y[2] * R[2][c]) + ab[c];
+    }
+  if (tform != nullptr) {
+    float* t = tform + ip * 14;
+    for (int p = 0; p < 3; ++p)
+      for (int c = 0; c < 3; ++c) t[p * 3 + c] = R[p][c];
+    t[9] = scale;
+    for (int c = 0; c < 3; ++c) t[10 + c] = ab[c] - scale * (bb[0] * R[0][c] + bb[1] * R[1][c] + bb[2] * R[2][c]);   // :176
+    t[13] = d;
+  }
+}
+extern "C" int lcn_procrustes(const float* d_A, const float* d_B, int64_t n, int scaling, int reflection, float* d_Z,
+                              float* d_tform, void* stream) {
+  LCN_REQUIRE(d_A && d_B && (d_Z || d_tform), "null argument");
+  LCN_REQUIRE(n > 0, "n must be positive");
+  LCN_REQUIRE(reflection >= 0 && reflection <= 2, "reflection: 0 = 'best', 1 = False, 2 = True");
+  const int flags = (scaling ? 1 : 0) | (reflection << 1);
+  k_procrustes<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_A, d_B, n, flags, d_Z, d_tform);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }

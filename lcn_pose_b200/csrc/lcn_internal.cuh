@@ -75,8 +75,11 @@ struct LcnAux {
   cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
 };
 
+struct LcnDp;                      // data-parallel communicator + stream + events (lcn_dp.cu); null: single process
+
 struct lcn_model {
   mutable LcnAux aux;
+  LcnDp* dp = nullptr;
   lcn_model_desc d;
   int n_lin, n_bn, P, FC, nnz;
   JointLists by_out, by_in;
@@ -239,6 +242,14 @@ static inline void lcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     }                            \
   } while (0)
 
+// ---- data-parallel exchange (lcn_dp.cu) ----
+bool lcn_dp_active(const lcn_model* m);
+int lcn_dp_allreduce_after(const lcn_model* m, cudaStream_t producer, float* buf, size_t count);
+int lcn_dp_allreduce_group_after(const lcn_model* m, cudaStream_t producer, float* base, const int64_t* offs,
+                                 const int64_t* counts, int n);
+int lcn_dp_join(const lcn_model* m, cudaStream_t consumer);
+void lcn_dp_destroy(lcn_model* m);
+
 // ---- launch wrappers implemented in the kernel translation units ----
 struct FwdArgs {                 // one call of the forward pass
   const lcn_model* m;
@@ -251,6 +262,7 @@ struct FwdArgs {                 // one call of the forward pass
   uint64_t seed, step;
   const lcn_step_scalars* dyn;   // device-resident step scalars (overrides `step` when not null)
   cudaStream_t st;
+  int layer_begin = 0, layer_end = -1;   // linear layers [begin, end) to run; end < 0: all (lcn_model_forward_layers)
 };
 
 int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const WsLayout& lay,
@@ -270,6 +282,8 @@ int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, con
                           int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,
                            float* dst, cudaStream_t st);
+int lcn_launch_write_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int layer, const float* src,
+                            cudaStream_t st);
 
 // BatchNorm statistics of the forward tensor-core GEMM without a second launch (one BatchNorm group): every CTA adds
 // its per-channel (sum x, sum x^2) to fp64 accumulators (LCN_GACC_REP replicas indexed by row tile spread the atomics),

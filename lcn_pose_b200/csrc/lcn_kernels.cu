@@ -206,14 +206,9 @@ __global__ void k_pack_first16(const float* __restrict__ wm_first, int Kin, int 
   }
 }
 
-// side stream + events of the model (LcnAux); nullptr when disabled (LCN_DISABLE_AUX_STREAM=1) or creation failed
+// side stream + events of the model (LcnAux), created on first use under aux.mu (held by the caller); nullptr when
+// the creation failed -- the callers then enqueue everything on the caller's stream
 static LcnAux* lcn_aux_get(const lcn_model* m) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("LCN_DISABLE_AUX_STREAM");
-    enabled = (e && e[0] == '1') ? 0 : 1;
-  }
-  if (!enabled) return nullptr;
   LcnAux& a = m->aux;
   if (a.failed) return nullptr;
   if (!a.ready) {
@@ -246,7 +241,7 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
   LCN_CHECK_LAUNCH();
   int last = m->n_lin - 1;
   int n_mid = m->n_lin - 2;
-  const bool use_tc = m->d.path == LCN_PATH_BF16 && lcn_tc_enabled();
+  const bool use_tc = m->d.path == LCN_PATH_BF16;
   // the edge-layer packs (four small dependent launches) run on the model's side stream next to the mid-layer pack
   std::unique_lock<std::mutex> aux_lock;
   LcnAux* ax = nullptr;
@@ -1172,168 +1167,6 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_apply(const T* __restrict
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_bn_bwd_reduce + k_bn_bwd_apply in ONE persistent launch (bf16 path, <= BF_R rows per thread): every block
-// stages its rows of dOut / Z (raw bf16, 16 B per thread and row) and the keep bytes in shared memory, reduces the
-// per-channel sums, meets the other blocks at a grid barrier (all 2 x SMs blocks are co-resident: checked by the
-// host with the occupancy API), then applies from the staged copy.  Saves one launch and one full read pass of
-// dOut and Z per BatchNorm layer.  `counter` is zeroed by the memset that clears `sums`.  Measured per launch at
-// B=4096 (cycles): stage + reduce 16 k, grid barrier 5-6 k, apply 10 k; train step 0.820 -> 0.807 ms.
-// ------------------------------------------------------------------------------------------------
-#define BF_R 8
-__global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_fused(const __nv_bfloat16* __restrict__ dOut,
-                                                             const __nv_bfloat16* __restrict__ Z,
-                                                             const uint8_t* __restrict__ keepbits,
-                                                             const float* __restrict__ stat,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float* sums,
-                                                             unsigned* counter, __nv_bfloat16* __restrict__ dZ,
-                                                             float* __restrict__ dbpart, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, int P, int F, int rows_pad,
-                                                             int bn_group, float rate) {
-  lcn_pdl_prologue();
-  extern __shared__ __align__(16) uint8_t fsm[];
-  __shared__ __align__(16) float s_a[256], s_b[256], s_c[256], s_d[256];
-  const int Y = blockDim.y, nt = blockDim.x, c8 = threadIdx.x * 8, f0 = c8 % F;
-  const int tid = threadIdx.y * nt + threadIdx.x, T = nt * Y;
-  uint4* sz = reinterpret_cast<uint4*>(fsm);                 // [BF_R][T]
-  uint4* sd = sz + BF_R * T;                                 // [BF_R][T]
-  float* red = reinterpret_cast<float*>(sd + BF_R * T);      // max([T][16], [Y-1][P]) floats
-  BnConsts k;
-  bn_load_consts(stat, gamma, beta, F, f0, s_a, s_b, s_c, s_d, k);
-  const float inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
-  const int stride = gridDim.x * Y;
-  const int r0 = blockIdx.x * Y + threadIdx.y;
-  uint32_t kb[BF_R];
-  // ---- stage + reduce ----
-#pragma unroll
-  for (int i = 0; i < BF_R; ++i) {
-    const int r = r0 + i * stride;
-    kb[i] = 0xffu;
-    if (r < bn_group) {
-      const size_t o = lcn_off<__nv_bfloat16>(r, c8, P);
-      sz[i * T + tid] = *reinterpret_cast<const uint4*>(Z + o);
-      sd[i * T + tid] = *reinterpret_cast<const uint4*>(dOut + o);
-      if (rate > 0.f) kb[i] = keepbits[(size_t)r * (P >> 3) + threadIdx.x];
-    }
-  }
-  auto unpack = [](const uint4& u, float v[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 t = __bfloat1622float2(h[e]);
-      v[2 * e] = t.x;
-      v[2 * e + 1] = t.y;
-    }
-  };
-  float s1[8], s2[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) s1[q] = s2[q] = 0.f;
-#pragma unroll
-  for (int i = 0; i < BF_R; ++i) {
-    const int r = r0 + i * stride;
-    if (r < bn_group) {
-      float zc[8], dc[8], dy[8], xh[8];
-      unpack(sz[i * T + tid], zc);
-      unpack(sd[i * T + tid], dc);
-      bn_bwd_dy8(zc, dc, kb[i], k, inv_keep, dy, xh);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        s1[q] += dy[q];
-        s2[q] = fmaf(dy[q], xh[q], s2[q]);
-      }
-    }
-  }
-  {
-    float* mine = red + (size_t)tid * 16;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      mine[q] = s1[q];
-      mine[8 + q] = s2[q];
-    }
-    __syncthreads();
-    const int per = F / 8;                         // threads (x) per joint
-    if (tid < per * 16) {                          // one thread per (channel octet, value)
-      int oct = tid / 16, v = tid % 16;
-      float a = 0.f;
-      for (int y = 0; y < Y; ++y)
-        for (int j = 0; j < LCN_J; ++j) a += red[((size_t)y * nt + oct + j * per) * 16 + v];
-      atomicAdd(&sums[(oct * 8 + (v & 7)) * 2 + (v >> 3)], a);
-    }
-  }
-  // ---- grid barrier ----
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    unsigned seen = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < gridDim.x);
-    __threadfence();
-  }
-  __syncthreads();
-  // ---- apply ----
-  // the 2F sums come from L2 once per block (one thread per value, L1 bypassed: they were written by atomics of
-  // other SMs) and are shared through s_a; every thread of the grid reading them with ld.cg serialises on four
-  // L2 lines (measured: 45 k cycles)
-  if (tid < 2 * F) s_a[tid] = __ldcg(&sums[tid]);
-  __syncthreads();
-  float m1[8], m2[8];
-  const float inv_n = 1.f / ((float)bn_group * (float)LCN_J);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    m1[q] = s_a[(f0 + q) * 2] * inv_n;
-    m2[q] = s_a[(f0 + q) * 2 + 1] * inv_n;
-  }
-  if (blockIdx.x == 0 && threadIdx.y == 0 && (int)threadIdx.x < F / 8) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      dbeta[f0 + q] = s_a[(f0 + q) * 2];
-      dgamma[f0 + q] = s_a[(f0 + q) * 2 + 1];
-    }
-  }
-  float bsum[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) bsum[q] = 0.f;
-#pragma unroll
-  for (int i = 0; i < BF_R; ++i) {
-    const int r = r0 + i * stride;
-    if (r < rows_pad) {
-      float dz[8];
-      if (r >= bn_group) {                          // tile padding rows: dZ must be zero (wgrad reduces over rows)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dz[q] = 0.f;
-      } else {
-        float zc[8], dc[8], dy[8], xh[8];
-        unpack(sz[i * T + tid], zc);
-        unpack(sd[i * T + tid], dc);
-        bn_bwd_dy8(zc, dc, kb[i], k, inv_keep, dy, xh);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          dz[q] = k.sc[q] * (dy[q] - m1[q] - xh[q] * m2[q]);
-          bsum[q] += dz[q];
-        }
-      }
-      lcn_st8(dZ, lcn_off<__nv_bfloat16>(r, c8, P), dz);
-    }
-  }
-  __syncthreads();                                 // `red` is reused below
-  if (threadIdx.y > 0) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) red[(size_t)(threadIdx.y - 1) * P + c8 + q] = bsum[q];
-  }
-  __syncthreads();
-  if (threadIdx.y == 0) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float a = bsum[q];
-      for (int y = 1; y < Y; ++y) a += red[(size_t)(y - 1) * P + c8 + q];
-      dbpart[(size_t)blockIdx.x * P + c8 + q] = a;
-    }
-  }
-}
-
 // db[l][col] = sum over the per-block partial rows written by k_bn_bwd_apply.  grid (ceil(P/64), n_bn), 256 threads
 __global__ void __launch_bounds__(256) k_db_reduce(const float* __restrict__ dbpart, int nblocks, int P,
                                                    float* __restrict__ graw, LinTable lt_b /* w_off holds b_off */) {
@@ -1742,15 +1575,16 @@ static int forward_impl(const FwdArgs& a) {
   const int P = m->P, F = m->d.F, FC = m->FC;
   RowGeom g{lay.n_rows, lay.bn_group, lay.gstride};
   float* part = reinterpret_cast<float*>(ws + lay.off_part);
-  const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  const bool tc = sizeof(T) == 2;
   size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_simt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_simt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_last_layer<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-    attr_done = true;
-  }
+  static std::once_flag attr_once;                 // one per instantiation; thread safe (header: re-entrancy)
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(attr_once, [&] {
+    attr_rc = cudaFuncSetAttribute(k_gemm_simt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+    if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(k_gemm_simt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+    if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(k_last_layer<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  });
+  LCN_CHECK_CUDA(attr_rc);
   int n_bn = m->n_bn;
   // training at one BatchNorm group on the tensor-core path: the mid-layer GEMMs accumulate the BatchNorm statistics
   // themselves (TcFuse, lcn_gemm_tc.cu) and k_bn_act_pre finalises them; the accumulators are cleared here, once per pass
@@ -1759,11 +1593,12 @@ static int forward_impl(const FwdArgs& a) {
     const int ewy0 = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
     const int grid0 = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy0);
     const int per0 = (int)(((lay.rows_pad / ewy0 + grid0 - 1) / grid0) * ewy0);
-    pre_ok = lay.n_groups == 1 && per0 <= BA_R * ewy0 && !getenv("LCN_DISABLE_BNACT_PRE");
+    pre_ok = lay.n_groups == 1 && per0 <= BA_R * ewy0;
   }
   const bool try_fuse = tc && lay.training && lay.n_groups == 1 && pre_ok;
   if (try_fuse) LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_gacc, 0, lay.gacc_stride * (size_t)n_bn, st));
-  for (int l = 0; l < n_bn; ++l) {
+  const int lb = a.layer_begin, le = a.layer_end < 0 ? m->n_lin : a.layer_end;   // linear layers [lb, le)
+  for (int l = lb; l < n_bn && l < le; ++l) {
     const LayerInfo& L = m->L[l];
     T* Z = reinterpret_cast<T*>(z_buf(ws, lay, l));
     T* Aout = reinterpret_cast<T*>(a_buf(ws, lay, l));
@@ -1772,12 +1607,7 @@ static int forward_impl(const FwdArgs& a) {
       dim3 grid(lay.tiles, P / 64);
       const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
       __nv_bfloat16* x16 = (tc && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
-      static int stats_on = -1;
-      if (stats_on < 0) {
-        const char* e = getenv("LCN_FUSED_BNSTATS");
-        stats_on = (e && e[0] == '0') ? 0 : 1;
-      }
-      double* gacc0 = (try_fuse && stats_on) ? reinterpret_cast<double*>(ws + lay.off_gacc) : nullptr;
+      double* gacc0 = try_fuse ? reinterpret_cast<double*>(ws + lay.off_gacc) : nullptr;
       fused_bn = gacc0 != nullptr;
       switch (m->d.in_F) {
         case 2: lcn_launch(k_first_layer<T, 2>, dim3(grid), dim3(256), 0, st, a.x, g, wm, a.params + L.b_off, Z, part, P, x16, gacc0, F, m->sup); break;
@@ -1818,7 +1648,7 @@ static int forward_impl(const FwdArgs& a) {
     if constexpr (sizeof(T) == 2) {
       // one BN group, <= BA_R rows per thread: all loads up front (k_bn_act_pre)
       const int per = (int)(((lay.rows_pad / ewy + ew_grid - 1) / ew_grid) * ewy);
-      if (lay.n_groups == 1 && per <= BA_R * ewy && !getenv("LCN_DISABLE_BNACT_PRE")) {
+      if (lay.n_groups == 1 && per <= BA_R * ewy) {
         pre = true;
         lcn_launch(k_bn_act_pre, dim3(ew_grid), dim3(P / 8, ewy), 0, st, reinterpret_cast<const __nv_bfloat16*>(Z), stat,
                    a.params + L.gamma_off, a.params + L.beta_off, reinterpret_cast<const __nv_bfloat16*>(res),
@@ -1837,6 +1667,7 @@ static int forward_impl(const FwdArgs& a) {
     LCN_CHECK_LAUNCH();
   }
   int last = m->n_lin - 1;
+  if (le <= last) return LCN_OK;
   const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, n_bn - 1));
   float* out_ws = lay.training ? reinterpret_cast<float*>(ws + lay.off_out) : nullptr;
   if (tc) {
@@ -1862,7 +1693,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
                          const float* labels, float rate, uint64_t seed, uint64_t step, float* loss,
                          float* graw, cudaStream_t st) {
   const int P = m->P, F = m->d.F, FC = m->FC;
-  const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  const bool tc = sizeof(T) == 2;
   // weight-gradient GEMMs go to the model's side stream (see LcnAux); `wst` is the stream they are enqueued on
   std::unique_lock<std::mutex> aux_lock;
   LcnAux* ax = nullptr;
@@ -1872,6 +1703,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     if (ax == nullptr) aux_lock.unlock();
   }
   cudaStream_t wst = ax ? ax->st : st;
+  const bool dp = lcn_dp_active(m);
   bool wg_pending[2] = {false, false};
   size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
   const int64_t blast = m->L[m->n_lin - 1].b_off;     // last-layer bias gradient: accumulated by k_loss_dout (caller's stream)
@@ -1932,36 +1764,6 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   const int ewy = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
   unsigned eg = (unsigned)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
   size_t red_smem = (size_t)ewy * (P / 8) * 16 * sizeof(float);
-  // fused reduce+apply (one launch, grid barrier): bf16 path, <= BF_R rows per thread, all blocks co-resident
-  const int ew_threads = (P / 8) * ewy;
-  const size_t fused_red = std::max((size_t)ew_threads * 16, (size_t)(ewy - 1) * P) * sizeof(float);
-  const size_t fused_smem = (size_t)2 * BF_R * ew_threads * sizeof(uint4) + fused_red;
-  bool fused_bwd = false;
-  if (sizeof(T) == 2 && (int64_t)BF_R * eg * ewy >= lay.rows_pad && eg == (unsigned)(2 * m->sm_count)) {
-    static int ok = -1;                   // co-residency of 2 blocks per SM at this shared-memory size
-    static size_t ok_smem = 0;
-    if (ok < 0 || ok_smem != fused_smem) {
-      int per_sm = 0;
-      if (cudaFuncSetAttribute(k_bn_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem) == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bn_bwd_fused, ew_threads, fused_smem) == cudaSuccess)
-        ok = per_sm >= 2 ? 1 : 0;
-      else
-        ok = 0;
-      (void)cudaGetLastError();
-      ok_smem = fused_smem;
-      const char* e = getenv("LCN_DISABLE_FUSED_BNBWD");
-      if (e && e[0] == '1') ok = 0;
-    }
-    // With the weight gradients on the side stream the grid-barrier kernel is the slower choice: it cannot start
-    // before the weight-gradient CTAs of the previous layer have drained (all of its blocks must be resident), while the
-    // two plain launches interleave with them (0.577 against 0.583 ms per step).  LCN_FORCE_FUSED_BNBWD=1 keeps it.
-    static int force = -1;
-    if (force < 0) {
-      const char* e = getenv("LCN_FORCE_FUSED_BNBWD");
-      force = (e && e[0] == '1') ? 1 : 0;
-    }
-    fused_bwd = ok == 1 && (ax == nullptr || force == 1);
-  }
   PairTable pt = make_pairs(m);
   if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_ms, 0));   // the bucket is clear before this stream stores into it
   for (int l = m->n_bn - 1; l >= 0; --l) {
@@ -1975,16 +1777,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
       LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_wg[l & 1], 0));
       wg_pending[l & 1] = false;
     }
-    if (fused_bwd) {
-      if constexpr (sizeof(T) == 2) {
-        unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(ws + lay.off_bnsum) + (size_t)m->n_bn * F * 2) + l;
-        lcn_launch(k_bn_bwd_fused, dim3(eg), dim3(P / 8, ewy), fused_smem, st, reinterpret_cast<const __nv_bfloat16*>(D(cur)),
-                   reinterpret_cast<const __nv_bfloat16*>(Z), keepbits, stat, params + L.gamma_off, params + L.beta_off, sums,
-                   counter, reinterpret_cast<__nv_bfloat16*>(dZ),
-                   reinterpret_cast<float*>(ws + lay.off_dbpart) + (size_t)l * eg * P, graw + L.gamma_off, graw + L.beta_off, P,
-                   F, (int)lay.rows_pad, lay.bn_group, rate);
-      }
-    } else {
+    {
       lcn_launch(k_bn_bwd_reduce<T>, dim3(eg), dim3(dim3(P / 8, ewy)), red_smem, st, D(cur), Z, keepbits, stat, params + L.gamma_off,
                                                                params + L.beta_off, sums, P, F, lay.bn_group, rate);
       lcn_launch(k_bn_bwd_apply<T>, dim3(eg), dim3(dim3(P / 8, ewy)), (size_t)ewy * P * sizeof(float), st, 
@@ -2030,6 +1823,12 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
         LCN_CHECK_CUDA(cudaEventRecord(ax->ev_wg[l & 1], wst));
         wg_pending[l & 1] = true;
       }
+      // data parallel: this layer's weight gradient is final -> average it over the ranks now, behind the wgrad GEMM,
+      // while the layers below are still being differentiated (lcn_dp.cu)
+      if (dp) {
+        int rc2 = lcn_dp_allreduce_after(m, wst, graw + L.w_off, (size_t)L.Kin * L.Kout);
+        if (rc2) return rc2;
+      }
       const char* wp = ws + lay.off_wp16b + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
       rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), wp, nullptr,
                        reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(D(nxt)),
@@ -2038,6 +1837,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     } else {
       lcn_launch(k_wgrad_simt<T>, dim3(dim3(m->nnz * FC * FC, (unsigned)(lay.rows_pad / rows_blk))), dim3(256), 0, st, 
           Ain, dZ, graw + L.w_off, pt, P, FC, rows_blk);
+      if (dp) {
+        int rc2 = lcn_dp_allreduce_after(m, st, graw + L.w_off, (size_t)L.Kin * L.Kout);
+        if (rc2) return rc2;
+      }
       const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
       lcn_launch(k_gemm_simt<T, true>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
           dZ, wp, nullptr, addend, D(nxt), nullptr, m->by_in, P, FC, lay.bn_group, lay.gstride);
@@ -2058,6 +1861,27 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, wst));
     LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   }
+  if (dp) {
+    // what only completes with the last kernels of the pass -- edge-layer weights (contiguous with their biases), the
+    // mid layers' biases, every BatchNorm gamma / beta (one contiguous tail of the parameter layout) -- travels as one
+    // grouped launch; then the caller's stream joins the communication stream: the bucket holds the ranks' average
+    int64_t offs[LCN_MAX_LIN + 1], cnts[LCN_MAX_LIN + 1];
+    int nr = 0;
+    for (int l = 0; l < m->n_lin; ++l) {
+      const LayerInfo& L = m->L[l];
+      const bool edge = l == 0 || l == m->n_lin - 1;
+      offs[nr] = edge ? L.w_off : L.b_off;
+      cnts[nr] = (edge ? (L.b_off - L.w_off) : 0) + L.Kout;
+      ++nr;
+    }
+    offs[nr] = m->L[0].gamma_off;
+    cnts[nr] = m->n_params - m->L[0].gamma_off;
+    ++nr;
+    int rc2 = lcn_dp_allreduce_group_after(m, st, graw, offs, cnts, nr);
+    if (rc2) return rc2;
+    rc2 = lcn_dp_join(m, st);
+    if (rc2) return rc2;
+  }
   return LCN_OK;
 }
 
@@ -2073,7 +1897,7 @@ template <typename T>
 static int layer_gemm_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int l,
                            int transposed, cudaStream_t st) {
   const int P = m->P, FC = m->FC;
-  const bool tc = (sizeof(T) == 2) && lcn_tc_enabled();
+  const bool tc = sizeof(T) == 2;
   size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
   float* part = reinterpret_cast<float*>(ws + lay.off_part);
   const T* Ain = reinterpret_cast<const T*>(transposed ? ws + lay.off_dz : a_buf(ws, lay, l - 1));
@@ -2115,6 +1939,33 @@ __global__ void k_read_rows(const T* __restrict__ src, float* __restrict__ dst, 
     dst[e] = lcn_ld(src, lcn_off<T>(pr, c, P));
   }
 }
+// inverse of k_read_rows: dense fp32 rows -> the activation layout of the path (padding rows of a group stay untouched)
+template <typename T>
+__global__ void k_write_rows(const float* __restrict__ src, T* __restrict__ dst, int64_t n_logical, int P, int bn_group,
+                             int gstride) {
+  lcn_pdl_prologue();
+  int64_t n = n_logical * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lr = e / P;
+    int c = (int)(e - lr * P);
+    int64_t pr = (lr / bn_group) * gstride + lr % bn_group;
+    lcn_st(dst, lcn_off<T>(pr, c, P), src[e]);
+  }
+}
+int lcn_launch_write_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int layer, const float* src,
+                            cudaStream_t st) {
+  LCN_REQUIRE(lay.training, "activation injection needs a training-mode workspace layout");
+  LCN_REQUIRE(layer >= 0 && layer < m->n_bn, "layer %d out of range", layer);
+  const int64_t n_logical = (int64_t)lay.n_groups * lay.bn_group;
+  char* dst = a_buf(ws, lay, layer);
+  LCN_CHECK_CUDA(cudaMemsetAsync(dst, 0, lay.a_stride, st));
+  if (m->d.path == LCN_PATH_BF16)
+    lcn_launch(k_write_rows<__nv_bfloat16>, dim3(256), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), n_logical, m->P, lay.bn_group, lay.gstride);
+  else
+    lcn_launch(k_write_rows<float>, dim3(256), dim3(256), 0, st, src, reinterpret_cast<float*>(dst), n_logical, m->P, lay.bn_group, lay.gstride);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
 __global__ void k_unpack_mid(const float* __restrict__ wp32, PairTable pt, int nnz, int F, int FC,
                              float* __restrict__ dst) {
   lcn_pdl_prologue();
@@ -2146,7 +1997,7 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
       LCN_CHECK_CUDA(cudaMemcpyAsync(dst, ws + (layer == 0 ? lay.off_wm_first : lay.off_wm_last),
                                      sizeof(float) * L.Kin * L.Kout, cudaMemcpyDeviceToDevice, st));
     } else {
-      LCN_REQUIRE(!(bf && lcn_tc_enabled()), "the mid-layer weight tap needs the fp32 path (or LCN_DISABLE_TC=1)");
+      LCN_REQUIRE(!bf, "the mid-layer weight tap needs the fp32 path");
       LCN_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * P * P, st));
       const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(layer - 1) * m->nnz * m->FC * m->FC * 4096;
       lcn_launch(k_unpack_mid, dim3(m->nnz * m->FC * m->FC), dim3(256), 0, st, wp, make_pairs(m), m->nnz, F, m->FC, dst);

@@ -651,9 +651,9 @@ __global__ void __launch_bounds__(NV * (64 + 32 * EW), 1) k_lcn_stack(const __gr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+static bool stack_verbose() {
+  static const bool v = getenv("LCN_STACK_VERBOSE") != nullptr;      // diagnostics of the configuration search only
+  return v;
 }
 
 // contiguous split of the 17 output joints over ns CTAs, at most gmax each, minimising the largest block count
@@ -711,16 +711,17 @@ static void stack_fill(StackCfg* c, int tpg) {
 
 template <int EW, int NV>
 static int stack_active_clusters(const StackCfg& c, int sm_count) {
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(k_lcn_stack<EW, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424) != cudaSuccess ||
-        cudaFuncSetAttribute(k_lcn_stack<EW, NV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-      if (getenv("LCN_STACK_VERBOSE")) fprintf(stderr, "lcn_stack: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+  static std::once_flag once;
+  static bool attr_ok = false;
+  std::call_once(once, [] {
+    attr_ok = cudaFuncSetAttribute(k_lcn_stack<EW, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424) == cudaSuccess &&
+              cudaFuncSetAttribute(k_lcn_stack<EW, NV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!attr_ok) {
+      if (stack_verbose()) fprintf(stderr, "lcn_stack: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
       (void)cudaGetLastError();
-      return 0;
     }
-    attr = true;
-  }
+  });
+  if (!attr_ok) return 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute at[1];
@@ -735,7 +736,7 @@ static int stack_active_clusters(const StackCfg& c, int sm_count) {
   cfg.gridDim = dim3((unsigned)(sm_count / c.ns * c.ns));
   int active = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(&active, k_lcn_stack<EW, NV>, &cfg);
-  if (getenv("LCN_STACK_VERBOSE"))
+  if (stack_verbose())
     fprintf(stderr, "lcn_stack: occupancy query EW=%d NV=%d ns=%d smem=%zu -> %s, %d active clusters\n", EW, NV, c.ns, c.smem,
             cudaGetErrorString(e), active);
   if (e != cudaSuccess) {
@@ -748,28 +749,29 @@ static int stack_active_clusters(const StackCfg& c, int sm_count) {
 // Configuration for `tpg` row tiles per BatchNorm group; `clusters` = how many clusters the device keeps resident.
 // Decided once per (tpg) and cached: the occupancy query needs the device, the workspace layout needs the answer.
 static StackCfg stack_config(int tpg, int sm_count, int* clusters) {
+  static std::mutex mu;
   static StackCfg cache[3];
   static int cache_cl[3] = {0, 0, 0};
+  std::lock_guard<std::mutex> lock(mu);
   if (cache_cl[tpg]) {
     *clusters = cache_cl[tpg];
     return cache[tpg];
   }
   StackCfg c;
   memset(&c, 0, sizeof(c));
-  c.mc = env_int("LCN_STACK_MC", 1) ? 1 : 0;
+  c.mc = 1;
   int active = 0;
-  if (env_int("LCN_STACK_NV", 2) == 2) {
+  {
     // two groups per SM: <= 256 TMEM columns each
     c.nv = 2;
-    c.ns = env_int("LCN_STACK_NS", tpg == 2 ? 9 : 5);
-    c.stages = env_int("LCN_STACK_STAGES", 2);
+    c.ns = tpg == 2 ? 9 : 5;
+    c.stages = 2;
     stack_fill(&c, tpg);
     if (c.ns >= 1 && c.ns <= ST_MAX_NS && c.tmem_cols <= 512 && c.smem <= 231424) active = stack_active_clusters<4, 2>(c, sm_count);
   }
   if (active == 0) {
     c.nv = 1;
-    c.ns = env_int("LCN_STACK_NS1", tpg == 2 ? 6 : 3);
-    if (c.ns < 1 || c.ns > ST_MAX_NS || (LCN_J + c.ns - 1) / c.ns > (tpg == 2 ? 4 : 6)) c.ns = tpg == 2 ? 6 : 3;
+    c.ns = tpg == 2 ? 6 : 3;
     c.stages = 3;
     stack_fill(&c, tpg);
     active = stack_active_clusters<8, 1>(c, sm_count);
@@ -777,7 +779,7 @@ static StackCfg stack_config(int tpg, int sm_count, int* clusters) {
   }
   const int want = sm_count / c.ns;
   if (active > want) active = want;
-  if (getenv("LCN_STACK_VERBOSE"))
+  if (stack_verbose())
     fprintf(stderr, "lcn_stack: tpg=%d ns=%d gmax=%d stages=%d mc=%d nv=%d tmem=%d stage=%d smem=%zu clusters=%d\n", tpg, c.ns,
             c.gmax, c.stages, c.mc, c.nv, c.tmem_cols, c.stage_bytes, c.smem, active);
   cache[tpg] = c;
@@ -787,9 +789,7 @@ static StackCfg stack_config(int tpg, int sm_count, int* clusters) {
 }
 
 bool lcn_stack_eligible(const lcn_model* m, int bn_group, int training) {
-  static int disabled = -1;
-  if (disabled < 0) disabled = env_int("LCN_DISABLE_FUSED", 0) ? 1 : 0;
-  return !disabled && !training && m->d.path == LCN_PATH_BF16 && lcn_tc_enabled() && m->FC == 1 &&
+  return !training && m->d.path == LCN_PATH_BF16 && m->FC == 1 &&
          bn_group <= 2 * LCN_TILE && LCN_J * m->d.in_F <= 64 && m->n_lin >= 3;
 }
 
@@ -863,7 +863,11 @@ int lcn_stack_forward(const lcn_model* m, const WsLayout& lay, const float* para
   p.stage_bytes = c.stage_bytes;
   p.vc_bytes = (int)c.vc_bytes;
   p.cols = c.gmax * 64;
-  p.dbg = env_int("LCN_STACK_DBG", 0);
+#ifdef LCN_TC_PROFILE
+  { const char* e = getenv("LCN_STACK_DBG"); p.dbg = e ? atoi(e) : 0; }    // profiling build only (timing experiments)
+#else
+  p.dbg = 0;
+#endif
   p.n_rows = lay.n_rows;
   p.bn_group = lay.bn_group;
   p.n_groups = lay.n_groups;

@@ -6,7 +6,12 @@
 * Data-parallel training all-reduces ONE bucket (the raw gradients, packed to the nonzero weight blocks + the small
   tensors: average_gradients_packed; or the flat parameter-layout vector: average_gradient_bucket) between backward
   and the fused Adam step; BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
-Everything here is backend agnostic (nccl on GPUs, gloo in the CPU tests)."""
+* Two exchange modes for training.  "overlap" (default, init_native_dp + LcnEngine.train_step_graph): the library owns an
+  NCCL communicator and lcn_model_backward all-reduces every layer's weight gradient right behind its weight-gradient
+  GEMM, overlapped with the rest of the backward pass; the whole step is ONE CUDA graph (csrc/lcn_dp.cu).  "packed": the
+  round-1 path -- backward, pack the nonzero blocks, one torch.distributed all-reduce, unpack, Adam -- two graphs
+  around an exposed collective; kept as the reference point the overlap is measured against.
+Everything else here is backend agnostic (nccl on GPUs, gloo in the CPU tests)."""
 import torch
 import torch.distributed as dist
 
@@ -56,3 +61,40 @@ def broadcast_parameters(flat_params, src=0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(flat_params, src=src, group=group)
     return flat_params
+
+
+def init_native_dp(engine, group=None):
+    """Create the engine's own NCCL communicator (lcn_dp_init): rank 0 draws the unique id, torch.distributed carries
+    it to the other ranks (any backend).  Collective over `group`.  No-op in a single process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return False
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [engine.dp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.dp_init(box[0], rank, world)
+    return True
+
+
+def dp_train_step(engine, x, labels, dropout=0.0, mode="overlap", group=None, graph=True):
+    """One data-parallel train step on this rank's shard of the global batch; returns (loss, lr) like train_step.
+    mode "overlap": exchange inside lcn_model_backward (needs init_native_dp once); "packed": torch all-reduce of the
+    packed bucket between backward and Adam."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if mode == "overlap":
+        if multi and getattr(engine, "dp_world", 1) == 1:
+            init_native_dp(engine, group)
+        return engine.train_step_graph(x, labels, dropout) if graph else engine.train_step(x, labels, dropout)
+    if mode != "packed":
+        raise ValueError("mode must be 'overlap' or 'packed'")
+    if getattr(engine, "dp_world", 1) > 1:
+        engine.dp_enable(False)          # the torch-level exchange below replaces the one inside backward
+        engine.dp_world = -engine.dp_world
+    if not multi:
+        return engine.train_step_graph(x, labels, dropout) if graph else engine.train_step(x, labels, dropout)
+    if graph:
+        return engine.train_step_graph(x, labels, dropout, lambda b: average_gradient_bucket(b, group), packed=True)
+    engine.forward(x, bn_group=x.shape[0], training=True, dropout=dropout)
+    loss = engine.backward(x, labels, dropout)
+    average_gradient_bucket(engine.pack_grads(), group)
+    engine.unpack_grads()
+    return loss, engine.adam()

@@ -52,6 +52,7 @@ class LcnEngine:
             desc.mask_kind = L.LCN_MASK_LOCALLY_CONNECTED
             sup = (nm.T != 0).astype(np.float32)
             cm = np.zeros((J, J), np.float32)
+            self.mask_init = nm.T.copy()                    # L = neighbour_matrix.T is the initial value (:549-566)
         self.support = sup.copy()
         desc.support[:] = sup.reshape(-1).tolist()
         desc.const_mask[:] = cm.reshape(-1).tolist()
@@ -70,6 +71,10 @@ class LcnEngine:
         self.adam_v = torch.zeros_like(self.params)
         self.grads_raw = torch.zeros_like(self.params)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # op_loss_average state (models_att.py:370-379): [biased EMA of the total loss, steps], updated on the device
+        self.ema_dev = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)       # sum of l2_loss(w*, b*)
+        self._reg_scratch = torch.zeros(16, dtype=torch.uint8, device=self.device)
         self.ws = None
         self.learning_rate, self.decay_steps, self.decay_rate = learning_rate, decay_steps, decay_rate
         self.regularization = 0.0 if regularization is None else float(regularization)
@@ -133,7 +138,7 @@ class LcnEngine:
         for k, (o, r, c) in self.tensors.items():
             base = k.rsplit("/", 1)[-1]
             if k == "mask":
-                p[k] = self.support.copy()
+                p[k] = self.mask_init.copy()                # the VALUES of L, not only its zero pattern
             elif base == "gamma":
                 p[k] = np.ones(c)
             elif base == "beta":
@@ -153,8 +158,30 @@ class LcnEngine:
         if need == 0:
             raise L.LcnError(self.lib.lcn_last_error().decode())
         if self.ws is None or self.ws.numel() < need:
-            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._prepared = False
+            self._realloc_ws(need)
+        return self.ws.numel()
+
+    def _realloc_ws(self, need):
+        # Captured train-step graphs hold the old blob's address and the packed weights live in its head: a
+        # reallocation drops both (they are rebuilt on the next call).  fit() avoids the reallocation altogether by
+        # reserving the maximum of its train and predict layouts up front (reserve_ws).
+        if self._graphs:
+            torch.cuda.synchronize(self.device)
+        self._graphs.clear()
+        self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._prepared = False
+
+    def reserve_ws(self, *layouts):
+        """Size the workspace once for several (n_rows, bn_group, training) layouts, so that none of them reallocates
+        later."""
+        need = 0
+        for n_rows, bn_group, training in layouts:
+            b = int(self.lib.lcn_model_workspace_bytes(self.h, int(n_rows), int(bn_group), int(training)))
+            if b == 0:
+                raise L.LcnError(self.lib.lcn_last_error().decode())
+            need = max(need, b)
+        if self.ws is None or self.ws.numel() < need:
+            self._realloc_ws(need)
         return self.ws.numel()
 
     def _stream(self):
@@ -220,6 +247,25 @@ class LcnEngine:
                                             _ptr(self.loss_dev), _ptr(self.grads_raw), self._stream()))
         return self.loss_dev
 
+    # ---- data-parallel exchange inside the backward pass (csrc/lcn_dp.cu) ---------------------------------
+    def dp_init(self, unique_id, rank, world):
+        """Collective: give the model its NCCL communicator (lcn_dp_init).  unique_id: the 128 bytes rank 0 obtained from
+        LcnEngine.dp_unique_id(), identical on every rank.  From here on backward() returns rank-averaged gradients."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        L.check(self.lib.lcn_dp_init(self.h, C.byref(buf), int(rank), int(world)))
+        self._graphs.clear()
+        self.dp_world = int(world)
+
+    @staticmethod
+    def dp_unique_id():
+        buf = (C.c_uint8 * 128)()
+        L.check(L.load().lcn_dp_unique_id(C.byref(buf)))
+        return bytes(buf)
+
+    def dp_enable(self, on):
+        L.check(self.lib.lcn_dp_enable(self.h, int(bool(on))))
+        self._graphs.clear()
+
     # ---- data-parallel exchange: only what backward produces travels (lcn_model_pack_grads) ----
     def pack_grads(self):
         """Gather the nonzero weight blocks + every other tensor of the raw-gradient bucket into self.grads_compact."""
@@ -272,7 +318,23 @@ class LcnEngine:
         self._dyn_ev[slot] = ev
         return lr
 
-    def train_step_graph(self, x, labels, dropout=0.0, allreduce=None, packed=False):
+    def update_loss_ema(self, decay=0.9):
+        """op_loss_average of the reference, run every step (models_att.py:210-212,370-379): EMA of the TOTAL loss
+        (mse + regularization * sum l2_loss when regularization != 0) on the device; read it with loss_average()."""
+        reg = C.c_void_p(0)
+        if self.regularization != 0.0:
+            L.check(self.lib.lcn_l2_regularizer(self.h, _ptr(self.params), _ptr(self._reg_scratch), _ptr(self.reg_dev),
+                                                self._stream()))
+            reg = _ptr(self.reg_dev)
+        L.check(self.lib.lcn_loss_ema(_ptr(self.loss_dev), reg, float(self.regularization), float(decay),
+                                      _ptr(self.ema_dev), self._stream()))
+
+    def loss_average(self, decay=0.9):
+        """averages.average(loss) with TF's zero-debias [TF-sem]: biased / (1 - decay^steps).  One D2H read."""
+        biased, steps = self.ema_dev.tolist()
+        return biased / (1.0 - decay ** steps) if steps > 0 else 0.0
+
+    def train_step_graph(self, x, labels, dropout=0.0, allreduce=None, packed=False, track_ema=False):
         """train_step() as CUDA-graph replays: the ~60 launches of one step (forward, loss, backward, chain rule,
         Adam, weight re-preparation) are captured once per (batch shape, dropout, buffers) and replayed; the
         per-step scalars (dropout counter, Adam step size) travel through 16 bytes of device memory.
@@ -281,7 +343,8 @@ class LcnEngine:
         then two graphs are replayed around it.  packed=True: the callable receives the packed bucket
         (self.grads_compact: nonzero weight blocks + small tensors); the pack / unpack launches are part of the two
         graphs.  Returns (loss device scalar, learning rate used)."""
-        key = (x.data_ptr(), labels.data_ptr(), tuple(x.shape), float(dropout), allreduce is not None, bool(packed))
+        key = (x.data_ptr(), labels.data_ptr(), tuple(x.shape), float(dropout), allreduce is not None, bool(packed),
+               bool(track_ema))
         n = x.shape[0]
         if key not in self._graphs:
             self._ensure_ws(n, n, True)
@@ -294,19 +357,24 @@ class LcnEngine:
             # warm-up on a side stream (first-call attribute setup must not happen under capture)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            saved = (self.params.clone(), self.adam_m.clone(), self.adam_v.clone())
+            saved = (self.params.clone(), self.adam_m.clone(), self.adam_v.clone(), self.ema_dev.clone())
             with torch.cuda.stream(side):
                 self.forward(x, bn_group=n, training=True, dropout=dropout, out=out, dyn=True)
                 self.backward(x, labels, dropout)
+                if track_ema:
+                    self.update_loss_ema()
                 self.adam(dyn=True)
             torch.cuda.current_stream(self.device).wait_stream(side)
             self.params.copy_(saved[0]); self.adam_m.copy_(saved[1]); self.adam_v.copy_(saved[2])
+            self.ema_dev.copy_(saved[3])
             self.prepare()
             torch.cuda.synchronize(self.device)
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 self.forward(x, bn_group=n, training=True, dropout=dropout, out=out, dyn=True)
                 self.backward(x, labels, dropout)
+                if track_ema:
+                    self.update_loss_ema()           # before Adam: the regulariser is that of the step's parameters
                 if allreduce is None:
                     self.adam(dyn=True)
                 elif packed:
@@ -330,13 +398,89 @@ class LcnEngine:
         self._fwd_geom = (n, n, True)
         return self.loss_dev, lr
 
-    def train_step(self, x, labels, dropout=0.0, out=None):
-        """One sess.run([op_train, ...]) of the reference (models_att.py:210-212): fwd, loss, bwd, Adam.
+    def train_step(self, x, labels, dropout=0.0, out=None, track_ema=False):
+        """One sess.run([op_train, op_loss_average]) of the reference (models_att.py:210-212): fwd, loss, bwd, Adam.
         Returns (loss device scalar, learning rate used)."""
         self.forward(x, bn_group=x.shape[0], training=True, dropout=dropout, out=out)
         loss = self.backward(x, labels, dropout)
+        if track_ema:
+            self.update_loss_ema()
         lr = self.adam()
         return loss, lr
+
+    # ---- optimizer / trainer state (what tf.train.Saver stores next to the variables) ---------------
+    def get_state(self):
+        """Adam slots, global_step and the loss EMA: with get_params() the complete trainer state."""
+        return {"adam_m": self.adam_m.detach().cpu().numpy(), "adam_v": self.adam_v.detach().cpu().numpy(),
+                "global_step": np.asarray(self.step, dtype=np.int64), "loss_ema": self.ema_dev.detach().cpu().numpy()}
+
+    def set_state(self, st):
+        self.adam_m.copy_(torch.as_tensor(np.asarray(st["adam_m"], dtype=np.float32)))
+        self.adam_v.copy_(torch.as_tensor(np.asarray(st["adam_v"], dtype=np.float32)))
+        self.step = int(st["global_step"])
+        if "loss_ema" in st:
+            self.ema_dev.copy_(torch.as_tensor(np.asarray(st["loss_ema"], dtype=np.float32)))
+
+    # ---- the reference's method-level layer API, one kernel launch sequence each ------------------------
+    def forward_layers(self, layer_begin, layer_end, n_rows, bn_group=None, x=None, dropout=0.0, out=None):
+        """Linear layers [layer_begin, layer_end) with what follows each (BN / LeakyReLU / dropout / residual) on
+        the training-layout workspace (lcn_model_forward_layers)."""
+        bn_group = n_rows if bn_group is None else int(bn_group)
+        size = self._ensure_ws(n_rows, bn_group, True)
+        if not self._prepared:
+            self.prepare()
+        L.check(self.lib.lcn_model_forward_layers(self.h, _ptr(self.params), _ptr(self.ws), size, _ptr(x), n_rows, bn_group,
+                                                  float(dropout), self.seed, self.step + 1, int(layer_begin),
+                                                  int(layer_end), _ptr(out), self._stream()))
+        self._fwd_geom = None
+
+    def write_activation(self, layer, a, bn_group=None):
+        """Inject a dense fp32 [n, 17*F] activation as the layer output A_layer (lcn_model_write_tensor)."""
+        n = a.shape[0]
+        bn_group = n if bn_group is None else int(bn_group)
+        size = self._ensure_ws(n, bn_group, True)
+        L.check(self.lib.lcn_model_write_tensor(self.h, _ptr(self.ws), size, 1, int(layer), n, bn_group, _ptr(a),
+                                                self._stream()))
+
+    def mask_weights(self, w):
+        """cgcnn.mask_weights (models_att.py:576-586) on a CUDA float32 [17*Fi, 17*Fo] tensor, current mask values."""
+        self.prepare()
+        mask = self.read_tensor(3, 0, 128, 128)
+        out = torch.empty_like(w)
+        L.check(self.lib.lcn_mask_weights(_ptr(w), w.shape[0], w.shape[1], _ptr(mask), _ptr(out), self._stream()))
+        return out
+
+    def batch_norm(self, y, bn_name):
+        """cgcnn.batch_normalization_warp (models_att.py:588-612) with the gamma / beta of BN layer `bn_name`."""
+        g, b = self.tensor(bn_name + "/gamma"), self.tensor(bn_name + "/beta")
+        out = torch.empty_like(y)
+        L.check(self.lib.lcn_batch_norm(_ptr(y), y.shape[0], y.shape[1] // J, _ptr(g), _ptr(b), 1e-3, _ptr(out),
+                                        C.c_void_p(0), self._stream()))
+        return out
+
+    def mse_loss(self, pred, labels, with_reg=True):
+        """base_model.loss (models_att.py:352-366) on CUDA float32 tensors: mse (+ regularization * sum l2_loss)."""
+        out = torch.empty(1, dtype=torch.float32, device=self.device)
+        reg = C.c_void_p(0)
+        if with_reg and self.regularization != 0.0:
+            L.check(self.lib.lcn_l2_regularizer(self.h, _ptr(self.params), _ptr(self._reg_scratch), _ptr(self.reg_dev),
+                                                self._stream()))
+            reg = _ptr(self.reg_dev)
+        L.check(self.lib.lcn_mse_loss(_ptr(pred), _ptr(labels), pred.numel(), reg, float(self.regularization), _ptr(out),
+                                      self._stream()))
+        return out
+
+    def l2_regularizer(self):
+        """tf.add_n(self.regularizers) (models_att.py:364,465-472): sum over w*, b* of sum(v^2)/2, as a float."""
+        L.check(self.lib.lcn_l2_regularizer(self.h, _ptr(self.params), _ptr(self._reg_scratch), _ptr(self.reg_dev),
+                                            self._stream()))
+        return float(self.reg_dev.item())
+
+    def gather_rows(self, src_a, dst_a, idx, src_b=None, dst_b=None):
+        """Batch gather of fit (models_att.py:200) from the device-resident set(s): dst[b] = src[idx[b]]."""
+        L.check(self.lib.lcn_gather_rows(_ptr(src_a), src_a.shape[1], _ptr(dst_a), _ptr(src_b),
+                                         src_b.shape[1] if src_b is not None else 0, _ptr(dst_b), _ptr(idx),
+                                         idx.numel(), src_a.shape[0], self._stream()))
 
     def read_tensor(self, kind, layer, n_rows, bn_group):
         n_groups = (n_rows + bn_group - 1) // bn_group
@@ -365,26 +509,76 @@ class LcnEngine:
         return k
 
     # ---- batched predict (base_model.predict, models_att.py:79-132) -------------------------------
-    def predict(self, data, batch_size, chunk_groups=None):
+    def predict(self, data, batch_size, chunk_groups=None, out=None):
         """data: [N, 17*in_F] array (host).  Batches of `batch_size` poses are BN groups; the last one is
         zero padded (the zero rows take part in the statistics) exactly like the reference.  Returns
-        float64 [N, 51]."""
+        float64 [N, 51].
+
+        Pipelined: chunks of `chunk_groups` batches rotate through two pinned input / output buffers and two device
+        buffer pairs; the H2D copy of chunk i+1 (copy stream) and the D2H copy of chunk i-1 (drain stream) overlap the
+        forward pass of chunk i, and the host only ever waits for the chunk before the previous one."""
         data = np.ascontiguousarray(data, dtype=np.float32)
         n = data.shape[0]
         if chunk_groups is None:
             chunk_groups = max(1, 32768 // batch_size)
-        chunk = chunk_groups * batch_size
-        preds = np.empty((n, J * 3), dtype=np.float64)
-        pin_in = torch.empty((min(chunk, n), data.shape[1]), dtype=torch.float32).pin_memory()
-        pin_out = torch.empty((min(chunk, n), J * 3), dtype=torch.float32).pin_memory()
-        for b in range(0, n, chunk):
-            e = min(b + chunk, n)
-            pin_in[: e - b].copy_(torch.from_numpy(data[b:e]))
-            x = pin_in[: e - b].to(self.device, non_blocking=True)
-            out = self.forward(x, bn_group=batch_size, training=False)
-            pin_out[: e - b].copy_(out, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            preds[b:e] = pin_out[: e - b].numpy()
+        chunk = min(chunk_groups * batch_size, max(n, 1))
+        preds = np.empty((n, J * 3), dtype=np.float64) if out is None else out
+        if n == 0:
+            return preds
+        self._ensure_ws(chunk, batch_size, False)
+        if not self._prepared:
+            self.prepare()
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_pp", None) is None or self._pp["chunk"] < chunk or self._pp["cols"] != data.shape[1]:
+            self._pp = {"chunk": chunk, "cols": data.shape[1],
+                        "pin_in": [torch.empty((chunk, data.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)],
+                        "pin_out": [torch.empty((chunk, J * 3), dtype=torch.float32).pin_memory() for _ in range(2)],
+                        "x": [torch.empty((chunk, data.shape[1]), dtype=torch.float32, device=dev) for _ in range(2)],
+                        "o": [torch.empty((chunk, J * 3), dtype=torch.float32, device=dev) for _ in range(2)],
+                        "copy_s": torch.cuda.Stream(device=dev), "drain_s": torch.cuda.Stream(device=dev)}
+        pp = self._pp
+        copy_s, drain_s = pp["copy_s"], pp["drain_s"]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        computed = [torch.cuda.Event(), torch.cuda.Event()]
+        drained, drain_ev = [None, None], [None, None]
+        spans = [None, None]
+        copy_s.wait_stream(main)
+        drain_s.wait_stream(main)
+
+        def finish(b):
+            if drained[b] is not None:
+                drained[b].synchronize()
+                lo, hi = spans[b]
+                preds[lo:hi] = pp["pin_out"][b][: hi - lo].numpy()
+                drained[b] = None
+
+        for i, lo in enumerate(range(0, n, chunk)):
+            hi = min(lo + chunk, n)
+            b = i & 1
+            finish(b)                                   # chunk i-2: its pinned buffers are free again
+            pp["pin_in"][b][: hi - lo].copy_(torch.from_numpy(data[lo:hi]))
+            with torch.cuda.stream(copy_s):
+                if i >= 2:
+                    copy_s.wait_event(computed[b])      # the forward pass that read x[b] has finished
+                pp["x"][b][: hi - lo].copy_(pp["pin_in"][b][: hi - lo], non_blocking=True)
+                copied[b].record(copy_s)
+            main.wait_event(copied[b])
+            if i >= 2:
+                main.wait_event(drain_ev[b])            # the D2H copy that read o[b] has finished
+            self.forward(pp["x"][b][: hi - lo], bn_group=batch_size, training=False, out=pp["o"][b][: hi - lo])
+            computed[b].record(main)
+            with torch.cuda.stream(drain_s):
+                drain_s.wait_event(computed[b])
+                pp["pin_out"][b][: hi - lo].copy_(pp["o"][b][: hi - lo], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(drain_s)
+            drained[b] = drain_ev[b] = ev
+            spans[b] = (lo, hi)
+        finish(0)
+        finish(1)
+        main.wait_stream(copy_s)
+        main.wait_stream(drain_s)
         return preds
 
 

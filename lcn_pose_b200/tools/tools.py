@@ -58,6 +58,36 @@ def align_to_gt(pose, pose_gt):
     return z[0].cpu().numpy().astype(np.float64)
 
 
+def procrustes(A, B, scaling=True, reflection='best'):
+    """tools/tools.py:96-181 for one pose pair (A = target [17,3], B = input [17,3]): returns (d, Z, tform) with
+    tform = {'rotation', 'scale', 'translation'} exactly like the reference, every option of its signature
+    (lcn_procrustes; float32 on the device, float64 out).  procrustes_batch takes [n,17,3] stacks."""
+    d, Z, tf = procrustes_batch(np.asarray(A)[None], np.asarray(B)[None], scaling, reflection)
+    return float(d[0]), Z[0], {"rotation": tf["rotation"][0], "scale": float(tf["scale"][0]),
+                               "translation": tf["translation"][0]}
+
+
+def procrustes_batch(A, B, scaling=True, reflection='best'):
+    """n pose pairs at once: A, B [n,17,3] (NumPy or CUDA float32).  Returns (d [n], Z [n,17,3], tform dict of
+    stacked 'rotation' [n,3,3], 'scale' [n], 'translation' [n,3]) as float64 NumPy."""
+    import ctypes as C
+    from .. import _lib as L
+    a = A if torch.is_tensor(A) else _dev(np.asarray(A, np.float32))
+    b = B if torch.is_tensor(B) else _dev(np.asarray(B, np.float32))
+    a, b = a.reshape(-1, 17, 3).contiguous(), b.reshape(-1, 17, 3).contiguous()
+    assert a.shape == b.shape
+    n = a.shape[0]
+    z = torch.empty_like(a)
+    tf = torch.empty((n, 14), dtype=torch.float32, device=a.device)
+    refl = 0 if isinstance(reflection, str) else (2 if reflection else 1)
+    L.check(L.load().lcn_procrustes(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), n, int(bool(scaling)), refl,
+                                    C.c_void_p(z.data_ptr()), C.c_void_p(tf.data_ptr()),
+                                    C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)))
+    t = tf.cpu().numpy().astype(np.float64)
+    return t[:, 13], z.cpu().numpy().astype(np.float64), {"rotation": t[:, :9].reshape(n, 3, 3), "scale": t[:, 9],
+                                                           "translation": t[:, 10:13]}
+
+
 def pose_errors(pred_image_frame, gt, box, camera, root_depth, protocol2=False):
     """One evaluate.py:54-61 iteration on the device (n = 1): returns the 17 per-joint errors in mm."""
     cam = np.array([[camera["fx"], camera["fy"], camera["cx"], camera["cy"]]], dtype=np.float32)

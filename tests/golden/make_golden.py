@@ -130,6 +130,38 @@ def main():
     out.update(aug_undo_in=u_in,
                aug_undo_out=data.undo(u_in, {"f": 1, "r": 2, "t": 3}, number_actions=3, angle=180, translation=0.07),
                aug_undo_fr_out=data.undo(u_in[:18], {"r": 1, "f": 2}, number_actions=2, angle=180, translation=0.0))
+    # ---- tools.procrustes with every option of its signature (tools/tools.py:96-181) ----
+    A = g[:12].copy()
+    B = camf[:12].copy()
+    B[3] = A[3] * np.array([-1.0, 1.0, 1.0]) * 0.8 + 30.0          # a reflected input: the forced variants differ from 'best'
+    for tag, kw in (("best", {}), ("noscale", {"scaling": False}), ("norefl", {"reflection": False}),
+                    ("refl", {"reflection": True}), ("noscale_norefl", {"scaling": False, "reflection": False})):
+        ds, Zs, Rs, ss, ts = [], [], [], [], []
+        for i in range(len(A)):
+            d_, Z_, tf_ = tools.procrustes(A[i].copy(), B[i].copy(), **kw)
+            ds.append(d_); Zs.append(Z_); Rs.append(tf_["rotation"]); ss.append(tf_["scale"]); ts.append(tf_["translation"])
+        out.update({f"proc_{tag}_d": np.array(ds), f"proc_{tag}_Z": np.array(Zs), f"proc_{tag}_R": np.array(Rs),
+                    f"proc_{tag}_scale": np.array(ss, dtype=np.float64), f"proc_{tag}_t": np.array(ts)})
+    out.update(proc_A=A, proc_B=B)
+    # ---- DataReader.read_2d / read_3d / denormalize (tools/data.py:338-489) on a synthetic dataitem list covering the
+    # three resolution classes; keys as tools/gendb.py:66-81 writes them ----
+    cams = ["54138969", "55011271", "cam_3", "7", "60457274", "58860488"]
+    def items(n, seed):
+        r = np.random.default_rng(seed)
+        return [{"joint_3d_image": np.concatenate([r.uniform(0, 1000, (17, 2)), r.normal(0, 200, (17, 1))], 1),
+                 "camera_param": {"name": cams[i % len(cams)]}, "cameraid": i % 4, "videoid": i, "subject": 1 + i % 3,
+                 "action": 2 + i % 5} for i in range(n)]
+    tr, te = items(7, 1), items(11, 2)
+    dr = data.DataReader()
+    with contextlib.redirect_stdout(io.StringIO()):
+        x_tr, x_te = dr.read_2d(tr, te)
+        y_tr, y_te = dr.read_3d()
+        res = dr.denormalize(y_te.copy())
+    out.update(dr_train_j3d=np.array([it["joint_3d_image"] for it in tr]), dr_test_j3d=np.array([it["joint_3d_image"] for it in te]),
+               dr_train_cam=np.array([it["camera_param"]["name"] for it in tr]), dr_test_cam=np.array([it["camera_param"]["name"] for it in te]),
+               dr_x_train=x_tr, dr_x_test=x_te, dr_y_train=y_tr, dr_y_test=y_te,
+               dr_denorm=np.array([r_["result"] for r_ in res]),
+               dr_denorm_action=np.array([r_["action"] for r_ in res]))
     np.savez_compressed(os.path.join(HERE, "reference_numpy.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_numpy.npz"), "with", len(out), "arrays")
 

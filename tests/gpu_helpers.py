@@ -38,5 +38,14 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def elem_rel_err(a, b, floor=1e-3):
+    """Elementwise relative error next to the max-norm rel_err: max_i |a_i - b_i| / (|b_i| + floor * max|b|).  The floor
+    keeps entries that are zero up to rounding (|b_i| << max|b|) from dominating; with floor = 1e-3 an entry 1000 times
+    smaller than the largest one is still held to the stated relative tolerance within a factor of two."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b) / (np.abs(b) + floor * max(np.abs(b).max(), 1e-300))).max())
+
+
 def dev(a):
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()

@@ -53,6 +53,19 @@ def test_mpjpe_and_pmpjpe_end_to_end(path, tol_mm):
     e1, _ = eval_mpjpe(pose, f32(gt), f32(box), f32(cam), f32(rd), False)
     e2, _ = eval_mpjpe(pose, f32(gt), f32(box), f32(cam), f32(rd), True)
     e1, e2 = e1.cpu().numpy().astype(np.float64), e2.cpu().numpy().astype(np.float64)
+    # what was measured goes on file (gpurun_out/parity_mpjpe.json -> profiles/r2/), not only pass / fail
+    import json
+    import os
+    rec_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_mpjpe.json")
+    os.makedirs(os.path.dirname(rec_path), exist_ok=True)
+    blob = json.load(open(rec_path)) if os.path.exists(rec_path) else {}
+    blob[path] = {"tolerance_mm": tol_mm, "poses": n, "mpjpe_oracle_mm": float(e1_ref.mean()), "pmpjpe_oracle_mm": float(e2_ref.mean()),
+                  "mpjpe_delta_mm": float(abs(e1.mean() - e1_ref.mean())), "pmpjpe_delta_mm": float(abs(e2.mean() - e2_ref.mean())),
+                  "per_joint_mpjpe_delta_max_mm": float(np.abs(e1.mean(0) - e1_ref.mean(0)).max()),
+                  "per_joint_pmpjpe_delta_max_mm": float(np.abs(e2.mean(0) - e2_ref.mean(0)).max()),
+                  "per_pose_joint_error_delta_max_mm": float(np.abs(e1 - e1_ref).max())}
+    json.dump(blob, open(rec_path, "w"), indent=1, sort_keys=True)
+    print("MPJPE parity", path, blob[path])
     assert abs(e1.mean() - e1_ref.mean()) < tol_mm, (path, e1.mean(), e1_ref.mean())
     assert abs(e2.mean() - e2_ref.mean()) < tol_mm, (path, e2.mean(), e2_ref.mean())
     # per-joint means (the table evaluate.py:102-106 prints)

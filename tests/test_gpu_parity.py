@@ -306,3 +306,73 @@ def test_forward_and_train_step_multi_wave_bf16():
     loss, _ = eng.train_step(xd, yd)
     ref_loss, _ = O.loss_and_grads(cfg, p, x.astype(np.float64), y.astype(np.float64))
     assert abs(loss.item() - ref_loss) < 2e-2 * ref_loss
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16"])
+def test_regularization_term_in_gradients_and_adam(path):
+    """regularization != 0 (models_att.py:362-365,465-472): reg * sum l2_loss(w*, b*) joins the loss, i.e. reg * theta
+    joins the gradient of every w* / b* inside the fused Adam kernel (lcn_model_adam_step's `regularization`)."""
+    reg = 5e-4
+    eng, cfg, p = make_pair(L=1, knn=3, path=path, reg=reg)
+    eng0, _, _ = make_pair(L=1, knn=3, path=path, reg=0.0)
+    n = 256
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    eng.forward(xd, bn_group=n, training=True)
+    eng.backward(xd, yd, 0.0)
+    eng0.forward(xd, bn_group=n, training=True)
+    eng0.backward(xd, yd, 0.0)
+    g, g0 = eng.unflatten(eng.true_grads()), eng0.unflatten(eng0.true_grads())
+    _, ref_g = O.loss_and_grads(cfg, p, x.astype(np.float64), y.astype(np.float64))
+    for k in sorted(ref_g):
+        base = k.rsplit("/", 1)[-1]
+        if base[0] in "wb":                     # the regulariser's share, isolated from the arithmetic path: exactly reg * theta
+            assert rel_err(g[k] - g0[k], reg * p[k]) < 1e-5, k
+        else:
+            assert np.array_equal(g[k], g0[k]), k
+        if path == "fp32":
+            assert rel_err(g[k], ref_g[k]) < GRAD_TOL["fp32"], k
+    assert abs(eng.l2_regularizer() - O.reg_loss(cfg, p) / reg) < 1e-5 * O.reg_loss(cfg, p) / reg
+    # three Adam steps with the regulariser against the oracle (fp32: elementwise; bf16: direction of the step)
+    st = O.AdamState()
+    p_ref = {k: v.copy() for k, v in p.items()}
+    for _ in range(3):
+        before = {k: v.copy() for k, v in p_ref.items()}
+        ref_loss, _, _ = O.train_step(cfg, p_ref, st, x.astype(np.float64), y.astype(np.float64))
+        loss, _ = eng.train_step(xd, yd)
+        got = eng.get_params()
+        for k in p_ref:
+            d_ref, d_got = p_ref[k] - before[k], got[k].astype(np.float64) - before[k]
+            bad = np.abs(d_got - d_ref) > (5e-3 if path == "fp32" else 1e-1) * np.abs(d_ref).max() + 1e-7 * np.abs(before[k]).max()
+            assert bad.mean() < (1e-9 if path == "fp32" else 0.02), (k, bad.mean())
+        eng.set_params({k: v.astype(np.float32) for k, v in p_ref.items()})
+        for k, (o, r, c) in eng.tensors.items():
+            eng.adam_m[o:o + r * c].copy_(torch.as_tensor(st.m[k].astype(np.float32).reshape(-1)))
+            eng.adam_v[o:o + r * c].copy_(torch.as_tensor(st.v[k].astype(np.float32).reshape(-1)))
+
+
+def test_trainer_state_round_trips_through_a_tf_checkpoint(tmp_path):
+    """N steps + save + restore into a fresh engine + N steps == 2N steps: variables, Adam slots and global_step (LR decay,
+    bias correction, dropout stream position) all travel through the TensorBundle files (ADVICE: resume)."""
+    from lcn_pose_b200.tools import tf_checkpoint
+    n = 256
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    a, _, _ = make_pair(L=1, knn=2, path="fp32")
+    b, _, _ = make_pair(L=1, knn=2, path="fp32")
+    for _ in range(6):
+        a.train_step(xd, yd, dropout=0.25)
+    for _ in range(3):
+        b.train_step(xd, yd, dropout=0.25)
+    prefix = tf_checkpoint.save_model(str(tmp_path), b.step, b.get_params(), b.get_state(), b.tensors)
+    c, _, _ = make_pair(L=1, knn=2, path="fp32", seed=9)          # different initial parameters
+    params, state = tf_checkpoint.load_model(prefix, c.tensors, c.n_params)
+    c.set_params(params)
+    c.set_state(state)
+    assert c.step == 3
+    for _ in range(3):
+        c.train_step(xd, yd, dropout=0.25)
+    assert c.step == a.step == 6
+    d = (a.params - c.params).abs()
+    assert float(d.max()) < 1e-5 and int((d > 1e-6 + 1e-4 * a.params.abs()).sum()) <= 8
+    assert float((a.adam_v - c.adam_v).abs().max()) <= 1e-3 * float(a.adam_v.abs().max())

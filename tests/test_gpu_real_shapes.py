@@ -1,0 +1,126 @@
+"""Parity at the shapes bench.py measures (BASELINE.json configs), not at toy sizes:
+
+  configs[1]  knn=3 locally connected, L=3, F=64, batch 4096, dropout 0.25, bf16, through train_step_graph (CUDA-graph
+              replay: the fp64-atomic BatchNorm statistics, the side-stream weight gradients and the device-resident step
+              scalars are all on) -- loss and EVERY gradient against the oracle, then one Adam step
+  configs[3]  exponential mask (289 blocks), L=3, batch 4096, bf16 -- loss and gradients
+  configs[4]  L=5, F=128, knn in {1, 3, full}, batch 16384 -- per-layer forward outputs and the loss
+
+Each test also records what it measured (max-norm AND elementwise relative errors) into
+gpurun_out/parity_real_shapes.json so that the numbers, not only pass / fail, are on file (profiles/r2/)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lcn_oracle as O
+from tests.gpu_helpers import dev, elem_rel_err, make_pair, rel_err, synth_xy
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RECORD = os.path.join(ROOT, "gpurun_out", "parity_real_shapes.json")
+
+
+def _record(key, value):
+    os.makedirs(os.path.dirname(RECORD), exist_ok=True)
+    blob = json.load(open(RECORD)) if os.path.exists(RECORD) else {}
+    blob[key] = value
+    json.dump(blob, open(RECORD, "w"), indent=1, sort_keys=True)
+
+
+def _grad_report(g, ref_g):
+    return {k: {"max_norm_rel": rel_err(g[k], ref_g[k]), "elementwise_rel": elem_rel_err(g[k], ref_g[k], floor=1e-2),
+                "cosine": float((g[k].astype(np.float64) * ref_g[k]).sum() /
+                                (np.linalg.norm(g[k].astype(np.float64)) * np.linalg.norm(ref_g[k]) + 1e-300))}
+            for k in sorted(ref_g)}
+
+
+def _check_grads(rep, path):
+    for k, r in rep.items():
+        base = k.rsplit("/", 1)[-1]
+        tol = {"fp32": 2e-3, "x3": 2e-3}.get(path, 1e-1)
+        if path == "bf16" and base.startswith("b") and not k.endswith("b4"):
+            tol = 0.25      # bias in front of BatchNorm: the gradient is a near-cancelling sum (BN removes the channel mean)
+        if path == "bf16" and k.endswith("/w1"):
+            tol = 0.15
+        assert r["max_norm_rel"] < tol, (k, r)
+        assert r["cosine"] > (0.999 if path != "bf16" else 0.98), (k, r)
+
+
+@pytest.mark.parametrize("mask_type,knn,tag", [("locally_connected", 3, "configs1_knn3_L3_B4096"),
+                                               ("exponential", 1, "configs3_exponential_L3_B4096")])
+def test_benchmarked_train_step_loss_and_every_gradient(mask_type, knn, tag):
+    n, rate = 4096, 0.25
+    eng, cfg, p = make_pair(L=3, knn=knn, mask_type=mask_type, path="bf16")
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    keep = [eng.dropout_keep(l, n, rate).cpu().numpy().astype(bool) for l in range(7)]
+    ref_loss, ref_g = O.loss_and_grads(cfg, p, x.astype(np.float64), y.astype(np.float64), rate, keep)
+    before = eng.params.clone()
+    loss, lr = eng.train_step_graph(xd, yd, dropout=rate)              # the exact call bench.py times
+    loss = float(loss.item())
+    after = eng.get_params()
+    # the graph replay left the raw gradients of THIS step in the bucket: finish the chain rule on the pre-step parameters
+    stepped = eng.params.clone()
+    eng.params.copy_(before)
+    eng.prepare()
+    g = eng.unflatten(eng.true_grads())
+    eng.params.copy_(stepped)
+    eng.prepare()
+    rep = _grad_report(g, ref_g)
+    _record(tag, {"loss": loss, "oracle_loss": ref_loss, "loss_rel": abs(loss - ref_loss) / ref_loss, "grads": rep})
+    assert abs(loss - ref_loss) < 2e-2 * ref_loss
+    _check_grads(rep, "bf16")
+    # one TF1-Adam step from zero moments moves every element by lr * sign(g) (|g| >> eps): direction parity
+    st = O.AdamState()
+    p_ref = {k: v.copy() for k, v in p.items()}
+    O.adam_step(cfg, p_ref, ref_g, st)
+    wrong = {}
+    for k in p:
+        d_ref, d_got = p_ref[k] - p[k], after[k].astype(np.float64) - p[k]
+        big = np.abs(d_ref) > 0.5 * np.abs(d_ref).max()
+        wrong[k] = float((np.sign(d_ref[big]) != np.sign(d_got[big])).mean()) if big.any() else 0.0
+        assert wrong[k] < 0.02, (k, wrong[k])
+    assert abs(lr - 1e-3) < 1e-12 and eng.step == 1
+
+
+@pytest.mark.parametrize("knn,tag", [(1, "knn1"), (3, "knn3"), (17, "full")])
+def test_wide_deep_sweep_forward_per_layer_and_loss(knn, tag):
+    """configs[4]: L=5, F=128, batch 16384 (the tensor-pipe utilisation sweep): every Z_l / A_l of the bf16 path against
+    the oracle layer applied to the GPU's own previous activation, and the loss."""
+    n, L, F = 16384, 5, 128
+    eng, cfg, p = make_pair(F=F, L=L, knn=knn, path="bf16")
+    x, y = synth_xy(n)
+    xd, yd = dev(x), dev(y)
+    out = eng.forward(xd, bn_group=n, training=True).cpu().numpy()
+    mask = O.mask_values(cfg, p)
+    wn, bn_, bnn = O.weight_names(cfg), O.bias_names(cfg), O.bn_names(cfg)
+    a_prev = torch.as_tensor(x.astype(np.float64))
+    worst_z = worst_a = 0.0
+    for l in range(1 + 2 * L):
+        wm, _, _ = O.effective_weight(cfg, p[wn[l]], mask)
+        z_ref = (a_prev @ torch.as_tensor(wm)).numpy() + p[bn_[l]]     # float64 on the host cores
+        z = eng.read_tensor(0, l, n, n).cpu().numpy().astype(np.float64)
+        worst_z = max(worst_z, rel_err(z, z_ref))
+        assert rel_err(z, z_ref) < 1e-2, (l, rel_err(z, z_ref))
+        a_ref, _, _, _ = O._bn_forward(z, p[bnn[l] + "/gamma"], p[bnn[l] + "/beta"], F)
+        a_ref = np.where(a_ref > 0, a_ref, 0.2 * a_ref)
+        if l >= 2 and l % 2 == 0:
+            a_ref = a_ref + eng.read_tensor(1, l - 2, n, n).cpu().numpy()
+        a = eng.read_tensor(1, l, n, n).cpu().numpy().astype(np.float64)
+        worst_a = max(worst_a, rel_err(a, a_ref))
+        assert rel_err(a, a_ref) < 1e-2, (l, rel_err(a, a_ref))
+        a_prev = torch.as_tensor(a)
+    wm, _, _ = O.effective_weight(cfg, p[wn[-1]], mask)
+    y_ref = ((a_prev @ torch.as_tensor(wm)).numpy() + p[bn_[-1]]).reshape(n, 17, 3)
+    y_ref[:, :, :2] += x.reshape(n, 17, 2)
+    e_out = rel_err(out, y_ref.reshape(n, 51))
+    loss = float(eng.backward(xd, yd, 0.0).item())
+    ref_loss = float(np.mean((y_ref.reshape(n, 51) - y) ** 2))
+    _record("configs4_L5_F128_B16384_" + tag, {"nnz_blocks": int(cfg.support().sum()), "worst_Z_rel": worst_z,
+                                               "worst_A_rel": worst_a, "head_rel": e_out, "loss": loss,
+                                               "loss_from_gpu_activations": ref_loss})
+    assert e_out < 1e-2
+    assert abs(loss - ref_loss) < 2e-3 * ref_loss

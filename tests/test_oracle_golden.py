@@ -102,3 +102,35 @@ def test_tta_undo_matches_reference(golden):
     np.testing.assert_allclose(got, g["aug_undo_out"], atol=1e-14)
     got = O.undo(g["aug_undo_in"][:18], {"r": 1, "f": 2}, number_actions=2, angle=180, translation=0.0)
     np.testing.assert_allclose(got, g["aug_undo_fr_out"], atol=1e-14)
+
+
+@pytest.mark.parametrize("tag,kw", [("best", {}), ("noscale", {"scaling": False}), ("norefl", {"reflection": False}),
+                                    ("refl", {"reflection": True}),
+                                    ("noscale_norefl", {"scaling": False, "reflection": False})])
+def test_procrustes_every_option_matches_reference(golden, tag, kw):
+    """tools.procrustes(A, B, scaling, reflection) (tools/tools.py:96-181): the oracle against the reference's own output
+    for every option of the signature, including a reflected input where the forced variants differ from 'best'."""
+    A, B = golden["proc_A"], golden["proc_B"]
+    for i in range(len(A)):
+        d, Z, tf = O.procrustes(A[i], B[i], **kw)
+        assert abs(d - golden[f"proc_{tag}_d"][i]) < 1e-10
+        np.testing.assert_allclose(Z, golden[f"proc_{tag}_Z"][i], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(tf["rotation"], golden[f"proc_{tag}_R"][i], rtol=0, atol=1e-10)
+        assert abs(tf["scale"] - golden[f"proc_{tag}_scale"][i]) < 1e-10
+        np.testing.assert_allclose(tf["translation"], golden[f"proc_{tag}_t"][i], rtol=0, atol=1e-7)
+    assert not np.allclose(golden["proc_best_Z"][3], golden["proc_norefl_Z"][3])     # the options do something
+
+
+def test_datareader_normalise_denormalise_pinned_to_reference(golden):
+    """DataReader.read_2d / read_3d / denormalize (tools/data.py:338-489), run by make_golden.py on a synthetic dataitem
+    list covering the three camera-resolution classes."""
+    for split in ("train", "test"):
+        cams = golden[f"dr_{split}_cam"]
+        res = np.array([O.camera_resolution(c) for c in cams], dtype=np.float64)
+        j3d = golden[f"dr_{split}_j3d"]
+        np.testing.assert_allclose(O.normalize_2d(j3d, res[:, 0], res[:, 1]), golden[f"dr_x_{split}"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(O.normalize_3d(j3d, res[:, 0], res[:, 1]), golden[f"dr_y_{split}"], rtol=0, atol=1e-13)
+    res = np.array([O.camera_resolution(c) for c in golden["dr_test_cam"]], dtype=np.float64)
+    den = O.denormalize(golden["dr_y_test"], res[:, 0], res[:, 1])
+    np.testing.assert_allclose(den, golden["dr_denorm"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(den, golden["dr_test_j3d"], rtol=0, atol=1e-9)     # denormalize inverts read_3d
