@@ -16,8 +16,12 @@
  *    library never synchronises the device and never allocates device memory.
  *  - every function returns 0 (LCN_OK) or a negative LCN_E* code; the message is available from
  *    lcn_last_error() (thread local).  No C++ exception crosses the boundary.
- *  - a model handle is immutable after creation (block lists, offsets); concurrent launches on
- *    distinct streams with distinct workspaces are safe.
+ *  - a model handle's tables (block lists, offsets) are immutable after creation.  It also owns one side stream with a
+ *    few events (the weight-gradient GEMMs of lcn_model_backward and the edge-layer packs of
+ *    lcn_model_prepare_weights run there, forked from and joined to the caller's stream) and, after lcn_dp_init, a
+ *    communication stream: calls that use them serialise on a mutex inside the handle while they ENQUEUE (never while
+ *    the GPU runs), so any number of host threads may call into the same handle with distinct streams and
+ *    workspaces; one-time kernel-attribute setup is guarded by std::call_once.
  *  - matrices are row-major; feature index inside a row is joint-major: column j*F + f
  *    (network/models_att.py:582); mask index is [input joint, output joint] (:583).
  */
@@ -41,10 +45,15 @@ enum {
   LCN_ESTATE = -4    /* call order violated (e.g. backward before forward) */
 };
 
-/* arithmetic path of the LCN layers */
+/* arithmetic path of the LCN layers -- BOTH run every mid-layer GEMM (forward, input gradient, weight gradient) on the
+ * tcgen05 tensor cores with fp32 accumulation in TMEM; they differ in how operands are stored */
 enum {
-  LCN_PATH_FP32 = 0, /* fp32 storage + fp32 FFMA accumulate: the 1e-4 parity path          */
-  LCN_PATH_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM (tcgen05): the 1e-2 path     */
+  LCN_PATH_FP32 = 0, /* the 1e-4 parity path ("fp32/TF32 path" of the north_star): activations and packed weights are
+                        split-bf16 pairs v = hi + lo (16 significand bits) and every block product is three tensor-core
+                        products hi*hi + hi*lo + lo*hi.  Single-pass TF32 (10-bit mantissa) measures 8e-5 per layer, too
+                        close to the 1e-4 bar; this measures 5e-7.  The K = 17*in_F first layer and the N = 51 head run
+                        on CUDA cores in fp32 (< 1.3 % of the FLOPs, degenerate MMA shapes).                           */
+  LCN_PATH_BF16 = 1  /* bf16 operands, one product per block: the 1e-2 path, 3x fewer tensor-core FLOPs, half the bytes */
 };
 
 enum {

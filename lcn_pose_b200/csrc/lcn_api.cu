@@ -265,7 +265,7 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.tiles = (int)(w.rows_pad / LCN_TILE);
   w.tiles_per_group = w.gstride / LCN_TILE;
   w.training = training;
-  w.es = m->d.path == LCN_PATH_BF16 ? 2 : 4;
+  w.es = m->d.path == LCN_PATH_BF16 ? 2 : 4;           // bf16, or a (hi, lo) pair of bf16 (lcn_sp16)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -284,6 +284,9 @@ WsLayout lcn_ws_layout(const lcn_model* m, int64_t n_rows, int bn_group, int tra
   w.off_wp32 = take(sizeof(float) * n_mid * sub);
   w.off_wp16f = take(2 * n_mid * sub);
   w.off_wp16b = take(2 * n_mid * sub);
+  const bool x3 = m->d.path == LCN_PATH_FP32;          // split-bf16 operands: the lo parts of the packed blocks
+  w.off_wp16f_lo = take(x3 ? 2 * n_mid * sub : 0);
+  w.off_wp16b_lo = take(x3 ? 2 * n_mid * sub : 0);
   w.off_wl16f = take((size_t)LCN_J * m->FC * 8192);
   w.off_wl16b = take((size_t)LCN_J * m->FC * 8192);
   w.off_wf16 = take((size_t)LCN_J * m->FC * 8192);

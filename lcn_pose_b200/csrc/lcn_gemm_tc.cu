@@ -33,10 +33,18 @@
 #define TC_GMAX 6                   // forward / dgrad: max N-side chunks (of 64 columns) per CTA -> <= 384 of 512 TMEM columns
 #define TC_A_BYTES 16384            // 128 rows x 64 bf16
 #define TC_B_BYTES 8192             // one 64x64 bf16 block
-#define TC_RING_UNITS 23            // operand ring: 23 x 8 KB; one K-chunk iteration takes 2 (A tile) + #blocks units
-#define TC_RING_BYTES (TC_RING_UNITS * TC_B_BYTES)
 #define TC_EPI_WARPS 8              // epilogue warps of k_tc_gemm: two per TMEM lane quarter (32 columns of a chunk each)
-#define TC_SMEM_BYTES (1024 + TC_RING_BYTES + 2 * TC_A_BYTES + TC_EPI_WARPS * 64 * 2 * 4)   // + 2 output staging tiles + BN partial scratch
+// Geometry of the two instantiations of k_tc_gemm.  X3 = split-bf16 operands (lcn_sp16, lcn_internal.cuh): every A tile
+// and every weight block comes as a (hi, lo) pair and each block costs three MMAs (hi*hi + hi*lo + lo*hi).
+template <bool X3>
+struct TcGeo {
+  static constexpr int PL = X3 ? 2 : 1;                  // planes per operand tile
+  static constexpr int A_UNITS = 2 * PL;                 // ring units (8 KB) of the A operand of one iteration
+  static constexpr int RING_UNITS = X3 ? 19 : 23;        // operand ring: one K-chunk iteration takes A_UNITS + PL * #blocks units
+  static constexpr int RING_BYTES = RING_UNITS * TC_B_BYTES;
+  static constexpr int STAGE_BYTES = PL * TC_A_BYTES;    // output staging per epilogue team
+  static constexpr int SMEM_BYTES = 1024 + RING_BYTES + 2 * STAGE_BYTES + TC_EPI_WARPS * 64 * 2 * 4;   // + BN partial scratch
+};
 #define TC_THREADS 192              // wgrad kernel
 #define TC_MMA_WARPS 2               // MMA-issuing warps of k_tc_gemm (iteration it is issued by warp it % 2)
 #define TC_EPI_T0 (32 + 32 * TC_MMA_WARPS)                  // first epilogue thread
@@ -115,8 +123,10 @@ struct TcParams {
 //   (tc_fill_schedule); the MMA warp commits to done[q] right after the last MMA into chunk q and the four epilogue
 //   warps convert / store / reduce that chunk while the remaining MMAs run.  Two 16 KB staging tiles alternate.
 // ---------------------------------------------------------------------------------------------
+template <bool X3>
 __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16* __restrict__ A,
                                                         const __nv_bfloat16* __restrict__ Wp,
+                                                        const __nv_bfloat16* __restrict__ Wp_lo,
                                                         const float* __restrict__ bias,
                                                         const __nv_bfloat16* __restrict__ addend,
                                                         __nv_bfloat16* __restrict__ Y, float* __restrict__ part,
@@ -135,25 +145,20 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
   const int n_it = p.gnit[g];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_CHUNKS]), done0 = smem_u32(&bars[2 * TC_MAX_CHUNKS]);
   const uint32_t tmem_cols = G <= 1 ? 64u : (G == 2 ? 128u : (G <= 4 ? 256u : 512u));
+  using Geo = TcGeo<X3>;
+  constexpr int PL = Geo::PL;
   TC_STAMP(0);
 
-  // Cluster of CT row tiles of the same chunk group (cluster dims (1, CT, 1), CT = 1: no cluster): the CTAs run the same
-  // schedule, so the weight panel of an iteration is fetched once per cluster -- every CTA loads 1/CT of it and
-  // multicasts that share into the same ring offset of all CTAs (L2 -> shared-memory traffic of the weights / CT).  A ring
-  // region may be overwritten when the MMAs of ALL CTAs have consumed it: empty[] takes CT multicast commits.
-  const uint32_t CT = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << CT) - 1u);
   if (threadIdx.x < 2 * TC_MAX_CHUNKS + TC_GMAX) {
     // every barrier is single use: one init each, in parallel.  done[q] collects one commit per MMA warp issuing into q
     const int i = threadIdx.x;
-    const uint32_t cnt = i < TC_MAX_CHUNKS ? 1u : (i < 2 * TC_MAX_CHUNKS ? CT : (uint32_t)max(1, (int)p.gdcnt[g][i - 2 * TC_MAX_CHUNKS]));
+    const uint32_t cnt = i < 2 * TC_MAX_CHUNKS ? 1u : (uint32_t)max(1, (int)p.gdcnt[g][i - 2 * TC_MAX_CHUNKS]);
     mbar_init(full0 + 8 * i, cnt);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), tmem_cols);
   tc_fence_before();
   __syncthreads();
-  if (CT > 1) cluster_sync_all();          // every CTA's barriers are initialised before remote bytes / arrivals land
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (warp > TC_MMA_WARPS) {
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform; one elected lane issues) =====
-    const __nv_bfloat16* a_tile = A + (size_t)tile * p.NCK * 8192;
+    const __nv_bfloat16* a_tile = A + (size_t)tile * p.NCK * (8192 * PL);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t s = p.sched[g][it];
       const uint32_t kc = TC_S_KC(s), cnt = (uint32_t)__popc(TC_S_BITS(s));
@@ -183,15 +188,11 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
       if (elect_one()) {
         TC_STAMP(16 + 4 * it);
         const uint32_t sa = sbase + TC_S_OFF(s) * TC_B_BYTES;
-        mbar_expect_tx(full0 + 8 * it, TC_A_BYTES + cnt * TC_B_BYTES);
-        bulk_g2s(sa, a_tile + (size_t)kc * 8192, TC_A_BYTES, full0 + 8 * it);
-        if (CT == 1) {
-          bulk_g2s(sa + TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * it);
-        } else {
-          const uint32_t share = cnt * TC_B_BYTES / CT;       // CT in {2, 4}: a multiple of 2 KB
-          bulk_g2s_mc(sa + TC_A_BYTES + crank * share, reinterpret_cast<const uint8_t*>(wsrc) + crank * share, share,
-                      full0 + 8 * it, cmask);
-        }
+        mbar_expect_tx(full0 + 8 * it, PL * (TC_A_BYTES + cnt * TC_B_BYTES));
+        bulk_g2s(sa, a_tile + (size_t)kc * (8192 * PL), PL * TC_A_BYTES, full0 + 8 * it);     // X3: hi and lo planes, contiguous
+        bulk_g2s(sa + PL * TC_A_BYTES, wsrc, cnt * TC_B_BYTES, full0 + 8 * it);
+        if (X3)
+          bulk_g2s(sa + PL * TC_A_BYTES + cnt * TC_B_BYTES, Wp_lo + (size_t)p.gslot[g][kc] * 4096, cnt * TC_B_BYTES, full0 + 8 * it);
         TC_STAMP(17 + 4 * it);
       }
       __syncwarp();
@@ -208,8 +209,10 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
       const int nr = (int)(rw >> 60);
       mbar_wait(full0 + 8 * it, 0u);
       tc_fence_after();
-      const uint32_t sa = sbase + TC_S_OFF(s) * TC_B_BYTES, sb = sa + TC_A_BYTES;
+      const uint32_t sa = sbase + TC_S_OFF(s) * TC_B_BYTES, sb = sa + PL * TC_A_BYTES;
+      const uint32_t sb_lo = sb + (uint32_t)__popc(bits) * TC_B_BYTES;               // X3: the lo parts of the panel's blocks
       const uint64_t ad0 = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+      const uint64_t ad0_lo = desc_hi | (uint64_t)(((sa + TC_A_BYTES) >> 4) & 0x3FFF);
       if (lane == 0) TC_STAMP(18 + 4 * it);
 #pragma unroll
       for (int r = 0; r < TC_GMAX; ++r) {
@@ -225,12 +228,18 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
           umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
           umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
           umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+          if (X3) {                                // + a_hi * w_lo + a_lo * w_hi: the fp32-parity products
+            const uint64_t bl0 = desc_hi | (uint64_t)(((sb_lo + rank * TC_B_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) umma_f16(d, ad0 + k, bl0 + k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) umma_f16(d, ad0_lo + k, bd0 + k, idesc, 1u);
+          }
         }
       }
       uint32_t done = TC_S_DONE(s);
       if (elect_one()) {
-        if (CT == 1) umma_commit(empty0 + 8 * it);  // frees the ring space when these MMAs have read it
-        else umma_commit_mc(empty0 + 8 * it, cmask);
+        umma_commit(empty0 + 8 * it);              // frees the ring space when these MMAs have read it
         while (done) {                             // accumulators that received their last block in this iteration
           const int dq = __ffs(done) - 1;
           done &= done - 1;
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
     const int et = threadIdx.x - TC_EPI_T0;          // 0..255
     constexpr int ET = 32 * TC_EPI_WARPS;
     const uint32_t written = p.gwritten[g];
-    uint8_t* stage = sgen + TC_RING_BYTES;           // 2 x 16 KB output tiles (head mode: one fp32 tile)
+    uint8_t* stage = sgen + Geo::RING_BYTES;         // 2 output staging tiles (head mode: one fp32 tile)
     if (p.mode != TC_MODE_DGRAD) {
       for (int c = et; c < G * 64; c += ET) {
         int col = oc0 * 64 + c;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
       }
       asm volatile("bar.sync 4, 256;" ::: "memory");
     }
-    if (p.mode == TC_MODE_HEAD) {
+    if (!X3 && p.mode == TC_MODE_HEAD) {
       // head mode (last layer, models_att.py:765-773): row geometry and the row's xy inputs are fetched while the main
       // loop runs (independent loads, all in flight before the accumulators are read)
       const int64_t pr = (int64_t)tile * LCN_TILE + row;
@@ -323,8 +332,8 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
       const int tig = tile % (p.gstride / LCN_TILE);
       const int nvalid = min(LCN_TILE, p.bn_group - tig * LCN_TILE);
       const float rn = 1.f / (float)nvalid;
-      uint8_t* tile_s = stage + team * TC_A_BYTES;
-      float* red = reinterpret_cast<float*>(stage + 2 * TC_A_BYTES) + team * (4 * 64 * 2);   // [4 warps][64 columns][s1, s2]
+      uint8_t* tile_s = stage + team * Geo::STAGE_BYTES;                       // X3: hi tile, then lo tile
+      float* red = reinterpret_cast<float*>(stage + 2 * Geo::STAGE_BYTES) + team * (4 * 64 * 2);   // [4 warps][64 columns][s1, s2]
       for (int e = team; e < G; e += 2) {
         const int q = p.gorder[g][e];
         const bool has = (written >> q) & 1u;
@@ -363,18 +372,20 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
             }
           } else if (addend != nullptr) {
             const uint8_t* arow = reinterpret_cast<const uint8_t*>(addend) +
-                                  (((size_t)tile * p.NCN + oc0 + q) * 128 + row) * 128;
+                                  ((((size_t)tile * p.NCN + oc0 + q) * PL) * 128 + row) * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 u = *reinterpret_cast<const uint4*>(arow + (((h * 4 + c) ^ (row & 7)) << 4));
-              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+            for (int pl = 0; pl < PL; ++pl)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float2 t = __bfloat1622float2(hp[k]);
-                f[c * 8 + 2 * k] += t.x;
-                f[c * 8 + 2 * k + 1] += t.y;
+              for (int c = 0; c < 4; ++c) {
+                uint4 u = *reinterpret_cast<const uint4*>(arow + pl * TC_A_BYTES + (((h * 4 + c) ^ (row & 7)) << 4));
+                const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 t = __bfloat1622float2(hp[k]);
+                  f[c * 8 + 2 * k] += t.x;
+                  f[c * 8 + 2 * k + 1] += t.y;
+                }
               }
-            }
           }
           // pack to bf16 and store the row's 4 sixteen-byte chunks into the swizzled staging tile
 #pragma unroll
@@ -389,6 +400,19 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
             u.z = *reinterpret_cast<uint32_t*>(&b2);
             u.w = *reinterpret_cast<uint32_t*>(&b3);
             *reinterpret_cast<uint4*>(tile_s + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = u;
+            if (X3) {                              // lo = bf16(f - hi): the second plane of the split-bf16 tile
+              const float2 h0 = __bfloat1622float2(b0), h1 = __bfloat1622float2(b1), h2 = __bfloat1622float2(b2), h3 = __bfloat1622float2(b3);
+              __nv_bfloat162 l0 = __floats2bfloat162_rn(f[c * 8 + 0] - h0.x, f[c * 8 + 1] - h0.y);
+              __nv_bfloat162 l1 = __floats2bfloat162_rn(f[c * 8 + 2] - h1.x, f[c * 8 + 3] - h1.y);
+              __nv_bfloat162 l2 = __floats2bfloat162_rn(f[c * 8 + 4] - h2.x, f[c * 8 + 5] - h2.y);
+              __nv_bfloat162 l3 = __floats2bfloat162_rn(f[c * 8 + 6] - h3.x, f[c * 8 + 7] - h3.y);
+              uint4 ul;
+              ul.x = *reinterpret_cast<uint32_t*>(&l0);
+              ul.y = *reinterpret_cast<uint32_t*>(&l1);
+              ul.z = *reinterpret_cast<uint32_t*>(&l2);
+              ul.w = *reinterpret_cast<uint32_t*>(&l3);
+              *reinterpret_cast<uint4*>(tile_s + TC_A_BYTES + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = ul;
+            }
           }
         }
         if (tt == 0) TC_STAMP(202 + 8 * e);
@@ -397,7 +421,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the 4 warps of the team
         if (tt == 0) {
           TC_STAMP(203 + 8 * e);
-          bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * 8192, smem_u32(tile_s), TC_A_BYTES);
+          bulk_s2g(Y + ((size_t)tile * p.NCN + oc0 + q) * (8192 * PL), smem_u32(tile_s), PL * TC_A_BYTES);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (p.mode == TC_MODE_FWD && (part != nullptr || p.fuse_on)) {
@@ -407,12 +431,14 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
           // Constant trip count: all 32 loads of the lane are in flight before the first add.
           const uint32_t coff = (uint32_t)(lane & 3) * 4;
           const int chunk = lane >> 2;
-          uint32_t w[32];
+          uint32_t w[32], wl[X3 ? 32 : 1];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int r = lq + 4 * i;
             w[i] = *reinterpret_cast<const uint32_t*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
+            if (X3) wl[i] = *reinterpret_cast<const uint32_t*>(tile_s + TC_A_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4) + coff);
           }
+          // the shift is the row-0 value of the hi plane in both instantiations (any common shift works)
           const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile_s + (chunk << 4) + coff);
           const float2 sh2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
           float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
@@ -420,6 +446,10 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
           for (int i = 0; i < 32; ++i) {
             if (lq + 4 * i < nvalid) {
               float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              if (X3) {
+                const float2 tl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl[i]));
+                t.x += tl.x; t.y += tl.y;
+              }
               float d0 = t.x - sh2.x, d1 = t.y - sh2.y;
               s1a += d0; s2a = fmaf(d0, d0, s2a);
               s1b += d1; s2b = fmaf(d1, d1, s2b);
@@ -464,7 +494,6 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
   }
   tc_fence_before();
   __syncthreads();
-  if (CT > 1) cluster_sync_all();          // no CTA leaves while peers may still multicast into it or arrive on its barriers
   if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
@@ -472,50 +501,26 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) k_tc_gemm(const __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-bool lcn_tc_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LCN_DISABLE_TC");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* addend,
-                          __nv_bfloat16* Y, float* part, const TcParams& p, int tiles, cudaStream_t st) {
-  static bool attr = false;
-  static int ct_env = 1;
-  if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    const char* e = getenv("LCN_TC_CLUSTER");              // row tiles per cluster sharing the weight panels: 1, 2 or 4
-    ct_env = e ? atoi(e) : 1;
-    if (ct_env != 2 && ct_env != 4) ct_env = 1;
-    attr = true;
-  }
-  int ct = ct_env;
-  while (ct > 1 && tiles % ct) ct >>= 1;
-  if (ct == 1) {
-    lcn_launch(k_tc_gemm, dim3(dim3(p.n_groups, tiles)), dim3(TC_GEMM_THREADS), (size_t)TC_SMEM_BYTES, st, A, W, bias, addend, Y, part, p);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(p.n_groups, tiles);
-    cfg.blockDim = dim3(TC_GEMM_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1;
-    at[0].val.clusterDim.y = (unsigned)ct;
-    at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = lcn_pdl_enabled() ? 2 : 1;
-    (void)cudaLaunchKernelEx(&cfg, k_tc_gemm, A, W, bias, addend, Y, part, p);
-  }
+template <bool X3>
+static int launch_tc_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const __nv_bfloat16* Wlo, const float* bias,
+                            const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, const TcParams& p, int tiles,
+                            cudaStream_t st) {
+  static std::once_flag once;              // thread-safe one-time attribute setup (include/lcn_b200.h: re-entrancy)
+  static cudaError_t rc = cudaSuccess;
+  std::call_once(once, [] {
+    rc = cudaFuncSetAttribute(k_tc_gemm<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcGeo<X3>::SMEM_BYTES);
+  });
+  LCN_CHECK_CUDA(rc);
+  lcn_launch(k_tc_gemm<X3>, dim3(dim3(p.n_groups, tiles)), dim3(TC_GEMM_THREADS), (size_t)TcGeo<X3>::SMEM_BYTES, st, A, W, Wlo,
+             bias, addend, Y, part, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
+}
+static int launch_tc_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const __nv_bfloat16* Wlo, const float* bias,
+                          const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, const TcParams& p, int tiles,
+                          cudaStream_t st) {
+  return Wlo != nullptr ? launch_tc_gemm_t<true>(A, W, Wlo, bias, addend, Y, part, p, tiles, st)
+                        : launch_tc_gemm_t<false>(A, W, nullptr, bias, addend, Y, part, p, tiles, st);
 }
 
 // blocks under N-side chunk oc (= K chunks with a block into it)
@@ -562,7 +567,7 @@ static int tc_partition(const TcParams& p, int ng, uint8_t* goc0) {
 //          `wait` = the newest earlier iteration whose units it overwrites (MMAs retire in order, so waiting for that
 //          one's empty barrier covers all older ones);
 //   slot : position of the iteration's first block in the packed panel (k_pack_mid order).
-static void tc_fill_schedule(TcParams& p) {
+static void tc_fill_schedule(TcParams& p, bool x3) {
   memset(p.sched, 0, sizeof(p.sched));
   memset(p.runs, 0, sizeof(p.runs));
   memset(p.gslot, 0, sizeof(p.gslot));
@@ -676,8 +681,9 @@ static void tc_fill_schedule(TcParams& p) {
     int head = 0, first_live = 0;
     int off[TC_MAX_CHUNKS], need[TC_MAX_CHUNKS];
     for (int it = 0; it < n_it; ++it) {
-      need[it] = 2 + __builtin_popcount(kbits[order[it]]);
-      if (head + need[it] > TC_RING_UNITS) head = 0;
+      need[it] = x3 ? TcGeo<true>::A_UNITS + 2 * __builtin_popcount(kbits[order[it]])
+                    : TcGeo<false>::A_UNITS + __builtin_popcount(kbits[order[it]]);
+      if (head + need[it] > (x3 ? TcGeo<true>::RING_UNITS : TcGeo<false>::RING_UNITS)) head = 0;
       off[it] = head;
       int wait = -1;
       for (int j = first_live; j < it; ++j)
@@ -691,7 +697,7 @@ static void tc_fill_schedule(TcParams& p) {
 }
 
 // choose the number of groups (whole waves of sm_count CTAs, minimal waves x per-CTA time), partition, fill the schedule
-static void tc_make_schedule(TcParams& p, int tiles, int sm_count, int force) {
+static void tc_make_schedule(TcParams& p, int tiles, int sm_count, bool x3) {
   int best_ng = p.NCN;
   double best = 1e30;
   uint8_t goc0[TC_MAX_CHUNKS + 1];
@@ -705,22 +711,17 @@ static void tc_make_schedule(TcParams& p, int tiles, int sm_count, int force) {
     double c = (double)waves * (maxblk + 1.5 * gmax + 8.0);
     if (c < best - 1e-9) { best = c; best_ng = ng; }
   }
-  if (force > 0 && (p.NCN + force - 1) / force <= TC_GMAX) best_ng = force < p.NCN ? force : p.NCN;
   p.n_groups = best_ng;
   tc_partition(p, best_ng, p.goc0);
-  tc_fill_schedule(p);
+  tc_fill_schedule(p, x3);
 }
 
 // Pick the N-side grouping.  One CTA is resident per SM (TMEM kernels), so the grid should be whole waves of
 // sm_count CTAs: choose the number of chunk groups that minimises waves x (work per CTA + fixed per-CTA cost).
-static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
+static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const __nv_bfloat16* Wlo, const float* bias,
                            const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part, TcParams& p, int tiles,
                            int sm_count, cudaStream_t st) {
-  static int force = -1;
-  if (force < 0) {
-    const char* e = getenv("LCN_TC_GROUPS");
-    force = e ? atoi(e) : 0;
-  }
+  const int force = Wlo != nullptr ? 1 : 0;          // cache key: the ring geometry of the split-bf16 instantiation differs
   // The grouping and its schedule depend only on (mask, chunk geometry, tiles, SM count): computed once, then
   // served from a small cache (the launch path must stay cheap: it runs ~20 times per train step).
   struct Entry { uint32_t kmask[LCN_J]; int FCK, FCN, NCK, NCN, tiles, sm, force; TcParams sched; };
@@ -737,7 +738,7 @@ static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const
       memcpy(e.kmask, p.kmask, sizeof(e.kmask));
       e.FCK = p.FCK; e.FCN = p.FCN; e.NCK = p.NCK; e.NCN = p.NCN; e.tiles = tiles; e.sm = sm_count; e.force = force;
       e.sched = p;
-      tc_make_schedule(e.sched, tiles, sm_count, force);
+      tc_make_schedule(e.sched, tiles, sm_count, force != 0);
       cache.push_back(e);
       hit = &cache.back();
     }
@@ -751,7 +752,7 @@ static int pick_and_launch(const __nv_bfloat16* A, const __nv_bfloat16* W, const
     memcpy(p.gdcnt, hit->sched.gdcnt, sizeof(p.gdcnt));
     memcpy(p.goc0, hit->sched.goc0, sizeof(p.goc0));
   }
-  return launch_tc_gemm(A, W, bias, addend, Y, part, p, tiles, st);
+  return launch_tc_gemm(A, W, Wlo, bias, addend, Y, part, p, tiles, st);
 }
 
 // schedule of the knn-masked mid layer for inspection / tests (host only): returns the number of groups and fills, per
@@ -764,7 +765,7 @@ extern "C" int lcn_debug_tc_schedule(const uint32_t* kmask17, int FC, int tiles,
   for (int a = 0; a < LCN_J; ++a) p.kmask[a] = kmask17[a];
   p.FCK = p.FCN = FC;
   p.NCK = p.NCN = LCN_J * FC;
-  tc_make_schedule(p, tiles, sm_count, 0);
+  tc_make_schedule(p, tiles, sm_count, false);
   memcpy(sched_out, p.sched, sizeof(p.sched));
   memcpy(nit_out, p.gnit, sizeof(p.gnit));
   memcpy(goc0_out, p.goc0, sizeof(p.goc0));
@@ -776,7 +777,7 @@ extern "C" int lcn_debug_tc_schedule(const uint32_t* kmask17, int FC, int tiles,
 
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed, const __nv_bfloat16* A,
                 const char* wpacked, const float* bias, const __nv_bfloat16* addend, __nv_bfloat16* Y, float* part,
-                cudaStream_t st, const TcFuse* fuse, int* fused) {
+                cudaStream_t st, const TcFuse* fuse, int* fused, const char* wpacked_lo) {
   (void)mid_index;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -789,16 +790,11 @@ int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int tran
   p.mode = transposed ? TC_MODE_DGRAD : TC_MODE_FWD;
   if (fused) *fused = 0;
   if (fuse != nullptr && !transposed && lay.n_groups == 1) {
-    static int on = -1;                // LCN_FUSED_BNSTATS=0: per-tile partials + k_bn_finalize as on the other paths
-    if (on < 0) {
-      const char* e = getenv("LCN_FUSED_BNSTATS");
-      on = (e && e[0] == '0') ? 0 : 1;
-    }
     p.fuse = *fuse;
-    p.fuse_on = on;
+    p.fuse_on = 1;
   }
-  int rc = pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, addend, Y, part, p, lay.tiles,
-                           m->sm_count, st);
+  int rc = pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), reinterpret_cast<const __nv_bfloat16*>(wpacked_lo),
+                           bias, addend, Y, part, p, lay.tiles, m->sm_count, st);
   if (fused) *fused = p.fuse_on;
   return rc;
 }
@@ -823,7 +819,7 @@ int lcn_tc_head(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A,
   p.n_rows = lay.n_rows;
   p.out_user = out_user;
   p.out_ws = out_ws;
-  return pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), bias, nullptr, nullptr, nullptr, p,
+  return pick_and_launch(A, reinterpret_cast<const __nv_bfloat16*>(wpacked), nullptr, bias, nullptr, nullptr, nullptr, p,
                          lay.tiles, m->sm_count, st);
 }
 
@@ -841,7 +837,7 @@ int lcn_tc_head_dgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat
   p.bn_group = lay.bn_group;
   p.gstride = lay.gstride;
   p.mode = TC_MODE_DGRAD;
-  return pick_and_launch(dOut16, reinterpret_cast<const __nv_bfloat16*>(wpacked), nullptr, nullptr, dA, nullptr, p,
+  return pick_and_launch(dOut16, reinterpret_cast<const __nv_bfloat16*>(wpacked), nullptr, nullptr, nullptr, dA, nullptr, p,
                          lay.tiles, m->sm_count, st);
 }
 
@@ -887,6 +883,9 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src, ui
                : "memory");
 }
 
+// X3 (split-bf16 operands, lcn_internal.cuh): the K loop runs three times per half tile -- (A_hi, dZ_hi), (A_hi, dZ_lo),
+// (A_lo, dZ_hi) -- into the same accumulators; the planes of a tile are adjacent in HBM / L2.
+template <bool X3>
 __global__ void __launch_bounds__(TCW_THREADS) k_tc_wgrad(const __nv_bfloat16* __restrict__ A,
                                                           const __nv_bfloat16* __restrict__ dZ,
                                                           float* __restrict__ dW, const __grid_constant__ TcwParams p) {
@@ -928,21 +927,24 @@ __global__ void __launch_bounds__(TCW_THREADS) k_tc_wgrad(const __nv_bfloat16* _
   if (warp >= 1) asm volatile("bar.sync 3, %0;" ::"n"(TCW_THREADS - 32) : "memory");
   lcn_pdl_wait();                 // the previous kernel's outputs are visible from here on
 
-  const int n_it = 2 * (t1 - t0);                  // two 64-row half tiles per 128-row tile
+  constexpr int PL = X3 ? 2 : 1, NPASS = X3 ? 3 : 1;
+  const int n_it = NPASS * 2 * (t1 - t0);          // two 64-row half tiles per 128-row tile (x 3 operand-plane passes)
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < n_it; ++it) {
         int s = it % TCW_STAGES;
         uint32_t ph = (uint32_t)(it / TCW_STAGES) & 1u;
-        int t = t0 + (it >> 1), half = it & 1;
+        const int ih = it / NPASS, pass = it - ih * NPASS;
+        int t = t0 + (ih >> 1), half = ih & 1;
+        const size_t pa = pass == 2 ? 8192 : 0, pz = pass == 1 ? 8192 : 0;   // plane offsets (elements): lo follows hi
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         uint32_t sa = sbase + s * TCW_STAGE_BYTES;
         mbar_expect_tx(full0 + 8 * s, (na + len) * TCW_HALF_BYTES);
-        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic0) * 8192 + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
+        bulk_g2s(sa, A + ((size_t)t * p.NCK + ic0) * (8192 * PL) + pa + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
         if (na == 2)
-          bulk_g2s(sa + TCW_HALF_BYTES, A + ((size_t)t * p.NCK + ic1) * 8192 + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
+          bulk_g2s(sa + TCW_HALF_BYTES, A + ((size_t)t * p.NCK + ic1) * (8192 * PL) + pa + half * 4096, TCW_HALF_BYTES, full0 + 8 * s);
         for (int q = 0; q < len; ++q)
-          bulk_g2s(sa + (2 + q) * TCW_HALF_BYTES, dZ + ((size_t)t * p.NCN + u.oc[q]) * 8192 + half * 4096,
+          bulk_g2s(sa + (2 + q) * TCW_HALF_BYTES, dZ + ((size_t)t * p.NCN + u.oc[q]) * (8192 * PL) + pz + half * 4096,
                    TCW_HALF_BYTES, full0 + 8 * s);
       }
     }
@@ -1075,43 +1077,41 @@ extern "C" int lcn_debug_tcw_units(const uint32_t* row17, int FCK, int FCN, int 
 }
 
 static int launch_tc_wgrad(TcwParams& p, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW, int tiles,
-                           int sm_count, cudaStream_t st) {
+                           int sm_count, cudaStream_t st, bool x3 = false) {
   tcw_build_units(p);
   const int units = p.n_units;
   p.tiles = tiles;
   // One CTA is resident per SM (TMEM kernels: profiles/micro/occ.cu): the row range per CTA is the smallest for which
   // the grid is a single wave.  LCN_TCW_SLOTS overrides the slot count for experiments.
-  static int slots_env = -1;
-  if (slots_env < 0) {
-    const char* e = getenv("LCN_TCW_SLOTS");
-    slots_env = e ? atoi(e) : 0;
-  }
-  int slots = slots_env > 0 ? slots_env : sm_count;
+  int slots = sm_count;
   int tpc = 1;
   while (tpc < tiles && (long)units * ((tiles + tpc - 1) / tpc) > slots) ++tpc;
   p.tiles_per_cta = tpc;
   int splits = (tiles + tpc - 1) / tpc;
   size_t smem = (size_t)TCW_STAGES * TCW_STAGE_BYTES + 1024;
-  static bool attr = false;
-  if (!attr) {
-    LCN_CHECK_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  lcn_launch(k_tc_wgrad, dim3(dim3(units, splits)), dim3(TCW_THREADS), smem, st, A, dZ, dW, p);
+  static std::once_flag once;
+  static cudaError_t rc = cudaSuccess;
+  std::call_once(once, [smem] {
+    rc = cudaFuncSetAttribute(k_tc_wgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_tc_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  LCN_CHECK_CUDA(rc);
+  if (x3) lcn_launch(k_tc_wgrad<true>, dim3(dim3(units, splits)), dim3(TCW_THREADS), smem, st, A, dZ, dW, p);
+  else lcn_launch(k_tc_wgrad<false>, dim3(dim3(units, splits)), dim3(TCW_THREADS), smem, st, A, dZ, dW, p);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
 
 // mid layers: dWm (dense [P,P], only the nonzero blocks are touched)
 int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ, float* dW,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool x3) {
   TcwParams p;
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < LCN_J; ++i) p.row[i] = m->sup.row[i];
   p.FCK = p.FCN = m->FC;
   p.NCK = p.NCN = LCN_J * m->FC;
   p.ldw = m->P;
-  return launch_tc_wgrad(p, A, dZ, dW, lay.tiles, m->sm_count, st);
+  return launch_tc_wgrad(p, A, dZ, dW, lay.tiles, m->sm_count, st, x3);
 }
 // last layer: dW4pad[P][64] += A_L^T dOut16 (one N chunk: 51 columns padded to 64)
 int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dOut16,

@@ -113,6 +113,7 @@ struct WsLayout {
   size_t off_wm_first, off_wm_last;  // dense masked fp32 effective weights of the edge layers
   size_t off_wp32;                   // fp32 packed mid-layer blocks  [mid][pair][FC][FC][64][64]
   size_t off_wp16f, off_wp16b;       // bf16 UMMA-layout packed blocks (forward / transposed)
+  size_t off_wp16f_lo, off_wp16b_lo; // their lo parts (split-bf16 path only)
   size_t off_wl16f, off_wl16b;       // bf16 packed last-layer weights: per K chunk [64 n][64 k] / per N chunk
   size_t off_wf16;                   // bf16 packed first-layer weights: per N chunk [64 n][64 k (17*in_F used)]
   size_t off_x16, off_dout16;        // bf16 tiles of the 2D input / of dOut (64-column padded), training
@@ -296,11 +297,14 @@ struct TcFuse {
 // tcgen05 (bf16) mid-layer kernels, lcn_gemm_tc.cu.  transposed=0: Y = A*Wm (+bias, BN partials);
 // transposed=1: dA = dZ*Wm^T (+addend).  fuse != nullptr (forward, one BatchNorm group): *fused = 1 if the statistics
 // went to fuse->gacc (the caller skips k_bn_finalize and hands gacc to k_bn_act_pre), 0: per-tile partials as usual.
+// x3: split-bf16 operands (A / addend / Y are lcn_sp16 buffers, wpacked_lo holds the lo parts of the packed weights):
+// three tensor-core products per block, fp32-parity results.
 int lcn_tc_gemm(const lcn_model* m, const WsLayout& lay, int mid_index, int transposed,
                 const __nv_bfloat16* A, const char* wpacked, const float* bias, const __nv_bfloat16* addend,
-                __nv_bfloat16* Y, float* part, cudaStream_t st, const TcFuse* fuse = nullptr, int* fused = nullptr);
+                __nv_bfloat16* Y, float* part, cudaStream_t st, const TcFuse* fuse = nullptr, int* fused = nullptr,
+                const char* wpacked_lo = nullptr);
 int lcn_tc_wgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const __nv_bfloat16* dZ,
-                 float* dW /* dense [P,P] */, cudaStream_t st);
+                 float* dW /* dense [P,P] */, cudaStream_t st, bool x3 = false);
 int lcn_tc_head(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* A, const char* wpacked,
                 const float* bias, const float* x, float* out_user, float* out_ws, cudaStream_t st);
 int lcn_tc_head_dgrad(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* dOut16, const char* wpacked,
@@ -309,7 +313,6 @@ int lcn_tc_wgrad_last(const lcn_model* m, const WsLayout& lay, const __nv_bfloat
                       float* dWpad, cudaStream_t st);
 int lcn_tc_wgrad_first(const lcn_model* m, const WsLayout& lay, const __nv_bfloat16* X16, const __nv_bfloat16* dZ,
                        float* dWpad, cudaStream_t st);
-bool lcn_tc_enabled();
 
 // fused whole-stack inference kernel (lcn_stack_tc.cu): one thread-block cluster per BatchNorm group
 bool lcn_stack_eligible(const lcn_model* m, int bn_group, int training);
@@ -343,6 +346,37 @@ __device__ __forceinline__ size_t lcn_off<__nv_bfloat16>(int64_t row, int col, i
   return (tile * 128 + r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
 }
 
+// Split-bf16 storage of an fp32 value: v ~ hi + lo with hi = bf16(v), lo = bf16(v - hi) (16 significand bits, relative
+// error <= 2^-17).  This is the activation type of the fp32-PARITY tensor-core path (LCN_PATH_FP32): a product
+// a * w is formed on the tensor cores as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM (the dropped
+// lo*lo term is <= 2^-18 relative), which holds the 1e-4 per-layer tolerance of the north_star with two orders of
+// magnitude to spare (measured: DESIGN.md section 4.5) where single-pass TF32 (10-bit mantissa) does not.
+// Layout: the bf16 tile-major layout with the hi and lo planes of each (128-row tile, 64-channel chunk) block stored
+// back to back (hi block at 2b, lo block at 2b+1): a GEMM operand tile is still ONE contiguous bulk copy (32 KB), and
+// an element's lo part sits 8192 elements behind its hi part.  The type is a tag: pointers to it index bf16 elements.
+struct lcn_sp16 {
+  __nv_bfloat16 h;
+};
+#define LCN_SP_LO 8192        // element distance from the hi part to the lo part
+template <>
+__device__ __forceinline__ size_t lcn_off<lcn_sp16>(int64_t row, int col, int P) {
+  int r = (int)(row & 127), k = col & 63;
+  size_t tile = ((size_t)(row >> 7) * (P >> 6) + (col >> 6)) * 2;
+  return (tile * 128 + r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
+}
+__device__ __forceinline__ void lcn_sp_split(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ float lcn_ld(const lcn_sp16* p, size_t i) {
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
+  return __bfloat162float(q[i]) + __bfloat162float(q[i + LCN_SP_LO]);
+}
+__device__ __forceinline__ void lcn_st(lcn_sp16* p, size_t i, float v) {
+  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p);
+  lcn_sp_split(v, q[i], q[i + LCN_SP_LO]);
+}
+
 // 4-wide vector access (16 B for fp32, 8 B for bf16); i is the element index, multiple of 4
 __device__ __forceinline__ float4 lcn_ld4(const float* p, size_t i) {
   return *reinterpret_cast<const float4*>(p + i);
@@ -364,6 +398,23 @@ __device__ __forceinline__ void lcn_st4(__nv_bfloat16* p, size_t i, float4 v) {
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p + i) = u;
+}
+
+__device__ __forceinline__ float4 lcn_ld4(const lcn_sp16* p, size_t i) {
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
+  float4 a = lcn_ld4(q, i), b = lcn_ld4(q, i + LCN_SP_LO);
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ void lcn_st4(lcn_sp16* p, size_t i, float4 v) {
+  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p);
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  uint2 uh, ul;
+  uh.x = *reinterpret_cast<uint32_t*>(&h0); uh.y = *reinterpret_cast<uint32_t*>(&h1);
+  ul.x = *reinterpret_cast<uint32_t*>(&l0); ul.y = *reinterpret_cast<uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(q + i) = uh;
+  *reinterpret_cast<uint2*>(q + i + LCN_SP_LO) = ul;
 }
 
 // 4-wide access into float arrays
@@ -404,6 +455,31 @@ __device__ __forceinline__ void lcn_st8(__nv_bfloat16* p, size_t i, const float 
   u.z = *reinterpret_cast<uint32_t*>(&b2);
   u.w = *reinterpret_cast<uint32_t*>(&b3);
   *reinterpret_cast<uint4*>(p + i) = u;
+}
+
+__device__ __forceinline__ void lcn_ld8(const lcn_sp16* p, size_t i, float v[8]) {
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
+  float lo[8];
+  lcn_ld8(q, i, v);
+  lcn_ld8(q, i + LCN_SP_LO, lo);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] += lo[e];
+}
+__device__ __forceinline__ void lcn_st8(lcn_sp16* p, size_t i, const float v[8]) {
+  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p);
+  uint4 uh, ul;
+  uint32_t* ph = reinterpret_cast<uint32_t*>(&uh);
+  uint32_t* pl = reinterpret_cast<uint32_t*>(&ul);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    float2 f = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+    ph[e] = *reinterpret_cast<uint32_t*>(&h);
+    pl[e] = *reinterpret_cast<uint32_t*>(&l);
+  }
+  *reinterpret_cast<uint4*>(q + i) = uh;
+  *reinterpret_cast<uint4*>(q + i + LCN_SP_LO) = ul;
 }
 
 // Philox4x32-10 counter-based generator; one call yields 128 random bits (lcn_keep8: the keep bits of 8 elements).

@@ -10,8 +10,19 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "lcn_internal.cuh"
+
+// Activation types of the two arithmetic paths (include/lcn_b200.h): __nv_bfloat16 = LCN_PATH_BF16 (every GEMM on the
+// tensor cores, fused BatchNorm statistics, tensor-core edge layers), lcn_sp16 = LCN_PATH_FP32 (split-bf16 storage,
+// three tensor-core products per block: fp32 parity; the K = 17*in_F first layer and the N = 51 head stay on CUDA cores,
+// < 1.3 % of the FLOPs).  There is no CUDA-core GEMM for the mid layers any more.
+template <typename T>
+struct PathTraits {
+  static constexpr bool bf16 = std::is_same<T, __nv_bfloat16>::value;
+  static constexpr bool x3 = std::is_same<T, lcn_sp16>::value;
+};
 
 struct LinTable {
   int n;
@@ -132,7 +143,8 @@ __global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ para
                                                   SupportBits sup, const LayerScalars* sc,
                                                   const float* __restrict__ mask, int F, int FC, int nnz,
                                                   float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
-                                                  __nv_bfloat16* __restrict__ wp16b, int write32, int write16) {
+                                                  __nv_bfloat16* __restrict__ wp16b, __nv_bfloat16* __restrict__ wp16f_lo,
+                                                  __nv_bfloat16* __restrict__ wp16b_lo, int write32, int write16) {
   lcn_pdl_prologue();
   __shared__ float tile[64][65];     // tile[fi][fo], scaled
   int mid = blockIdx.y, l = mid + 1;
@@ -164,6 +176,9 @@ __global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ para
   size_t slot_b = (size_t)FC * FC * base_j + (size_t)ho * (cnt_in * FC) + rank_in * FC + hi;
   uint4* df = reinterpret_cast<uint4*>(wp16f + ((size_t)mid * mid_sb + slot_f) * 4096);
   uint4* db = reinterpret_cast<uint4*>(wp16b + ((size_t)mid * mid_sb + slot_b) * 4096);
+  // split-bf16 path: the lo parts w - bf16(w) of the same blocks, same layout, separate arrays
+  uint4* dfl = wp16f_lo ? reinterpret_cast<uint4*>(wp16f_lo + ((size_t)mid * mid_sb + slot_f) * 4096) : nullptr;
+  uint4* dbl = wp16b_lo ? reinterpret_cast<uint4*>(wp16b_lo + ((size_t)mid * mid_sb + slot_b) * 4096) : nullptr;
   for (int e = threadIdx.x; e < 512; e += 256) {          // one 16-byte chunk (8 bf16) per store
     int n = e >> 3, kc = e & 7;
     __nv_bfloat162 hf[4], hb[4];
@@ -174,6 +189,17 @@ __global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ para
     }
     df[n * 8 + (kc ^ (n & 7))] = *reinterpret_cast<uint4*>(hf);
     db[n * 8 + (kc ^ (n & 7))] = *reinterpret_cast<uint4*>(hb);
+    if (dfl != nullptr) {
+      __nv_bfloat162 lf[4], lb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(hf[q]), b = __bfloat1622float2(hb[q]);
+        lf[q] = __floats2bfloat162_rn(tile[kc * 8 + 2 * q][n] - f.x, tile[kc * 8 + 2 * q + 1][n] - f.y);
+        lb[q] = __floats2bfloat162_rn(tile[n][kc * 8 + 2 * q] - b.x, tile[n][kc * 8 + 2 * q + 1] - b.y);
+      }
+      dfl[n * 8 + (kc ^ (n & 7))] = *reinterpret_cast<uint4*>(lf);
+      dbl[n * 8 + (kc ^ (n & 7))] = *reinterpret_cast<uint4*>(lb);
+    }
   }
 }
 
@@ -241,7 +267,8 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
   LCN_CHECK_LAUNCH();
   int last = m->n_lin - 1;
   int n_mid = m->n_lin - 2;
-  const bool use_tc = m->d.path == LCN_PATH_BF16;
+  const bool use_tc = true;                          // both paths run the mid layers on the tensor cores
+  const bool x3 = m->d.path == LCN_PATH_FP32;
   // the edge-layer packs (four small dependent launches) run on the model's side stream next to the mid-layer pack
   std::unique_lock<std::mutex> aux_lock;
   LcnAux* ax = nullptr;
@@ -267,7 +294,10 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
     lcn_launch(k_pack_mid, dim3(dim3(m->nnz * m->FC * m->FC, n_mid)), dim3(256), 0, st, 
         params, lt, make_pairs(m), m->sup, sc, mask, m->d.F, m->FC, m->nnz,
         reinterpret_cast<float*>(ws + lay.off_wp32), reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f),
-        reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b), use_tc ? 0 : 1, use_tc ? 1 : 0);
+        reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b),
+        x3 ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f_lo) : nullptr,
+        x3 ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b_lo) : nullptr,
+        x3 ? 1 : 0 /* fp32 copy: the parity tap of the fp32-parity path (lcn_model_read_tensor kind 2) */, 1);
   }
   lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
                                   reinterpret_cast<float*>(ws + lay.off_wm_last));
@@ -422,131 +452,9 @@ __global__ void __launch_bounds__(256) k_first_layer(const float* __restrict__ x
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// fp32 block-sparse GEMM of the mid layers (CUDA cores).
-//   TRANSPOSED = false: Z[tile, oc] = sum_{i in N(j)} A[tile, i-chunks] * Wp(i->j) + bias, BN partials
-//   TRANSPOSED = true : dA[tile, ic] = sum_{j in O(i)} dZ[tile, j-chunks] * Wp(i->j)^T (+ addend)
-// grid (tiles, 17*FC), 256 threads, thread = 8 rows x 4 cols of the 128 x 64 output tile.
-// ------------------------------------------------------------------------------------------------
+// shared-memory pitches of k_last_layer (activation rows / weight rows)
 #define GS_APAD 65
 #define GS_BPAD 68
-template <typename T, bool TRANSPOSED>
-__global__ void __launch_bounds__(256) k_gemm_simt(const T* __restrict__ A, const float* __restrict__ wp32,
-                                                   const float* __restrict__ bias, const T* __restrict__ addend,
-                                                   T* __restrict__ Y, float* __restrict__ part, JointLists lists,
-                                                   int P, int FC, int bn_group, int gstride) {
-  lcn_pdl_prologue();
-  extern __shared__ __align__(16) float smem[];
-  float* As = smem;                          // [128][65]
-  float* Bs = smem + LCN_TILE * GS_APAD;     // [64][68]
-  __shared__ float red[4][64];
-  int tile = blockIdx.x, oc = blockIdx.y;
-  int a = oc / FC, ha = oc % FC;             // joint / sub-chunk owning the output columns
-  int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  size_t row0 = (size_t)tile * LCN_TILE;
-  float acc[8][4];
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-
-  int cnt = lists.cnt[a];
-  for (int n = 0; n < cnt; ++n) {
-    int b = lists.idx[a][n];
-    int p = lists.blk[a][n];
-    for (int h = 0; h < FC; ++h) {
-      int col0 = (b * FC + h) * 64;
-      // sub-block (pair p, hi, ho): forward hi = h (input side), ho = ha; transposed hi = ha, ho = h
-      int hi = TRANSPOSED ? ha : h, ho = TRANSPOSED ? h : ha;
-      const float* blk = wp32 + ((size_t)(p * FC + hi) * FC + ho) * 4096;
-      __syncthreads();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        int f = tid + 256 * it;
-        int r = f >> 4, kq = f & 15;
-        float4 v = lcn_ld4(A, lcn_off<T>(row0 + r, col0 + kq * 4, P));
-        float* dst = As + r * GS_APAD + kq * 4;
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-      }
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        int f = tid + 256 * it;                 // float4 index in the 64x64 block
-        int r = f >> 4, cq = f & 15;
-        float4 v = *reinterpret_cast<const float4*>(blk + r * 64 + cq * 4);
-        if (!TRANSPOSED) {
-          *reinterpret_cast<float4*>(Bs + r * GS_BPAD + cq * 4) = v;   // Bs[k=fi][n=fo]
-        } else {                                                       // Bs[k=fo][n=fi]
-          Bs[(cq * 4 + 0) * GS_BPAD + r] = v.x;
-          Bs[(cq * 4 + 1) * GS_BPAD + r] = v.y;
-          Bs[(cq * 4 + 2) * GS_BPAD + r] = v.z;
-          Bs[(cq * 4 + 3) * GS_BPAD + r] = v.w;
-        }
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int k = 0; k < 64; ++k) {
-        float4 bv = *reinterpret_cast<const float4*>(Bs + k * GS_BPAD + tx * 4);
-        float av[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) av[r] = As[(ty * 8 + r) * GS_APAD + k];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          acc[r][0] = fmaf(av[r], bv.x, acc[r][0]);
-          acc[r][1] = fmaf(av[r], bv.y, acc[r][1]);
-          acc[r][2] = fmaf(av[r], bv.z, acc[r][2]);
-          acc[r][3] = fmaf(av[r], bv.w, acc[r][3]);
-        }
-      }
-    }
-  }
-  int ccol = oc * 64 + tx * 4;
-  if (!TRANSPOSED) {
-    float4 bv = *reinterpret_cast<const float4*>(bias + ccol);
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float4 v = make_float4(acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w);
-      lcn_st4(Y, lcn_off<T>(row0 + ty * 8 + r, ccol, P), v);
-      float* dst = As + (ty * 8 + r) * GS_APAD + tx * 4;
-      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-    }
-    __syncthreads();
-    // exact two-pass column statistics over the valid rows of this tile
-    int tig = tile % (gstride / LCN_TILE);
-    int nvalid = min(LCN_TILE, bn_group - tig * LCN_TILE);
-    int col = tid & 63, prt = tid >> 6;
-    float s = 0.f;
-    for (int r = prt * 32; r < prt * 32 + 32; ++r)
-      if (r < nvalid) s += As[r * GS_APAD + col];
-    red[prt][col] = s;
-    __syncthreads();
-    float mean = (red[0][col] + red[1][col] + red[2][col] + red[3][col]) / (float)nvalid;
-    __syncthreads();
-    float q = 0.f;
-    for (int r = prt * 32; r < prt * 32 + 32; ++r)
-      if (r < nvalid) {
-        float d = As[r * GS_APAD + col] - mean;
-        q = fmaf(d, d, q);
-      }
-    red[prt][col] = q;
-    __syncthreads();
-    if (prt == 0) {
-      float m2 = red[0][col] + red[1][col] + red[2][col] + red[3][col];
-      part[((size_t)tile * P + oc * 64 + col) * 2 + 0] = mean;
-      part[((size_t)tile * P + oc * 64 + col) * 2 + 1] = m2;
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      if (addend != nullptr) {
-        float4 ad = lcn_ld4(addend, lcn_off<T>(row0 + ty * 8 + r, ccol, P));
-        v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
-      }
-      lcn_st4(Y, lcn_off<T>(row0 + ty * 8 + r, ccol, P), v);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics: merge per-tile (mean, M2) partials over the tiles of a group and the 17
@@ -1183,55 +1091,6 @@ __global__ void __launch_bounds__(256) k_db_reduce(const float* __restrict__ dbp
   if (sl == 0 && c < P) graw[lt_b.w_off[l] + c] = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
 }
 
-// ------------------------------------------------------------------------------------------------
-// fp32 weight gradient of the mid layers, nonzero 64x64 sub-blocks only: dWm = A^T dZ (K = rows)
-// grid (nnz*FC*FC, row splits), 256 threads, thread = 4x4 outputs; atomics into the dense dW.
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) k_wgrad_simt(const T* __restrict__ A, const T* __restrict__ dZ,
-                                                    float* __restrict__ dW, PairTable pt, int P, int FC,
-                                                    int rows_per_block) {
-  lcn_pdl_prologue();
-  __shared__ __align__(16) float As[32][64];
-  __shared__ __align__(16) float Ds[32][64];
-  int sb = blockIdx.x;
-  int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
-  int ic = pt.pi[p] * FC + hi, oc = pt.pj[p] * FC + ho;
-  int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  float acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  size_t row0 = (size_t)blockIdx.y * rows_per_block;
-  for (int rc = 0; rc < rows_per_block; rc += 32) {
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      int f = tid + 256 * it;
-      int r = f >> 4, kq = f & 15;
-      *reinterpret_cast<float4*>(&As[r][kq * 4]) = lcn_ld4(A, lcn_off<T>(row0 + rc + r, ic * 64 + kq * 4, P));
-      *reinterpret_cast<float4*>(&Ds[r][kq * 4]) = lcn_ld4(dZ, lcn_off<T>(row0 + rc + r, oc * 64 + kq * 4, P));
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      float4 av = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
-      float4 dv = *reinterpret_cast<const float4*>(&Ds[r][tx * 4]);
-      float a4[4] = {av.x, av.y, av.z, av.w}, d4[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], d4[b], acc[a][b]);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      atomicAdd(&dW[(size_t)(ic * 64 + ty * 4 + a) * P + oc * 64 + tx * 4 + b], acc[a][b]);
-}
-
 // first layer weight gradient: dWm1[k][c] = sum_rows X[row][k] dZ0[row][c]  (dense 17*in_F x P)
 template <typename T, int IN_F>
 __global__ void __launch_bounds__(256) k_first_wgrad(const float* __restrict__ x, int64_t n_rows,
@@ -1575,27 +1434,25 @@ static int forward_impl(const FwdArgs& a) {
   const int P = m->P, F = m->d.F, FC = m->FC;
   RowGeom g{lay.n_rows, lay.bn_group, lay.gstride};
   float* part = reinterpret_cast<float*>(ws + lay.off_part);
-  const bool tc = sizeof(T) == 2;
+  constexpr bool kBf = PathTraits<T>::bf16, kX3 = PathTraits<T>::x3;
   size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
   static std::once_flag attr_once;                 // one per instantiation; thread safe (header: re-entrancy)
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [&] {
-    attr_rc = cudaFuncSetAttribute(k_gemm_simt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
-    if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(k_gemm_simt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
-    if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(k_last_layer<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+    attr_rc = cudaFuncSetAttribute(k_last_layer<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
   });
   LCN_CHECK_CUDA(attr_rc);
   int n_bn = m->n_bn;
   // training at one BatchNorm group on the tensor-core path: the mid-layer GEMMs accumulate the BatchNorm statistics
   // themselves (TcFuse, lcn_gemm_tc.cu) and k_bn_act_pre finalises them; the accumulators are cleared here, once per pass
   bool pre_ok = false;                 // k_bn_act_pre eligible (same test as below): it is the kernel that accepts gacc
-  if constexpr (sizeof(T) == 2) {
+  if constexpr (kBf) {
     const int ewy0 = (P / 8) * 2 <= EW_MAXT ? 2 : 1;
     const int grid0 = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy0);
     const int per0 = (int)(((lay.rows_pad / ewy0 + grid0 - 1) / grid0) * ewy0);
     pre_ok = lay.n_groups == 1 && per0 <= BA_R * ewy0;
   }
-  const bool try_fuse = tc && lay.training && lay.n_groups == 1 && pre_ok;
+  const bool try_fuse = kBf && lay.training && lay.n_groups == 1 && pre_ok;
   if (try_fuse) LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_gacc, 0, lay.gacc_stride * (size_t)n_bn, st));
   const int lb = a.layer_begin, le = a.layer_end < 0 ? m->n_lin : a.layer_end;   // linear layers [lb, le)
   for (int l = lb; l < n_bn && l < le; ++l) {
@@ -1606,7 +1463,7 @@ static int forward_impl(const FwdArgs& a) {
     if (l == 0) {
       dim3 grid(lay.tiles, P / 64);
       const float* wm = reinterpret_cast<const float*>(ws + lay.off_wm_first);
-      __nv_bfloat16* x16 = (tc && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
+      __nv_bfloat16* x16 = (kBf && lay.training) ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_x16) : nullptr;
       double* gacc0 = try_fuse ? reinterpret_cast<double*>(ws + lay.off_gacc) : nullptr;
       fused_bn = gacc0 != nullptr;
       switch (m->d.in_F) {
@@ -1616,22 +1473,17 @@ static int forward_impl(const FwdArgs& a) {
       }
     } else {
       const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, l - 1));
-      if (tc) {
-        const char* wp = ws + lay.off_wp16f + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
-        TcFuse fu;
-        memset(&fu, 0, sizeof(fu));
-        if (try_fuse) {
-          fu.gacc = reinterpret_cast<double*>(ws + lay.off_gacc + (size_t)l * lay.gacc_stride);
-          fu.F = F;
-        }
-        int rc = lcn_tc_gemm(m, lay, l - 1, 0, reinterpret_cast<const __nv_bfloat16*>(Ain), wp, a.params + L.b_off,
-                             nullptr, reinterpret_cast<__nv_bfloat16*>(Z), part, st, try_fuse ? &fu : nullptr, &fused_bn);
-        if (rc) return rc;
-      } else {
-        const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
-        lcn_launch(k_gemm_simt<T, false>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
-            Ain, wp, a.params + L.b_off, nullptr, Z, part, m->by_out, P, FC, lay.bn_group, lay.gstride);
+      const size_t wofs = (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+      TcFuse fu;
+      memset(&fu, 0, sizeof(fu));
+      if (try_fuse) {
+        fu.gacc = reinterpret_cast<double*>(ws + lay.off_gacc + (size_t)l * lay.gacc_stride);
+        fu.F = F;
       }
+      int rc = lcn_tc_gemm(m, lay, l - 1, 0, reinterpret_cast<const __nv_bfloat16*>(Ain), ws + lay.off_wp16f + wofs,
+                           a.params + L.b_off, nullptr, reinterpret_cast<__nv_bfloat16*>(Z), part, st,
+                           try_fuse ? &fu : nullptr, &fused_bn, kX3 ? ws + lay.off_wp16f_lo + wofs : nullptr);
+      if (rc) return rc;
     }
     LCN_CHECK_LAUNCH();
     float* stat = bn_stat(ws, lay, m, l);
@@ -1645,7 +1497,7 @@ static int forward_impl(const FwdArgs& a) {
                             : nullptr;
     int ew_grid = (int)std::min<int64_t>(2 * m->sm_count, lay.rows_pad / ewy);
     bool pre = false;
-    if constexpr (sizeof(T) == 2) {
+    if constexpr (kBf) {
       // one BN group, <= BA_R rows per thread: all loads up front (k_bn_act_pre)
       const int per = (int)(((lay.rows_pad / ewy + ew_grid - 1) / ew_grid) * ewy);
       if (lay.n_groups == 1 && per <= BA_R * ewy) {
@@ -1670,7 +1522,7 @@ static int forward_impl(const FwdArgs& a) {
   if (le <= last) return LCN_OK;
   const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, n_bn - 1));
   float* out_ws = lay.training ? reinterpret_cast<float*>(ws + lay.off_out) : nullptr;
-  if (tc) {
+  if constexpr (kBf) {
     int rc = lcn_tc_head(m, lay, reinterpret_cast<const __nv_bfloat16*>(Ain), ws + lay.off_wl16f,
                          a.params + m->L[last].b_off, a.x, a.out, out_ws, st);
     if (rc) return rc;
@@ -1685,7 +1537,7 @@ static int forward_impl(const FwdArgs& a) {
 
 int lcn_launch_forward(const FwdArgs& a) {
   if (a.lay.fused) return lcn_stack_forward(a.m, a.lay, a.params, a.ws, a.x, a.out, nullptr, a.st);
-  return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<float>(a);
+  return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<lcn_sp16>(a);
 }
 
 template <typename T>
@@ -1693,19 +1545,14 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
                          const float* labels, float rate, uint64_t seed, uint64_t step, float* loss,
                          float* graw, cudaStream_t st) {
   const int P = m->P, F = m->d.F, FC = m->FC;
-  const bool tc = sizeof(T) == 2;
+  constexpr bool kBf = PathTraits<T>::bf16, kX3 = PathTraits<T>::x3;
   // weight-gradient GEMMs go to the model's side stream (see LcnAux); `wst` is the stream they are enqueued on
-  std::unique_lock<std::mutex> aux_lock;
-  LcnAux* ax = nullptr;
-  if (tc) {
-    aux_lock = std::unique_lock<std::mutex>(m->aux.mu);
-    ax = lcn_aux_get(m);
-    if (ax == nullptr) aux_lock.unlock();
-  }
+  std::unique_lock<std::mutex> aux_lock(m->aux.mu);
+  LcnAux* ax = lcn_aux_get(m);
+  if (ax == nullptr) aux_lock.unlock();
   cudaStream_t wst = ax ? ax->st : st;
   const bool dp = lcn_dp_active(m);
   bool wg_pending[2] = {false, false};
-  size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
   const int64_t blast = m->L[m->n_lin - 1].b_off;     // last-layer bias gradient: accumulated by k_loss_dout (caller's stream)
   if (ax) {
     // fork at the very start: the 4 B/parameter clear of the gradient bucket (the weight-gradient GEMMs reduce-add
@@ -1726,10 +1573,10 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   LCN_CHECK_CUDA(cudaMemsetAsync(ws + lay.off_bnsum, 0, sizeof(float) * m->n_bn * (F * 2 + 1), st));   // sums + grid-barrier counters
   float* dout = reinterpret_cast<float*>(ws + lay.off_dout);
   double* lacc = reinterpret_cast<double*>(ws + lay.off_loss);
-  __nv_bfloat16* dout16 = tc ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dout16) : nullptr;
+  __nv_bfloat16* dout16 = kBf ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dout16) : nullptr;
   lcn_launch(k_loss_dout, dim3((unsigned)(lay.rows_pad / 16)), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_out), labels,
                                                              lay.n_rows, dout, dout16,
-                                                             tc ? graw + m->L[m->n_lin - 1].b_off : nullptr, lacc, loss);
+                                                             kBf ? graw + m->L[m->n_lin - 1].b_off : nullptr, lacc, loss);
   LCN_CHECK_LAUNCH();
 
   auto D = [&](int i) { return reinterpret_cast<T*>(ws + lay.off_d + (size_t)i * lay.d_stride); };
@@ -1738,7 +1585,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   int rows_blk = 512;
   while (lay.rows_pad % rows_blk) rows_blk >>= 1;   // rows_pad is a multiple of 128
   int cur = 0;
-  if (tc) {
+  if constexpr (kBf) {
     const __nv_bfloat16* Ain = reinterpret_cast<const __nv_bfloat16*>(a_buf(ws, lay, m->n_bn - 1));
     float* dwl = reinterpret_cast<float*>(ws + lay.off_dw_last);
     if (ax) {                       // the loss gradient (caller's stream) precedes the last layer's weight gradient
@@ -1755,6 +1602,9 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LCN_CHECK_CUDA(cudaMemcpy2DAsync(graw + m->L[last].w_off, 51 * sizeof(float), dwl, 64 * sizeof(float),
                                      51 * sizeof(float), P, cudaMemcpyDeviceToDevice, wst));
   } else {
+    // fp32-parity path: the N = 51 head on CUDA cores.  It accumulates dWm4 / db4 with atomics into the bucket, which the
+    // side stream is clearing: wait for that first
+    if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_ms, 0));
     const T* Ain = reinterpret_cast<const T*>(a_buf(ws, lay, m->n_bn - 1));
     lcn_launch(k_last_layer_bwd<T>, dim3(dim3((unsigned)(lay.rows_pad / rows_blk), (P + 255) / 256)), dim3(256), 0, st, 
         Ain, dout, reinterpret_cast<const float*>(ws + lay.off_wm_last), D(cur), graw + m->L[last].w_off,
@@ -1789,7 +1639,7 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
       LCN_CHECK_CUDA(cudaEventRecord(ax->ev_dz[l & 1], st));
       LCN_CHECK_CUDA(cudaStreamWaitEvent(wst, ax->ev_dz[l & 1], 0));
     }
-    if (l == 0 && tc) {
+    if (l == 0 && kBf) {
       float* dwf = reinterpret_cast<float*>(ws + lay.off_dw_first);
       int rc = lcn_tc_wgrad_first(m, lay, reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_x16),
                                   reinterpret_cast<const __nv_bfloat16*>(dZ), dwf, wst);
@@ -1815,9 +1665,9 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
       // first layer of the block: D(cur) is the mid gradient, D(prev) the block-output gradient
       addend = D((cur + 2) % 3);
     }
-    if (tc) {
+    {
       int rc = lcn_tc_wgrad(m, lay, reinterpret_cast<const __nv_bfloat16*>(Ain),
-                            reinterpret_cast<const __nv_bfloat16*>(dZ), graw + L.w_off, wst);
+                            reinterpret_cast<const __nv_bfloat16*>(dZ), graw + L.w_off, wst, kX3);
       if (rc) return rc;
       if (ax) {
         LCN_CHECK_CUDA(cudaEventRecord(ax->ev_wg[l & 1], wst));
@@ -1829,21 +1679,11 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
         int rc2 = lcn_dp_allreduce_after(m, wst, graw + L.w_off, (size_t)L.Kin * L.Kout);
         if (rc2) return rc2;
       }
-      const char* wp = ws + lay.off_wp16b + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
-      rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), wp, nullptr,
+      const size_t wofs = (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+      rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), ws + lay.off_wp16b + wofs, nullptr,
                        reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(D(nxt)),
-                       nullptr, st);
+                       nullptr, st, nullptr, nullptr, kX3 ? ws + lay.off_wp16b_lo + wofs : nullptr);
       if (rc) return rc;
-    } else {
-      lcn_launch(k_wgrad_simt<T>, dim3(dim3(m->nnz * FC * FC, (unsigned)(lay.rows_pad / rows_blk))), dim3(256), 0, st, 
-          Ain, dZ, graw + L.w_off, pt, P, FC, rows_blk);
-      if (dp) {
-        int rc2 = lcn_dp_allreduce_after(m, st, graw + L.w_off, (size_t)L.Kin * L.Kout);
-        if (rc2) return rc2;
-      }
-      const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
-      lcn_launch(k_gemm_simt<T, true>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
-          dZ, wp, nullptr, addend, D(nxt), nullptr, m->by_in, P, FC, lay.bn_group, lay.gstride);
     }
     LCN_CHECK_LAUNCH();
     (void)keep;
@@ -1890,38 +1730,28 @@ int lcn_launch_backward(const lcn_model* m, const float* params, char* ws, const
                         float* grads_raw, cudaStream_t st) {
   return m->d.path == LCN_PATH_BF16
              ? backward_impl<__nv_bfloat16>(m, params, ws, lay, x, labels, dropout_rate, seed, step, loss, grads_raw, st)
-             : backward_impl<float>(m, params, ws, lay, x, labels, dropout_rate, seed, step, loss, grads_raw, st);
+             : backward_impl<lcn_sp16>(m, params, ws, lay, x, labels, dropout_rate, seed, step, loss, grads_raw, st);
 }
 
 template <typename T>
 static int layer_gemm_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int l,
                            int transposed, cudaStream_t st) {
-  const int P = m->P, FC = m->FC;
-  const bool tc = sizeof(T) == 2;
-  size_t gemm_smem = (LCN_TILE * GS_APAD + 64 * GS_BPAD) * sizeof(float);
+  const int FC = m->FC;
+  constexpr bool kX3 = PathTraits<T>::x3;
   float* part = reinterpret_cast<float*>(ws + lay.off_part);
   const T* Ain = reinterpret_cast<const T*>(transposed ? ws + lay.off_dz : a_buf(ws, lay, l - 1));
   T* Y = reinterpret_cast<T*>(transposed ? ws + lay.off_d + 2 * lay.d_stride : z_buf(ws, lay, l));
-  if (tc) {
-    const char* wp = ws + (transposed ? lay.off_wp16b : lay.off_wp16f) + (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
-    return lcn_tc_gemm(m, lay, l - 1, transposed, reinterpret_cast<const __nv_bfloat16*>(Ain), wp,
-                       transposed ? nullptr : params + m->L[l].b_off, nullptr, reinterpret_cast<__nv_bfloat16*>(Y),
-                       transposed ? nullptr : part, st);
-  }
-  const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(l - 1) * m->nnz * FC * FC * 4096;
-  if (transposed)
-    lcn_launch(k_gemm_simt<T, true>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, Ain, wp, nullptr, nullptr, Y, nullptr,
-                                                                              m->by_in, P, FC, lay.bn_group, lay.gstride);
-  else
-    lcn_launch(k_gemm_simt<T, false>, dim3(dim3(lay.tiles, LCN_J * FC)), dim3(256), gemm_smem, st, 
-        Ain, wp, params + m->L[l].b_off, nullptr, Y, part, m->by_out, P, FC, lay.bn_group, lay.gstride);
-  LCN_CHECK_LAUNCH();
-  return LCN_OK;
+  const size_t wofs = (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
+  const char* wp = ws + (transposed ? lay.off_wp16b : lay.off_wp16f) + wofs;
+  const char* wl = kX3 ? ws + (transposed ? lay.off_wp16b_lo : lay.off_wp16f_lo) + wofs : nullptr;
+  return lcn_tc_gemm(m, lay, l - 1, transposed, reinterpret_cast<const __nv_bfloat16*>(Ain), wp,
+                     transposed ? nullptr : params + m->L[l].b_off, nullptr, reinterpret_cast<__nv_bfloat16*>(Y),
+                     transposed ? nullptr : part, st, nullptr, nullptr, wl);
 }
 int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
                           int transposed, cudaStream_t st) {
   return m->d.path == LCN_PATH_BF16 ? layer_gemm_impl<__nv_bfloat16>(m, params, ws, lay, layer, transposed, st)
-                                    : layer_gemm_impl<float>(m, params, ws, lay, layer, transposed, st);
+                                    : layer_gemm_impl<lcn_sp16>(m, params, ws, lay, layer, transposed, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1962,7 +1792,7 @@ int lcn_launch_write_tensor(const lcn_model* m, char* ws, const WsLayout& lay, i
   if (m->d.path == LCN_PATH_BF16)
     lcn_launch(k_write_rows<__nv_bfloat16>, dim3(256), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), n_logical, m->P, lay.bn_group, lay.gstride);
   else
-    lcn_launch(k_write_rows<float>, dim3(256), dim3(256), 0, st, src, reinterpret_cast<float*>(dst), n_logical, m->P, lay.bn_group, lay.gstride);
+    lcn_launch(k_write_rows<lcn_sp16>, dim3(256), dim3(256), 0, st, src, reinterpret_cast<lcn_sp16*>(dst), n_logical, m->P, lay.bn_group, lay.gstride);
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
@@ -1989,7 +1819,7 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
     LCN_REQUIRE(layer >= 0 && layer < m->n_bn, "layer %d out of range", layer);
     const char* src = kind == 0 ? z_buf(ws, lay, layer) : kind == 1 ? a_buf(ws, lay, layer) : ws + lay.off_dz;
     if (bf) lcn_launch(k_read_rows<__nv_bfloat16>, dim3(256), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
-    else lcn_launch(k_read_rows<float>, dim3(256), dim3(256), 0, st, reinterpret_cast<const float*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
+    else lcn_launch(k_read_rows<lcn_sp16>, dim3(256), dim3(256), 0, st, reinterpret_cast<const lcn_sp16*>(src), dst, n_logical, P, lay.bn_group, lay.gstride);
   } else if (kind == 2) {
     LCN_REQUIRE(layer >= 0 && layer < m->n_lin, "layer %d out of range", layer);
     const LayerInfo& L = m->L[layer];
@@ -1997,7 +1827,7 @@ int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, in
       LCN_CHECK_CUDA(cudaMemcpyAsync(dst, ws + (layer == 0 ? lay.off_wm_first : lay.off_wm_last),
                                      sizeof(float) * L.Kin * L.Kout, cudaMemcpyDeviceToDevice, st));
     } else {
-      LCN_REQUIRE(!bf, "the mid-layer weight tap needs the fp32 path");
+      LCN_REQUIRE(!bf, "the mid-layer weight tap needs the fp32-parity path (LCN_PATH_FP32 keeps an fp32 copy of the packed blocks)");
       LCN_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * P * P, st));
       const float* wp = reinterpret_cast<const float*>(ws + lay.off_wp32) + (size_t)(layer - 1) * m->nnz * m->FC * m->FC * 4096;
       lcn_launch(k_unpack_mid, dim3(m->nnz * m->FC * m->FC), dim3(256), 0, st, wp, make_pairs(m), m->nnz, F, m->FC, dst);

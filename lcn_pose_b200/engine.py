@@ -22,8 +22,8 @@ class LcnEngine:
     """One model (mask support + layer stack) on one GPU.
 
     Mirrors the arithmetic of cgcnn (network/models_att.py:475-775) and base_model's loss / Adam
-    (:352-421).  `path` selects the arithmetic: "bf16" (tcgen05 tensor cores, 1e-2 parity) or
-    "fp32" (CUDA cores, 1e-4 parity)."""
+    (:352-421).  `path` selects the arithmetic, both on the tcgen05 tensor cores: "bf16" (bf16 operands, 1e-2 parity)
+    or "fp32" (alias "x3": split-bf16 operands, three products per block, fp32 parity -- the 1e-4 path)."""
 
     def __init__(self, F=64, in_F=2, num_layers=3, mask_type="locally_connected", neighbour_matrix=None,
                  residual=True, batch_norm=True, max_norm=True, path="bf16", device="cuda:0",
@@ -35,6 +35,9 @@ class LcnEngine:
         torch.cuda.set_device(self.device)
         self.F, self.in_F, self.num_layers = int(F), int(in_F), int(num_layers)
         self.mask_type = mask_type
+        if path not in ("bf16", "fp32", "x3"):
+            raise ValueError("path must be 'bf16' or 'fp32' (alias 'x3')")
+        path = "fp32" if path == "x3" else path
         self.path = path
         desc = L.ModelDesc()
         desc.F, desc.in_F, desc.num_layers = self.F, self.in_F, self.num_layers

@@ -174,7 +174,8 @@ def undo(data, op_ord, number_actions=2, angle=180, translation=0.5):
     out = torch.empty((n, 51), dtype=torch.float32, device=src.device)
     L.check(lib.lcn_tta_undo(C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), n, int(number_actions),
                              int(op_ord.get("f", -1)), int(op_ord.get("r", -1)), int(op_ord.get("t", -1)), float(angle),
-                             float(translation), C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)))
+                             float(translation) if translation is not None else 0.0,     # inference.py passes None without --translate_data
+                             C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)))
     return out.cpu().numpy().astype(np.float64) if is_np else out
 
 

@@ -1,8 +1,9 @@
 """End-to-end parity of the whole path (BASELINE.json north_star: "end-to-end MPJPE and P-MPJPE within 0.1 mm"):
 inference (predict batching, models_att.py:79-132) -> denormalize (tools/data.py:471-472) -> image_to_camera_frame ->
 [Procrustes] -> per-joint error (evaluate.py:53-61), GPU kernels through the C ABI against the float64 oracle on the
-same seeded H36M-shaped inputs and the same parameters.  The fp32 path must hold 0.1 mm on both protocols; the bf16
-tensor-core path (1e-2 relative per layer) is held to 1 mm on the means."""
+same seeded H36M-shaped inputs and the same parameters.  BOTH arithmetic paths hold the north_star's 0.1 mm on the MPJPE
+and P-MPJPE means and on every per-joint mean (measured on the B200, profiles/r2/parity_mpjpe.json: bf16 0.001 mm on the
+means, 0.07 mm worst per-joint mean; the fp32-parity path 2e-6 mm)."""
 import numpy as np
 import pytest
 import torch
@@ -34,7 +35,7 @@ def _synthetic_set(n, seed=1234):
     return x2d.astype(np.float32), gt, box, cam, root[:, 2].copy()
 
 
-@pytest.mark.parametrize("path,tol_mm", [("fp32", 0.1), ("bf16", 1.0)])
+@pytest.mark.parametrize("path,tol_mm", [("fp32", 0.1), ("bf16", 0.1)])
 def test_mpjpe_and_pmpjpe_end_to_end(path, tol_mm):
     n, bs = 1000, 256                       # four batches, the last one zero padded
     x2d, gt, box, cam, rd = _synthetic_set(n)

@@ -50,7 +50,7 @@ def test_fit_predict_roundtrip_like_train_py(tmp_path, monkeypatch):
     assert net.get_var("linear_model/w1").shape == (34, 17 * 64)
     net2 = models_att.cgcnn(**params, path="fp32", seed=4)
     pred2 = net2.predict(xv)                                       # restores experiment/<dir>/checkpoints/final
-    assert np.array_equal(pred, pred2)
+    assert rel_err(pred2, pred) < 1e-6          # same checkpoint, same kernels (last bit: accumulation in arrival order)
     string, loss = net2.evaluate(xv, yv)
     assert "loss" in string and abs(loss - losses[-1]) < 1e-6 * max(1.0, abs(losses[-1]))
 

@@ -40,13 +40,11 @@ def _grad_report(g, ref_g):
 def _check_grads(rep, path):
     for k, r in rep.items():
         base = k.rsplit("/", 1)[-1]
-        tol = {"fp32": 2e-3, "x3": 2e-3}.get(path, 1e-1)
-        if path == "bf16" and base.startswith("b") and not k.endswith("b4"):
-            tol = 0.25      # bias in front of BatchNorm: the gradient is a near-cancelling sum (BN removes the channel mean)
-        if path == "bf16" and k.endswith("/w1"):
-            tol = 0.15
+        # measured on the B200 at these shapes (profiles/r2/parity_real_shapes.json): bf16 <= 2.2e-2 on the mid-layer tensors,
+        # 3.3e-2 on w1 (dZ of 1088 columns rounded to bf16 before the K = batch reduction); every cosine >= 0.99985
+        tol = {"fp32": 2e-3}.get(path, 5e-2)
         assert r["max_norm_rel"] < tol, (k, r)
-        assert r["cosine"] > (0.999 if path != "bf16" else 0.98), (k, r)
+        assert r["cosine"] > (0.999999 if path != "bf16" else 0.9995), (k, r)
 
 
 @pytest.mark.parametrize("mask_type,knn,tag", [("locally_connected", 3, "configs1_knn3_L3_B4096"),
