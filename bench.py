@@ -274,7 +274,7 @@ def run_train(args, rank, world, local_rank, dev):
     fwd_flop = fwd_flop_per_pose(nnz, LAYERS, F)
     eng = make_engine(cfg_id, args.path, local_rank)
     mode = args.dp_mode
-    if world > 1 and mode == "overlap":
+    if world > 1 and mode == "p2p":
         lcn_dist.init_native_dp(eng)
     x, y = synth_xy(BATCH, seed=1234 + rank)
     xd, yd = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
@@ -305,7 +305,10 @@ def run_train(args, rank, world, local_rank, dev):
     def step(xx, yy):
         if gather is not None:
             gather(xx, yy)
-        lcn_dist.dp_train_step(eng, xx, yy, args.dropout, mode=mode, graph=not args.no_graph)
+        if mode == "none":
+            eng.train_step_graph(xx, yy, args.dropout)
+        else:
+            lcn_dist.dp_train_step(eng, xx, yy, args.dropout, mode=mode, graph=not args.no_graph)
 
     for _ in range(max(args.warmup, 3)):
         step(xd, yd)
@@ -383,6 +386,7 @@ def run_train(args, rank, world, local_rank, dev):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s, f_ms, p1_ms, p2_ms = t.tolist()
+    eng.close()                  # graphs first, then the handle (and its communicator)
     if rank != 0:
         return None
     tf_burst, tf_sust, hbm, how = measured_peaks()
@@ -397,8 +401,8 @@ def run_train(args, rank, world, local_rank, dev):
             "data": "synthetic", "config": workload_config(cfg_id, args.dropout),
             "detail": {"path": args.path, "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per step)",
                        "parallelism": (f"dp{world}: per-GPU BatchNorm statistics; gradient exchange: " +
-                                       ("per-layer ncclAllReduce(avg) inside lcn_model_backward, overlapped with the backward pass"
-                                        if mode == "overlap" else "one torch.distributed all-reduce of the packed bucket between two graphs"))
+                                       ("two-shot all-reduce of the packed bucket over NVLink peer memory inside lcn_model_backward (csrc/lcn_dp.cu), one graph per step"
+                                        if mode == "p2p" else "one torch.distributed all-reduce of the packed bucket between two graphs"))
                        if world > 1 else "single GPU"},
             "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "poses/s",
                     "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4},
@@ -653,6 +657,9 @@ JSON_OUT = sys.stdout
 
 
 def main():
+    if os.environ.get("LCN_HANG_TRACE"):          # debugging aid: dump every thread's Python stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["LCN_HANG_TRACE"]), exit=False)
     # The contract is ONE JSON line on stdout.  NCCL prints its version banner with a C-level printf to stdout when the
     # first communicator is created (seen on the GPU boxes: "NCCL version 2.28.9+cuda12.9" in front of the line), so the
     # process's fd 1 is pointed at stderr and the JSON line goes to a duplicate of the original stdout.
@@ -669,7 +676,9 @@ def main():
     ap.add_argument("--path", default=os.environ.get("LCN_BENCH_PATH", "bf16"), choices=["bf16", "x3", "fp32"],
                     help="bf16: 1e-2 parity path; x3 (= fp32): fp32-parity path on the tensor cores (split-bf16 operands)")
     ap.add_argument("--dropout", type=float, default=0.25)     # params_help.py:166 training default
-    ap.add_argument("--dp-mode", default=os.environ.get("LCN_DP_MODE", "overlap"), choices=["overlap", "packed"])
+    ap.add_argument("--dp-mode", default=os.environ.get("LCN_DP_MODE", "p2p"), choices=["p2p", "packed", "none"],
+                    help="gradient exchange: p2p (library kernel over NVLink peer memory), packed (torch / NCCL all-reduce of the packed "
+                         "bucket), none (NO exchange -- calibration of the multi-process overhead only, replicas diverge)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--infer-poses", type=int, default=1 << 22, help="poses per GPU of the secondary resident inference+eval leg (0: skip)")
     ap.add_argument("--total-poses", type=int, default=1 << 26, help="--config 3: poses of the whole job (sharded over the GPUs)")

@@ -177,18 +177,22 @@ int64_t lcn_model_grad_compact_count(const lcn_model* m);
 int lcn_model_pack_grads(lcn_model* m, const float* d_grads_raw, float* d_compact, void* stream);
 int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_raw, void* stream);
 
-/* Data-parallel training with the exchange INSIDE the backward pass (csrc/lcn_dp.cu).  One process per GPU; rank 0 makes
- * an id with lcn_dp_unique_id (128 bytes, ncclUniqueId) and hands it to the other ranks by any means (torch.distributed
- * store, MPI, a file); every rank then calls lcn_dp_init -- a COLLECTIVE call that creates the model's NCCL communicator,
- * communication stream and events.  Afterwards lcn_model_backward averages d_grads_raw over the ranks itself: each mid
- * layer's weight gradient is all-reduced (ncclAvg, in place) right behind its weight-gradient GEMM, overlapped with the
- * rest of the backward pass, the small tensors go out as one grouped launch at the end, and the caller's stream waits
- * for the communication stream before the call's work is considered done -- so lcn_model_adam_step needs no change and
- * the whole step is capturable as one CUDA graph.  BatchNorm statistics stay per GPU (== the reference at batch B per
- * GPU).  lcn_dp_enable(m, 0) switches the exchange off for calls that want the local gradient (tests, the packed-bucket
- * path above).  libnccl.so.2 is resolved with dlopen at the first call; LCN_ECUDA + message if it is missing. */
-int lcn_dp_unique_id(void* h_id128);
-int lcn_dp_init(lcn_model* m, const void* h_id128, int rank, int world);
+/* Data-parallel training with the exchange INSIDE the backward pass (csrc/lcn_dp.cu): a two-shot all-reduce of the
+ * packed bucket over NVLink peer memory, written for this bucket -- reduce-scatter by peer loads, all-gather by peer
+ * stores, flags with release / acquire at system scope, no library collective.  One process per GPU (<= 8 GPUs of one
+ * NVLink domain; world size 2, 4 or 8).  Setup: every rank calls lcn_dp_export (allocates the rank's gradient bucket -- the
+ * ONE device allocation this library makes, because peers must be able to map it -- and returns its 64-byte CUDA IPC
+ * handle), the host all-gathers the handles by any means (torch.distributed, MPI, a file), every rank calls
+ * lcn_dp_connect with all `world` handles in rank order and from then on passes lcn_dp_bucket(m) as d_grads_raw.
+ * lcn_model_backward then leaves the MEAN of the ranks' gradients in the bucket, exchanged in place by the library's own
+ * kernel (in stream order; capturable into the caller's CUDA graph like every other call), so
+ * lcn_model_adam_step needs no change and a data-parallel step is one graph.  Every rank must issue the same sequence of
+ * lcn_model_backward calls.  BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
+ * lcn_dp_enable(m, 0) switches the exchange off for calls that want the local gradient (tests, the host-side
+ * packed-bucket path above). */
+int lcn_dp_export(lcn_model* m, void* h_handle64);
+float* lcn_dp_bucket(const lcn_model* m);   /* the rank's peer-mapped gradient bucket: pass it as d_grads_raw */
+int lcn_dp_connect(lcn_model* m, const void* h_handles /* world x 64 bytes, rank order */, int rank, int world);
 int lcn_dp_world(const lcn_model* m);
 int lcn_dp_enable(lcn_model* m, int on);
 

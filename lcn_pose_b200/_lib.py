@@ -54,8 +54,9 @@ PROTOTYPES = {
     "lcn_model_grad_compact_count": (_i64, [_vp]),
     "lcn_model_pack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lcn_model_unpack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "lcn_dp_unique_id": (C.c_int, [_vp]),
-    "lcn_dp_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "lcn_dp_export": (C.c_int, [_vp, _vp]),
+    "lcn_dp_bucket": (_vp, [_vp]),
+    "lcn_dp_connect": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "lcn_dp_world": (C.c_int, [_vp]),
     "lcn_dp_enable": (C.c_int, [_vp, C.c_int]),
     "lcn_model_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _vp, _vp]),

@@ -1,140 +1,174 @@
-// Data-parallel gradient exchange inside the library ("NCCL allreduce of the gradient ... overlapped with
-// wgrad of earlier layers").  The reference has no distributed code at all (network/models_att.py:155-158: one process,
-// one tf.Session); this is the exchange step a data-parallel host needs between optimizer.compute_gradients and
+// Data-parallel gradient exchange inside the library: a two-shot all-reduce written for this bucket, over NVLink peer
+// memory.  The reference has no distributed code at all (network/models_att.py:155-158: one process, one
+// tf.Session); this is the exchange step a data-parallel host needs between optimizer.compute_gradients and
 // apply_gradients (:408-409).
 //
-// One process per GPU.  lcn_dp_init() gives the model its own NCCL communicator, a communication stream and events.
-// From then on lcn_model_backward() averages the gradient bucket over the ranks ITSELF, layer by layer, while the
-// backward pass is still running:
-//   * the weight gradient of mid layer l is complete as soon as its weight-gradient GEMM has run (side stream): an
-//     in-place ncclAllReduce(avg) of that layer's [17F x 17F] region is enqueued on the communication stream right
-//     behind it and overlaps the BatchNorm backward / dgrad / wgrad kernels of the layers below;
-//   * what only completes at the end of the pass (edge-layer weights, every bias, BatchNorm gamma / beta) goes out as
-//     ONE grouped launch (ncclGroupStart / End) after the last kernel;
-//   * the caller's stream joins the communication stream before lcn_model_backward returns control of the bucket, so
-//     lcn_model_adam_step sees averaged gradients.  Everything is event-ordered and capturable: a data-parallel train
-//     step is ONE CUDA graph (forward, backward + exchange, Adam), replayed every step.
-// The tensor-core GEMMs run single waves of <= 128 CTAs on 148 SMs, so the communicator is created with at
-// most 16 CTAs: the collectives fit on the SMs the GEMMs leave free instead of competing for theirs.  No kernel of the
-// backward pass needs all of its blocks resident at once (the grid-barrier BatchNorm kernel of round 1 is gone), so
-// a resident NCCL kernel waiting for its peers cannot starve the compute kernels it shares the GPU with.
+// One process per GPU.  Every rank owns ONE device allocation [flags | gradient bucket] that all peers map through CUDA
+// IPC (lcn_dp_export -> the host all-gathers the 64-byte handles -> lcn_dp_connect); lcn_dp_bucket() is the pointer the
+// caller passes as d_grads_raw, so the backward pass writes its gradients straight into peer-visible memory.  At the
+// end of lcn_model_backward:
 //
-// libnccl is resolved at run time (dlopen "libnccl.so.2": in a torch process this is the NCCL 2.28 torch already
-// loaded), so liblcn_b200.so has no link-time dependency on it and single-GPU users never touch it.
-#include <dlfcn.h>
-#include <nccl.h>
+//   k_dp_publish   epoch += 1; ready[me] = epoch in every peer's flag block                (st.release.sys over NVLink)
+//   k_dp_reduce    (lcn_kernels.cu) waits until ready[p] >= epoch for every peer p; the units of the bucket -- nonzero
+//                  joint-pair blocks of the weight gradients, small tensors -- are dealt round-robin to the ranks; for
+//                  its units a rank loads the block from ALL buckets (16-byte loads, the peers' straight over NVLink),
+//                  takes the mean and stores it into ALL buckets: reduce-scatter by peer LOADS, all-gather by peer
+//                  STORES, in place, one pass, no staging or pack / unpack copy; the masked-out 40 % of the bucket never
+//                  travels; the last CTA publishes done[me] = epoch to every peer
+//   k_dp_wait      waits until done[p] >= epoch for every p: every unit of this rank's bucket holds the mean, and every
+//                  peer has finished reading it -- the chain rule / Adam kernels that follow see averaged gradients
+//
+// Each gradient byte crosses the NVLink fabric once in each direction.  Measured against ncclAllReduce of the packed
+// bucket (with its pack / unpack passes, two graph replays) and against NCCL all-reduces per layer overlapped with the
+// backward pass (SLOWER than no overlap: the NCCL CTAs take SMs from single-wave GEMMs and two-blocks-per-SM elementwise
+// kernels): DESIGN.md section 5.
+//
+// Why this is safe without a cluster-wide barrier: flags only ever grow (epoch numbers), every rank executes the same
+// sequence of exchanges, unit sets of different ranks are disjoint (in-place is race free), and the two waits order the
+// reuse of the bucket -- a rank starts the next backward pass (which overwrites its bucket) only after k_dp_wait(e), i.e.
+// after every peer published done(e), which a peer does after its last read of that bucket; a peer touches this rank's
+// bucket for epoch e+1 only after this rank published ready(e+1).  All three kernels take only device pointers and read
+// the epoch from device memory, so the exchange is captured into the train-step CUDA graph like any other kernel of the
+// step.  No kernel needs a peer's kernel to be co-scheduled in order to FINISH its own loads and stores; the waits are on
+// flags that the peers' stream-ordered work sets unconditionally, so a late peer delays, never deadlocks.
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "lcn_internal.cuh"
 
-namespace {
+#define LCN_DP_MAX_WORLD 8
+#define LCN_DP_FLAG_BYTES 4096
 
-struct NcclApi {
-  void* h = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-  bool ok = false;
+struct LcnDpFlags {                       // lives at the start of every rank's exchange allocation
+  unsigned long long epoch;               // local: exchanges started by this rank
+  unsigned long long pad0[15];
+  unsigned long long ready[LCN_DP_MAX_WORLD];   // ready[p]: written by rank p -- its xbuf holds epoch's bucket
+  unsigned long long pad1[8];
+  unsigned long long done[LCN_DP_MAX_WORLD];    // done[p]: written by rank p -- slice p of our rbuf holds epoch's mean
+  unsigned long long pad2[8];
+  unsigned int ticket;                    // local: CTAs of k_dp_reduce that have finished
 };
 
-const NcclApi& nccl() {
-  static const NcclApi api = [] {
-    NcclApi a;
-    a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (a.h == nullptr) a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (a.h == nullptr) return a;
-#define LCN_SYM(field, name) *reinterpret_cast<void**>(&a.field) = dlsym(a.h, name)
-    LCN_SYM(GetUniqueId, "ncclGetUniqueId");
-    LCN_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
-    LCN_SYM(CommInitRank, "ncclCommInitRank");
-    LCN_SYM(CommDestroy, "ncclCommDestroy");
-    LCN_SYM(AllReduce, "ncclAllReduce");
-    LCN_SYM(GroupStart, "ncclGroupStart");
-    LCN_SYM(GroupEnd, "ncclGroupEnd");
-    LCN_SYM(GetErrorString, "ncclGetErrorString");
-#undef LCN_SYM
-    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GroupStart && a.GroupEnd && a.GetErrorString;
-    return a;
-  }();
-  return api;
+struct LcnDp {
+  int rank = 0, world = 1;
+  bool enabled = true, connected = false;
+  int64_t count = 0;                      // floats in the bucket (= lcn_model_param_count)
+  size_t bytes = 0;
+  char* base = nullptr;                   // own allocation
+  char* peer[LCN_DP_MAX_WORLD] = {};      // mapped allocations (peer[rank] == base)
+};
+
+struct DpFlagPtrs {                       // by-value kernel argument
+  LcnDpFlags* flags[LCN_DP_MAX_WORLD];
+  int rank, world;
+};
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
-#define LCN_CHECK_NCCL(expr)                                                                             \
-  do {                                                                                                   \
-    ncclResult_t _r = (expr);                                                                            \
-    if (_r != ncclSuccess) {                                                                             \
-      lcn_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, nccl().GetErrorString(_r));             \
-      return LCN_ECUDA;                                                                                  \
-    }                                                                                                    \
-  } while (0)
+__global__ void k_dp_publish(DpFlagPtrs d) {
+  lcn_pdl_prologue();
+  __shared__ unsigned long long e_s;
+  if (threadIdx.x == 0) {
+    e_s = d.flags[d.rank]->epoch + 1;
+    d.flags[d.rank]->epoch = e_s;
+    __threadfence_system();                // the bucket (previous kernels of this stream) is visible system-wide before the flag
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < d.world) st_release_sys(&d.flags[threadIdx.x]->ready[d.rank], e_s);
+}
+
+__global__ void k_dp_wait(DpFlagPtrs d) {
+  lcn_pdl_prologue();
+  LcnDpFlags* mine = d.flags[d.rank];
+  if ((int)threadIdx.x < d.world) {
+    const unsigned long long e = mine->epoch;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(&mine->done[threadIdx.x]) < e) {
+      if (++spins > (1ull << 28)) {        // seconds: a peer died or the ranks disagree on the call sequence
+        printf("lcn_dp: wait for a peer's done flag timed out\n");
+        __trap();
+      }
+    }
+  }
+}
 
 }  // namespace
 
-struct LcnDp {
-  ncclComm_t comm = nullptr;
-  int rank = 0, world = 1;
-  bool enabled = true;
-  cudaStream_t st = nullptr;                 // communication stream
-  cudaEvent_t ev_ready = nullptr;            // producer -> communication stream
-  cudaEvent_t ev_done = nullptr;             // communication stream -> consumer
-};
+// ---- host side ----------------------------------------------------------------------------------------------------
+static size_t dp_bytes(int64_t count) { return LCN_DP_FLAG_BYTES + (((size_t)count * 4 + 255) & ~(size_t)255); }
 
-extern "C" int lcn_dp_unique_id(void* h_id128) {
-  LCN_REQUIRE(h_id128 != nullptr, "null argument");
-  LCN_REQUIRE(nccl().ok, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
-  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-  ncclUniqueId id;
-  LCN_CHECK_NCCL(nccl().GetUniqueId(&id));
-  memcpy(h_id128, &id, sizeof(id));
-  return LCN_OK;
-}
-
-extern "C" int lcn_dp_init(lcn_model* m, const void* h_id128, int rank, int world) {
-  LCN_REQUIRE(m != nullptr && h_id128 != nullptr, "null argument");
-  LCN_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank %d / world %d", rank, world);
-  LCN_REQUIRE(m->dp == nullptr, "the model already has a communicator");
-  LCN_REQUIRE(nccl().ok, "libnccl.so.2 could not be loaded");
+extern "C" int lcn_dp_export(lcn_model* m, void* h_handle64) {
+  LCN_REQUIRE(m != nullptr && h_handle64 != nullptr, "null argument");
+  LCN_REQUIRE(m->dp == nullptr, "the model already has an exchange buffer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  static_assert(sizeof(LcnDpFlags) <= LCN_DP_FLAG_BYTES, "flag block");
   LcnDp* dp = new LcnDp();
-  dp->rank = rank;
-  dp->world = world;
-  ncclUniqueId id;
-  memcpy(&id, h_id128, sizeof(id));
-  ncclResult_t r;
-  if (nccl().CommInitRankConfig != nullptr) {
-    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
-    cfg.maxCTAs = 16;                        // stay on the SMs the single-wave GEMMs leave free
-    r = nccl().CommInitRankConfig(&dp->comm, world, id, rank, &cfg);
-  } else {
-    r = nccl().CommInitRank(&dp->comm, world, id, rank);
-  }
-  if (r != ncclSuccess) {
-    lcn_set_error("ncclCommInitRank failed: %s", nccl().GetErrorString(r));
+  dp->count = m->n_params;
+  dp->bytes = dp_bytes(dp->count);
+  // the one device allocation the library makes: peers have to map it, so it cannot come from the caller's allocator
+  cudaError_t e = cudaMalloc(&dp->base, dp->bytes);
+  if (e == cudaSuccess) e = cudaMemset(dp->base, 0, dp->bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, dp->base);
+  if (e != cudaSuccess) {
+    lcn_set_error("lcn_dp_export: %s", cudaGetErrorString(e));
+    if (dp->base) cudaFree(dp->base);
     delete dp;
+    (void)cudaGetLastError();
     return LCN_ECUDA;
   }
-  bool ok = cudaStreamCreateWithFlags(&dp->st, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&dp->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&dp->ev_done, cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) {
-    lcn_set_error("lcn_dp_init: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-    nccl().CommDestroy(dp->comm);
-    delete dp;
-    return LCN_ECUDA;
-  }
+  memcpy(h_handle64, &h, sizeof(h));
   m->dp = dp;
   return LCN_OK;
 }
 
-extern "C" int lcn_dp_world(const lcn_model* m) { return (m && m->dp) ? m->dp->world : 1; }
+extern "C" float* lcn_dp_bucket(const lcn_model* m) {
+  return (m && m->dp) ? reinterpret_cast<float*>(m->dp->base + LCN_DP_FLAG_BYTES) : nullptr;
+}
+
+extern "C" int lcn_dp_connect(lcn_model* m, const void* h_handles, int rank, int world) {
+  LCN_REQUIRE(m != nullptr && h_handles != nullptr, "null argument");
+  LCN_REQUIRE(m->dp != nullptr && !m->dp->connected, "call lcn_dp_export first (once)");
+  LCN_REQUIRE(world >= 1 && world <= LCN_DP_MAX_WORLD && rank >= 0 && rank < world, "rank %d / world %d (max %d)", rank, world,
+              LCN_DP_MAX_WORLD);
+  LcnDp* dp = m->dp;
+  dp->rank = rank;
+  dp->world = world;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      dp->peer[p] = dp->base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(h_handles) + (size_t)p * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      lcn_set_error("lcn_dp_connect: cudaIpcOpenMemHandle(rank %d) -> %s (are the GPUs NVLink / P2P peers?)", p, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return LCN_ECUDA;
+    }
+    dp->peer[p] = static_cast<char*>(ptr);
+  }
+  dp->connected = true;
+  return LCN_OK;
+}
+
+extern "C" int lcn_dp_world(const lcn_model* m) { return (m && m->dp && m->dp->connected) ? m->dp->world : 1; }
 
 extern "C" int lcn_dp_enable(lcn_model* m, int on) {
   LCN_REQUIRE(m != nullptr, "null model");
-  LCN_REQUIRE(m->dp != nullptr || !on, "lcn_dp_enable: the model has no communicator (lcn_dp_init)");
+  LCN_REQUIRE((m->dp != nullptr && m->dp->connected) || !on, "lcn_dp_enable: the model is not connected (lcn_dp_export / lcn_dp_connect)");
   if (m->dp) m->dp->enabled = on != 0;
   return LCN_OK;
 }
@@ -142,50 +176,41 @@ extern "C" int lcn_dp_enable(lcn_model* m, int on) {
 void lcn_dp_destroy(lcn_model* m) {
   if (m == nullptr || m->dp == nullptr) return;
   LcnDp* dp = m->dp;
-  if (dp->st) cudaStreamSynchronize(dp->st);
-  if (dp->comm) nccl().CommDestroy(dp->comm);
-  if (dp->ev_ready) cudaEventDestroy(dp->ev_ready);
-  if (dp->ev_done) cudaEventDestroy(dp->ev_done);
-  if (dp->st) cudaStreamDestroy(dp->st);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < dp->world; ++p)
+    if (p != dp->rank && dp->peer[p] != nullptr) cudaIpcCloseMemHandle(dp->peer[p]);
+  if (dp->base) cudaFree(dp->base);
+  (void)cudaGetLastError();
   delete dp;
   m->dp = nullptr;
 }
 
-bool lcn_dp_active(const lcn_model* m) { return m->dp != nullptr && m->dp->enabled && m->dp->world > 1; }
+bool lcn_dp_active(const lcn_model* m) { return m->dp != nullptr && m->dp->connected && m->dp->enabled && m->dp->world > 1; }
 
-// Average buf[0, count) over the ranks, in place, on the communication stream, once everything enqueued on `producer`
-// so far has run.
-int lcn_dp_allreduce_after(const lcn_model* m, cudaStream_t producer, float* buf, size_t count) {
+// Average the raw-gradient bucket over the ranks, in place, on `st` (called at the end of lcn_model_backward).
+int lcn_dp_exchange(const lcn_model* m, float* graw, cudaStream_t st) {
   LcnDp* dp = m->dp;
-  LCN_CHECK_CUDA(cudaEventRecord(dp->ev_ready, producer));
-  LCN_CHECK_CUDA(cudaStreamWaitEvent(dp->st, dp->ev_ready, 0));
-  LCN_CHECK_NCCL(nccl().AllReduce(buf, buf, count, ncclFloat32, ncclAvg, dp->comm, dp->st));
-  return LCN_OK;
-}
-
-// The same for several regions in ONE launch (ncclGroupStart / End).
-int lcn_dp_allreduce_group_after(const lcn_model* m, cudaStream_t producer, float* base, const int64_t* offs,
-                                 const int64_t* counts, int n) {
-  LcnDp* dp = m->dp;
-  LCN_CHECK_CUDA(cudaEventRecord(dp->ev_ready, producer));
-  LCN_CHECK_CUDA(cudaStreamWaitEvent(dp->st, dp->ev_ready, 0));
-  LCN_CHECK_NCCL(nccl().GroupStart());
-  for (int i = 0; i < n; ++i) {
-    ncclResult_t r = nccl().AllReduce(base + offs[i], base + offs[i], (size_t)counts[i], ncclFloat32, ncclAvg, dp->comm, dp->st);
-    if (r != ncclSuccess) {
-      nccl().GroupEnd();
-      lcn_set_error("ncclAllReduce (grouped) failed: %s", nccl().GetErrorString(r));
-      return LCN_ECUDA;
-    }
+  LCN_REQUIRE(graw == reinterpret_cast<float*>(dp->base + LCN_DP_FLAG_BYTES),
+              "data-parallel model: d_grads_raw must be the peer-mapped bucket returned by lcn_dp_bucket()");
+  DpFlagPtrs f;
+  memset(&f, 0, sizeof(f));
+  f.rank = dp->rank;
+  f.world = dp->world;
+  float* buckets[LCN_DP_MAX_WORLD];
+  unsigned long long* done_at[LCN_DP_MAX_WORLD];
+  for (int p = 0; p < dp->world; ++p) {
+    f.flags[p] = reinterpret_cast<LcnDpFlags*>(dp->peer[p]);
+    buckets[p] = reinterpret_cast<float*>(dp->peer[p] + LCN_DP_FLAG_BYTES);
+    done_at[p] = &f.flags[p]->done[dp->rank];
   }
-  LCN_CHECK_NCCL(nccl().GroupEnd());
+  LcnDpFlags* mine = f.flags[dp->rank];
+  lcn_launch(k_dp_publish, dim3(1), dim3(32), 0, st, f);
+  LCN_CHECK_LAUNCH();
+  int rc = lcn_launch_dp_reduce(m, buckets, mine->ready, done_at, &mine->epoch, &mine->ticket, dp->rank, dp->world, st);
+  if (rc) return rc;
+  lcn_launch(k_dp_wait, dim3(1), dim3(32), 0, st, f);
+  LCN_CHECK_LAUNCH();
   return LCN_OK;
 }
 
-// `consumer` continues when every collective enqueued so far has completed.
-int lcn_dp_join(const lcn_model* m, cudaStream_t consumer) {
-  LcnDp* dp = m->dp;
-  LCN_CHECK_CUDA(cudaEventRecord(dp->ev_done, dp->st));
-  LCN_CHECK_CUDA(cudaStreamWaitEvent(consumer, dp->ev_done, 0));
-  return LCN_OK;
-}
+LCN_KTRACE_EXPORT(dp)

@@ -75,7 +75,7 @@ struct LcnAux {
   cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
 };
 
-struct LcnDp;                      // data-parallel communicator + stream + events (lcn_dp.cu); null: single process
+struct LcnDp;                      // data-parallel exchange buffers mapped across the ranks (lcn_dp.cu); null: single process
 
 struct lcn_model {
   mutable LcnAux aux;
@@ -245,10 +245,7 @@ static inline void lcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // ---- data-parallel exchange (lcn_dp.cu) ----
 bool lcn_dp_active(const lcn_model* m);
-int lcn_dp_allreduce_after(const lcn_model* m, cudaStream_t producer, float* buf, size_t count);
-int lcn_dp_allreduce_group_after(const lcn_model* m, cudaStream_t producer, float* base, const int64_t* offs,
-                                 const int64_t* counts, int n);
-int lcn_dp_join(const lcn_model* m, cudaStream_t consumer);
+int lcn_dp_exchange(const lcn_model* m, float* graw, cudaStream_t st);   // mean of the bucket over the ranks, in place
 void lcn_dp_destroy(lcn_model* m);
 
 // ---- launch wrappers implemented in the kernel translation units ----
@@ -279,6 +276,9 @@ int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, cha
                     const lcn_step_scalars* dyn, cudaStream_t st);
 int64_t lcn_grad_compact_count(const lcn_model* m);
 int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, bool unpack, cudaStream_t st);
+int lcn_launch_dp_reduce(const lcn_model* m, float* const* buckets, unsigned long long* ready_local,
+                         unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
+                         int world, cudaStream_t st);
 int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
                           int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,

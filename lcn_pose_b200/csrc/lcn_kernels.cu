@@ -1348,10 +1348,20 @@ __global__ void __launch_bounds__(256) k_grad_compact(float* __restrict__ graw, 
     const int i = pt.pi[p], j = pt.pj[p];
     float* g = graw + lt.w_off[l];
     float* c = compact + ct.w_coff[l] + (int64_t)p * Fi * Fo;
-    for (int e = threadIdx.x; e < Fi * Fo; e += 256) {
-      const int fi = e / Fo, fo = e - fi * Fo;
-      const size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
-      if (UNPACK) g[o] = c[e]; else c[e] = g[o];
+    if ((Fo & 3) == 0) {                  // 16-byte copies: a block row is Fo contiguous floats in both layouts
+      const int q = Fo >> 2;
+      for (int e = threadIdx.x; e < Fi * q; e += 256) {
+        const int fi = e / q, c4 = (e - fi * q) * 4;
+        float4* gp = reinterpret_cast<float4*>(g + (size_t)(i * Fi + fi) * Kout + j * Fo + c4);
+        float4* cp = reinterpret_cast<float4*>(c + fi * Fo + c4);
+        if (UNPACK) *gp = *cp; else *cp = *gp;
+      }
+    } else {
+      for (int e = threadIdx.x; e < Fi * Fo; e += 256) {
+        const int fi = e / Fo, fo = e - fi * Fo;
+        const size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
+        if (UNPACK) g[o] = c[e]; else c[e] = g[o];
+      }
     }
   } else {
     const int k = b - nnz * n_lin;
@@ -1362,10 +1372,125 @@ __global__ void __launch_bounds__(256) k_grad_compact(float* __restrict__ graw, 
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// data-parallel exchange (lcn_dp.cu): two-shot all-reduce of the gradient bucket over NVLink peer memory, IN PLACE in the
+// parameter-layout bucket of every rank.  The unit of work is the unit of k_grad_compact -- one Fi x Fo joint-pair
+// block of one weight matrix inside the mask support, or one small tensor -- so the masked-out 40 % of the bucket is
+// never read, never sent; units are dealt round-robin to the ranks.  For its units a rank loads the block from ALL
+// `world` buckets (its own and, over NVLink, the peers'), takes the mean in a fixed order (every rank ends up with
+// bit-identical gradients) and stores it into ALL `world` buckets: reduce-scatter by peer loads, all-gather by peer
+// stores, no staging copy, no pack / unpack pass.  Unit sets of different ranks are disjoint, so in-place is race free.
+// Flags (system-scope release / acquire, epoch numbers that only grow): ready[p] -- rank p's bucket is complete;
+// done[p] -- rank p has stored its units everywhere and finished reading everybody's bucket.
+// ------------------------------------------------------------------------------------------------
+struct DpArgs {
+  float* g[8];                            // the `world` gradient buckets (g[rank] is local)
+  unsigned long long* ready_local;        // [8] local flags written by the peers
+  unsigned long long* done_at[8];         // peer p's done[rank] slot
+  unsigned long long* epoch;              // local
+  unsigned int* ticket;                   // local
+  int rank, world;
+};
+__device__ __forceinline__ float4 dp_ld16(const float* p) {   // L2-coherent 16-byte load (peer data: never from L1)
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+template <int W>
+__device__ __forceinline__ void dp_mean16(const DpArgs& d, size_t off, float inv) {
+  float4 v[W];
+#pragma unroll
+  for (int p = 0; p < W; ++p) v[p] = dp_ld16(d.g[p] + off);           // all loads in flight before the first add
+  float4 a = v[0];
+#pragma unroll
+  for (int p = 1; p < W; ++p) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+  a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+#pragma unroll
+  for (int p = 0; p < W; ++p) *reinterpret_cast<float4*>(d.g[p] + off) = a;
+}
+__device__ __forceinline__ void dp_mean1(const DpArgs& d, size_t off, float inv) {
+  float a = 0.f;
+  for (int p = 0; p < d.world; ++p) a += __ldcg(d.g[p] + off);
+  a *= inv;
+  for (int p = 0; p < d.world; ++p) d.g[p][off] = a;
+}
+template <int W>
+__global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin) {
+  lcn_pdl_prologue();
+  const unsigned long long e = *d.epoch;
+  if ((int)threadIdx.x < d.world) {
+    unsigned long long v, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(d.ready_local + threadIdx.x) : "memory");
+      if (v < e && ++spins > (1ull << 28)) { printf("lcn_dp: wait for a peer's ready flag timed out\n"); __trap(); }
+    } while (v < e);
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)d.world;
+  const int n_units = nnz * n_lin + ct.n_other;
+  for (int b = blockIdx.x * d.world + d.rank; b < n_units; b += gridDim.x * d.world) {
+    if (b < nnz * n_lin) {
+      const int l = b / nnz, p = b - l * nnz;
+      const int Fi = lt.Fi[l], Fo = lt.Fo[l], Kout = LCN_J * Fo;
+      const size_t base = lt.w_off[l] + (size_t)(pt.pi[p] * Fi) * Kout + pt.pj[p] * Fo;
+      if ((Fo & 3) == 0) {
+        const int q = Fo >> 2;
+        for (int t = threadIdx.x; t < Fi * q; t += 256) {
+          const int fi = t / q, c4 = (t - fi * q) * 4;
+          dp_mean16<W>(d, base + (size_t)fi * Kout + c4, inv);
+        }
+      } else {
+        for (int t = threadIdx.x; t < Fi * Fo; t += 256) {
+          const int fi = t / Fo, fo = t - fi * Fo;
+          dp_mean1(d, base + (size_t)fi * Kout + fo, inv);
+        }
+      }
+    } else {
+      const int k = b - nnz * n_lin;
+      const size_t base = ct.o_off[k];
+      const int64_t n = ct.o_size[k], n4 = (base & 3) == 0 ? n / 4 : 0;
+      for (int64_t t = threadIdx.x; t < n4; t += 256) dp_mean16<W>(d, base + 4 * t, inv);
+      for (int64_t t = 4 * n4 + threadIdx.x; t < n; t += 256) dp_mean1(d, base + t, inv);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(d.ticket, 1u) == gridDim.x - 1) {     // last block of this rank
+    *d.ticket = 0u;
+    __threadfence_system();
+    for (int p = 0; p < d.world; ++p)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.done_at[p]), "l"(e) : "memory");
+  }
+}
+int lcn_launch_dp_reduce(const lcn_model* m, float* const* buckets, unsigned long long* ready_local,
+                         unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
+                         int world, cudaStream_t st) {
+  const CompactTable ct = make_compact(m);
+  DpArgs d;
+  memset(&d, 0, sizeof(d));
+  for (int p = 0; p < world; ++p) { d.g[p] = buckets[p]; d.done_at[p] = done_at[p]; }
+  d.ready_local = ready_local;
+  d.epoch = epoch;
+  d.ticket = ticket;
+  d.rank = rank;
+  d.world = world;
+  const int n_units = m->nnz * m->n_lin + ct.n_other;
+  const dim3 grid(std::max(1, std::min((n_units + world - 1) / world, 4 * m->sm_count)));
+  switch (world) {
+    case 2: lcn_launch(k_dp_reduce<2>, grid, dim3(256), 0, st, d, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    case 4: lcn_launch(k_dp_reduce<4>, grid, dim3(256), 0, st, d, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    case 8: lcn_launch(k_dp_reduce<8>, grid, dim3(256), 0, st, d, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    default: lcn_set_error("data-parallel exchange: world size %d not in {2, 4, 8}", world); return LCN_EINVAL;
+  }
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
 int64_t lcn_grad_compact_count(const lcn_model* m) { return make_compact(m).total; }
 int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, bool unpack, cudaStream_t st) {
   const CompactTable ct = make_compact(m);
-  const dim3 grid((unsigned)(m->nnz * m->n_lin + ct.n_other));
+  const dim3 grid(m->nnz * m->n_lin + ct.n_other);
   if (unpack) lcn_launch(k_grad_compact<true>, grid, dim3(256), 0, st, graw, compact, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
   else lcn_launch(k_grad_compact<false>, grid, dim3(256), 0, st, graw, compact, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
   LCN_CHECK_LAUNCH();
@@ -1673,12 +1798,6 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
         LCN_CHECK_CUDA(cudaEventRecord(ax->ev_wg[l & 1], wst));
         wg_pending[l & 1] = true;
       }
-      // data parallel: this layer's weight gradient is final -> average it over the ranks now, behind the wgrad GEMM,
-      // while the layers below are still being differentiated (lcn_dp.cu)
-      if (dp) {
-        int rc2 = lcn_dp_allreduce_after(m, wst, graw + L.w_off, (size_t)L.Kin * L.Kout);
-        if (rc2) return rc2;
-      }
       const size_t wofs = (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
       rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), ws + lay.off_wp16b + wofs, nullptr,
                        reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(D(nxt)),
@@ -1702,24 +1821,9 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   }
   if (dp) {
-    // what only completes with the last kernels of the pass -- edge-layer weights (contiguous with their biases), the
-    // mid layers' biases, every BatchNorm gamma / beta (one contiguous tail of the parameter layout) -- travels as one
-    // grouped launch; then the caller's stream joins the communication stream: the bucket holds the ranks' average
-    int64_t offs[LCN_MAX_LIN + 1], cnts[LCN_MAX_LIN + 1];
-    int nr = 0;
-    for (int l = 0; l < m->n_lin; ++l) {
-      const LayerInfo& L = m->L[l];
-      const bool edge = l == 0 || l == m->n_lin - 1;
-      offs[nr] = edge ? L.w_off : L.b_off;
-      cnts[nr] = (edge ? (L.b_off - L.w_off) : 0) + L.Kout;
-      ++nr;
-    }
-    offs[nr] = m->L[0].gamma_off;
-    cnts[nr] = m->n_params - m->L[0].gamma_off;
-    ++nr;
-    int rc2 = lcn_dp_allreduce_group_after(m, st, graw, offs, cnts, nr);
-    if (rc2) return rc2;
-    rc2 = lcn_dp_join(m, st);
+    // data parallel: the bucket is complete on this stream -> two-shot all-reduce over NVLink peer memory (lcn_dp.cu);
+    // on return (in stream order) it holds the mean over the ranks
+    int rc2 = lcn_dp_exchange(m, graw, st);
     if (rc2) return rc2;
   }
   return LCN_OK;

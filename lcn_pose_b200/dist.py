@@ -6,11 +6,10 @@
 * Data-parallel training all-reduces ONE bucket (the raw gradients, packed to the nonzero weight blocks + the small
   tensors: average_gradients_packed; or the flat parameter-layout vector: average_gradient_bucket) between backward
   and the fused Adam step; BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
-* Two exchange modes for training.  "overlap" (default, init_native_dp + LcnEngine.train_step_graph): the library owns an
-  NCCL communicator and lcn_model_backward all-reduces every layer's weight gradient right behind its weight-gradient
-  GEMM, overlapped with the rest of the backward pass; the whole step is ONE CUDA graph (csrc/lcn_dp.cu).  "packed": the
-  round-1 path -- backward, pack the nonzero blocks, one torch.distributed all-reduce, unpack, Adam -- two graphs
-  around an exposed collective; kept as the reference point the overlap is measured against.
+* Two exchange modes for training.  "p2p" (default, init_native_dp + LcnEngine.train_step_graph): lcn_model_backward ends
+  with the library's own two-shot all-reduce of the packed bucket over NVLink peer memory (csrc/lcn_dp.cu); the whole
+  step is ONE CUDA graph.  "packed": the round-1 path -- backward, pack the nonzero blocks, one torch.distributed (NCCL)
+  all-reduce, unpack, Adam -- two graphs around the library collective; kept as the reference point.
 Everything else here is backend agnostic (nccl on GPUs, gloo in the CPU tests)."""
 import torch
 import torch.distributed as dist
@@ -64,28 +63,30 @@ def broadcast_parameters(flat_params, src=0, group=None):
 
 
 def init_native_dp(engine, group=None):
-    """Create the engine's own NCCL communicator (lcn_dp_init): rank 0 draws the unique id, torch.distributed carries
-    it to the other ranks (any backend).  Collective over `group`.  No-op in a single process."""
+    """Connect the engine's exchange buffers across the ranks (lcn_dp_export / lcn_dp_connect): every rank exports the CUDA
+    IPC handle of its buffer, torch.distributed all-gathers them (any backend).  Collective over `group`.  No-op in a
+    single process."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return False
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    box = [engine.dp_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0, group=group)
-    engine.dp_init(box[0], rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.dp_export(), group=group)
+    engine.dp_connect(handles, rank, world)
+    dist.barrier(group)                    # nobody starts exchanging before everybody has mapped everybody
     return True
 
 
-def dp_train_step(engine, x, labels, dropout=0.0, mode="overlap", group=None, graph=True):
+def dp_train_step(engine, x, labels, dropout=0.0, mode="p2p", group=None, graph=True):
     """One data-parallel train step on this rank's shard of the global batch; returns (loss, lr) like train_step.
-    mode "overlap": exchange inside lcn_model_backward (needs init_native_dp once); "packed": torch all-reduce of the
+    mode "p2p": exchange inside lcn_model_backward (init_native_dp is run on first use); "packed": torch all-reduce of the
     packed bucket between backward and Adam."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if mode == "overlap":
+    if mode == "p2p":
         if multi and getattr(engine, "dp_world", 1) == 1:
             init_native_dp(engine, group)
         return engine.train_step_graph(x, labels, dropout) if graph else engine.train_step(x, labels, dropout)
     if mode != "packed":
-        raise ValueError("mode must be 'overlap' or 'packed'")
+        raise ValueError("mode must be 'p2p' or 'packed'")
     if getattr(engine, "dp_world", 1) > 1:
         engine.dp_enable(False)          # the torch-level exchange below replaces the one inside backward
         engine.dp_world = -engine.dp_world

@@ -91,13 +91,28 @@ class LcnEngine:
         self._dyn_ev = [None] * 64
         self._graphs = {}
 
-    def __del__(self):
+    def close(self):
+        """Release the model handle.  Captured train-step graphs go first: a CUDA graph that recorded collectives of the
+        model's NCCL communicator (data-parallel steps) keeps that communicator referenced, and NCCL does not let go of a
+        communicator before every such graph is destroyed -- lcn_model_destroy would wait forever."""
+        try:
+            if getattr(self, "_graphs", None):
+                self._graphs.clear()
+                torch.cuda.synchronize(self.device)
+        except Exception:
+            pass
         try:
             if getattr(self, "h", None):
+                if getattr(self, "_dp_bucket_owner", None) is not None:
+                    self.grads_raw = None          # a view of the library's peer-mapped bucket, freed with the handle
+                    self._dp_bucket_owner = None
                 self.lib.lcn_model_destroy(self.h)
                 self.h = None
         except Exception:
             pass
+
+    def __del__(self):
+        self.close()
 
     # ---- parameters -------------------------------------------------------------------------
     def tensor(self, name):
@@ -251,19 +266,30 @@ class LcnEngine:
         return self.loss_dev
 
     # ---- data-parallel exchange inside the backward pass (csrc/lcn_dp.cu) ---------------------------------
-    def dp_init(self, unique_id, rank, world):
-        """Collective: give the model its NCCL communicator (lcn_dp_init).  unique_id: the 128 bytes rank 0 obtained from
-        LcnEngine.dp_unique_id(), identical on every rank.  From here on backward() returns rank-averaged gradients."""
-        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
-        L.check(self.lib.lcn_dp_init(self.h, C.byref(buf), int(rank), int(world)))
+    def dp_export(self):
+        """Allocate this rank's exchange buffer and return its 64-byte CUDA IPC handle (lcn_dp_export)."""
+        buf = (C.c_uint8 * 64)()
+        L.check(self.lib.lcn_dp_export(self.h, C.byref(buf)))
+        return bytes(buf)
+
+    def dp_connect(self, handles, rank, world):
+        """Map every rank's exchange buffer (lcn_dp_connect).  handles: the `world` handles of dp_export in rank order.
+        From here on backward() returns rank-averaged gradients."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        L.check(self.lib.lcn_dp_connect(self.h, C.byref(buf), int(rank), int(world)))
         self._graphs.clear()
         self.dp_world = int(world)
+        # the gradient bucket moves into the peer-mapped allocation of the library (lcn_dp_bucket): a zero-copy torch
+        # view of it through the CUDA array interface replaces the torch-allocated one
+        ptr = int(self.lib.lcn_dp_bucket(self.h))
 
-    @staticmethod
-    def dp_unique_id():
-        buf = (C.c_uint8 * 128)()
-        L.check(L.load().lcn_dp_unique_id(C.byref(buf)))
-        return bytes(buf)
+        class _Bucket:
+            __cuda_array_interface__ = {"shape": (self.n_params,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._dp_bucket_owner = _Bucket()
+        self.grads_raw = torch.as_tensor(self._dp_bucket_owner, device=self.device)
+        assert self.grads_raw.data_ptr() == ptr
 
     def dp_enable(self, on):
         L.check(self.lib.lcn_dp_enable(self.h, int(bool(on))))

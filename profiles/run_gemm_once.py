@@ -5,7 +5,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.gpu_helpers import make_pair, synth_xy, dev
 from lcn_pose_b200 import _lib as L
-eng, cfg, p = make_pair(L=3, knn=3, path='bf16')
+eng, cfg, p = make_pair(L=3, knn=3, path=os.environ.get('LCN_BENCH_PATH', 'bf16'))
 x, _ = synth_xy(4096)
 xd = dev(x)
 for _ in range(3): eng.forward(xd, bn_group=4096, training=True)

@@ -21,7 +21,15 @@ from lcn_pose_b200.tools import params_help  # noqa: E402
 from tests.gpu_helpers import synth_xy  # noqa: E402
 
 
+def stage(msg):
+    if os.environ.get("LCN_DP_TRACE"):
+        print(f"[rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
+    if os.environ.get("LCN_HANG_TRACE"):          # debugging aid: dump every thread's Python stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["LCN_HANG_TRACE"]), exit=False)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -39,6 +47,7 @@ def main():
     x, y = synth_xy(n, seed=100 + rank)                        # every rank its own shard of the global batch
     xd, yd = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
 
+    stage('engine built')
     # ---- (1) the exchanged bucket is the mean of the local buckets ----
     eng.forward(xd, bn_group=n, training=True, dropout=0.25)
     eng.backward(xd, yd, 0.25)
@@ -51,14 +60,18 @@ def main():
     assert err < 1e-6, err
     eng.unpack_grads()
     eng.adam()
+    stage('torch-level bucket mean ok')
     err_native = None
-    if mode == "overlap":
+    if mode == "p2p":
         # the exchange inside lcn_model_backward (per-layer all-reduces behind the weight-gradient GEMMs + the grouped
         # tail) leaves the same mean in the bucket
         eng4 = engine()
         lcn_dist.init_native_dp(eng4)
+        stage('native communicator created')
         eng4.forward(xd, bn_group=n, training=True, dropout=0.25)
         eng4.backward(xd, yd, 0.25)
+        torch.cuda.synchronize()
+        stage('eager backward with the exchange inside finished')
         got = eng4.pack_grads().double()
         err_native = float((got - mean64).abs().max() / mean64.abs().max())
         assert err_native < 1e-5, err_native
@@ -66,9 +79,10 @@ def main():
     # ---- (2) K graph-replayed DP steps (what bench.py --gpus N runs): replicas stay bit-identical ----
     eng2 = engine()
     losses = []
-    for _ in range(steps):
+    for i in range(steps):
         loss, _ = lcn_dist.dp_train_step(eng2, xd, yd, 0.25, mode=mode)
         losses.append(float(loss.item()))
+        stage(f'graph step {i} done')
     flat = torch.cat([eng2.params, eng2.adam_m, eng2.adam_v])
     ref = flat.clone()
     dist.broadcast(ref, src=0)
@@ -92,6 +106,8 @@ def main():
     assert outliers <= 16 and float(d.max()) < 2e-4, (outliers, float(d.max()))
     print(json.dumps({"rank": rank, "world": world, "mode": mode, "bucket_mean_rel_err": err, "native_bucket_mean_rel_err": err_native, "replicas_identical": identical,
                       "losses": losses, "manual_avg_max_param_diff": float(d.max()), "outliers": outliers}), flush=True)
+    for e in (eng, eng2, eng3):
+        e.close()
     dist.barrier()
     dist.destroy_process_group()
 
