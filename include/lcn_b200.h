@@ -178,8 +178,8 @@ int lcn_model_pack_grads(lcn_model* m, const float* d_grads_raw, float* d_compac
 int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_raw, void* stream);
 
 /* Data-parallel training with the exchange INSIDE the backward pass (csrc/lcn_dp.cu): a two-shot all-reduce of the
- * packed bucket over NVLink peer memory, written for this bucket -- reduce-scatter by peer loads, all-gather by peer
- * stores, flags with release / acquire at system scope, no library collective.  One process per GPU (<= 8 GPUs of one
+ * packed bucket over NVLink peer memory, written for this bucket -- reduce-scatter by peer stores into the owner's staging slots, all-gather
+ * by peer stores into every rank's bucket, flags with release / acquire at system scope, no library collective.  One process per GPU (<= 8 GPUs of one
  * NVLink domain; world size 2, 4 or 8).  Setup: every rank calls lcn_dp_export (allocates the rank's gradient bucket -- the
  * ONE device allocation this library makes, because peers must be able to map it -- and returns its 64-byte CUDA IPC
  * handle), the host all-gathers the handles by any means (torch.distributed, MPI, a file), every rank calls
@@ -190,7 +190,7 @@ int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_
  * lcn_model_backward calls.  BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
  * lcn_dp_enable(m, 0) switches the exchange off for calls that want the local gradient (tests, the host-side
  * packed-bucket path above). */
-int lcn_dp_export(lcn_model* m, void* h_handle64);
+int lcn_dp_export(lcn_model* m, int world, void* h_handle64);
 float* lcn_dp_bucket(const lcn_model* m);   /* the rank's peer-mapped gradient bucket: pass it as d_grads_raw */
 int lcn_dp_connect(lcn_model* m, const void* h_handles /* world x 64 bytes, rank order */, int rank, int world);
 int lcn_dp_world(const lcn_model* m);

@@ -54,7 +54,7 @@ PROTOTYPES = {
     "lcn_model_grad_compact_count": (_i64, [_vp]),
     "lcn_model_pack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
     "lcn_model_unpack_grads": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "lcn_dp_export": (C.c_int, [_vp, _vp]),
+    "lcn_dp_export": (C.c_int, [_vp, C.c_int, _vp]),
     "lcn_dp_bucket": (_vp, [_vp]),
     "lcn_dp_connect": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "lcn_dp_world": (C.c_int, [_vp]),

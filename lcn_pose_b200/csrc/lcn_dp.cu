@@ -3,31 +3,33 @@
 // tf.Session); this is the exchange step a data-parallel host needs between optimizer.compute_gradients and
 // apply_gradients (:408-409).
 //
-// One process per GPU.  Every rank owns ONE device allocation [flags | gradient bucket] that all peers map through CUDA
-// IPC (lcn_dp_export -> the host all-gathers the 64-byte handles -> lcn_dp_connect); lcn_dp_bucket() is the pointer the
-// caller passes as d_grads_raw, so the backward pass writes its gradients straight into peer-visible memory.  At the
-// end of lcn_model_backward:
+// One process per GPU.  Every rank owns ONE device allocation [flags | gradient bucket | staging slots] that all peers map
+// through CUDA IPC (lcn_dp_export -> the host all-gathers the 64-byte handles -> lcn_dp_connect); lcn_dp_bucket() is the
+// pointer the caller passes as d_grads_raw, so the backward pass writes its gradients straight into peer-visible memory.
+// At the end of lcn_model_backward (kernels in lcn_kernels.cu, next to the pack kernel whose unit table they share):
 //
-//   k_dp_publish   epoch += 1; ready[me] = epoch in every peer's flag block                (st.release.sys over NVLink)
-//   k_dp_reduce    (lcn_kernels.cu) waits until ready[p] >= epoch for every peer p; the units of the bucket -- nonzero
-//                  joint-pair blocks of the weight gradients, small tensors -- are dealt round-robin to the ranks; for
-//                  its units a rank loads the block from ALL buckets (16-byte loads, the peers' straight over NVLink),
-//                  takes the mean and stores it into ALL buckets: reduce-scatter by peer LOADS, all-gather by peer
-//                  STORES, in place, one pass, no staging or pack / unpack copy; the masked-out 40 % of the bucket never
-//                  travels; the last CTA publishes done[me] = epoch to every peer
-//   k_dp_wait      waits until done[p] >= epoch for every p: every unit of this rank's bucket holds the mean, and every
-//                  peer has finished reading it -- the chain rule / Adam kernels that follow see averaged gradients
+//   k_dp_push     the units of the bucket -- nonzero joint-pair blocks of the weight gradients, small tensors -- are dealt
+//                 round-robin to the ranks; every rank copies its copy of the units it does not own into the owner's staging
+//                 slot [sender] with 16-byte peer STORES (posted writes: no NVLink round trip), then publishes
+//                 pushed[me] = ++epoch at every peer                                      (st.release.sys over NVLink)
+//   k_dp_reduce   the owner waits for pushed[p] >= epoch from every peer, adds its own block and the world-1 staged copies
+//                 (local reads, fixed order: every rank ends up with bit-identical gradients) and stores the mean into ALL
+//                 `world` buckets, in place (peer stores again); the masked-out 40 % of the bucket never travels; the last
+//                 CTA publishes done[me] = epoch at every peer
+//   k_dp_wait     waits until done[p] >= epoch for every p: every unit of this rank's bucket holds the mean -- the chain
+//                 rule / Adam kernels that follow see averaged gradients
 //
-// Each gradient byte crosses the NVLink fabric once in each direction.  Measured against ncclAllReduce of the packed
-// bucket (with its pack / unpack passes, two graph replays) and against NCCL all-reduces per layer overlapped with the
-// backward pass (SLOWER than no overlap: the NCCL CTAs take SMs from single-wave GEMMs and two-blocks-per-SM elementwise
-// kernels): DESIGN.md section 5.
+// Each gradient byte crosses the NVLink fabric once in each direction, always as a store.  Measured against ncclAllReduce
+// of the packed bucket (with its pack / unpack passes, two graph replays), against the same exchange with peer LOADS, and
+// against NCCL all-reduces per layer overlapped with the backward pass (SLOWER than no overlap: the NCCL CTAs take SMs
+// from single-wave GEMMs and two-blocks-per-SM elementwise kernels): DESIGN.md section 5.
 //
 // Why this is safe without a cluster-wide barrier: flags only ever grow (epoch numbers), every rank executes the same
-// sequence of exchanges, unit sets of different ranks are disjoint (in-place is race free), and the two waits order the
-// reuse of the bucket -- a rank starts the next backward pass (which overwrites its bucket) only after k_dp_wait(e), i.e.
-// after every peer published done(e), which a peer does after its last read of that bucket; a peer touches this rank's
-// bucket for epoch e+1 only after this rank published ready(e+1).  All three kernels take only device pointers and read
+// sequence of exchanges, unit sets of different ranks are disjoint (in-place is race free), and the waits order every
+// reuse -- an owner overwrites a unit in a peer's bucket only after that peer's pushed(e), i.e. after the peer has read
+// it; a rank starts the next backward pass (which overwrites its bucket) and the next push (which overwrites the owners'
+// staging slots) only after k_dp_wait(e), i.e. after every owner published done(e), which it does after its last read of
+// its staging slots and its last store into this rank's bucket.  All three kernels take only device pointers and read
 // the epoch from device memory, so the exchange is captured into the train-step CUDA graph like any other kernel of the
 // step.  No kernel needs a peer's kernel to be co-scheduled in order to FINISH its own loads and stores; the waits are on
 // flags that the peers' stream-ordered work sets unconditionally, so a late peer delays, never deadlocks.
@@ -43,9 +45,9 @@
 struct LcnDpFlags {                       // lives at the start of every rank's exchange allocation
   unsigned long long epoch;               // local: exchanges started by this rank
   unsigned long long pad0[15];
-  unsigned long long ready[LCN_DP_MAX_WORLD];   // ready[p]: written by rank p -- its xbuf holds epoch's bucket
+  unsigned long long ready[LCN_DP_MAX_WORLD];   // pushed[p]: written by rank p -- its copies of our units sit in our staging slot p
   unsigned long long pad1[8];
-  unsigned long long done[LCN_DP_MAX_WORLD];    // done[p]: written by rank p -- slice p of our rbuf holds epoch's mean
+  unsigned long long done[LCN_DP_MAX_WORLD];    // done[p]: written by rank p -- the units it owns hold epoch's mean in our bucket
   unsigned long long pad2[8];
   unsigned int ticket;                    // local: CTAs of k_dp_reduce that have finished
 };
@@ -54,6 +56,8 @@ struct LcnDp {
   int rank = 0, world = 1;
   bool enabled = true, connected = false;
   int64_t count = 0;                      // floats in the bucket (= lcn_model_param_count)
+  int64_t packed = 0;                     // floats in one staging slot (= lcn_model_grad_compact_count, 16-byte rounded)
+  size_t stage_off = 0, slot_bytes = 0;   // staging: `world` slots behind the bucket
   size_t bytes = 0;
   char* base = nullptr;                   // own allocation
   char* peer[LCN_DP_MAX_WORLD] = {};      // mapped allocations (peer[rank] == base)
@@ -75,18 +79,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void k_dp_publish(DpFlagPtrs d) {
-  lcn_pdl_prologue();
-  __shared__ unsigned long long e_s;
-  if (threadIdx.x == 0) {
-    e_s = d.flags[d.rank]->epoch + 1;
-    d.flags[d.rank]->epoch = e_s;
-    __threadfence_system();                // the bucket (previous kernels of this stream) is visible system-wide before the flag
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < d.world) st_release_sys(&d.flags[threadIdx.x]->ready[d.rank], e_s);
-}
-
 __global__ void k_dp_wait(DpFlagPtrs d) {
   lcn_pdl_prologue();
   LcnDpFlags* mine = d.flags[d.rank];
@@ -105,16 +97,19 @@ __global__ void k_dp_wait(DpFlagPtrs d) {
 }  // namespace
 
 // ---- host side ----------------------------------------------------------------------------------------------------
-static size_t dp_bytes(int64_t count) { return LCN_DP_FLAG_BYTES + (((size_t)count * 4 + 255) & ~(size_t)255); }
-
-extern "C" int lcn_dp_export(lcn_model* m, void* h_handle64) {
+extern "C" int lcn_dp_export(lcn_model* m, int world, void* h_handle64) {
   LCN_REQUIRE(m != nullptr && h_handle64 != nullptr, "null argument");
   LCN_REQUIRE(m->dp == nullptr, "the model already has an exchange buffer");
+  LCN_REQUIRE(world == 2 || world == 4 || world == 8, "world size %d not in {2, 4, 8}", world);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   static_assert(sizeof(LcnDpFlags) <= LCN_DP_FLAG_BYTES, "flag block");
   LcnDp* dp = new LcnDp();
+  dp->world = world;
   dp->count = m->n_params;
-  dp->bytes = dp_bytes(dp->count);
+  dp->packed = (lcn_grad_compact_count(m) + 3) & ~(int64_t)3;
+  dp->stage_off = LCN_DP_FLAG_BYTES + (((size_t)dp->count * 4 + 255) & ~(size_t)255);
+  dp->slot_bytes = ((size_t)dp->packed * 4 + 255) & ~(size_t)255;
+  dp->bytes = dp->stage_off + (size_t)world * dp->slot_bytes;
   // the one device allocation the library makes: peers have to map it, so it cannot come from the caller's allocator
   cudaError_t e = cudaMalloc(&dp->base, dp->bytes);
   if (e == cudaSuccess) e = cudaMemset(dp->base, 0, dp->bytes);
@@ -139,11 +134,10 @@ extern "C" float* lcn_dp_bucket(const lcn_model* m) {
 extern "C" int lcn_dp_connect(lcn_model* m, const void* h_handles, int rank, int world) {
   LCN_REQUIRE(m != nullptr && h_handles != nullptr, "null argument");
   LCN_REQUIRE(m->dp != nullptr && !m->dp->connected, "call lcn_dp_export first (once)");
-  LCN_REQUIRE(world >= 1 && world <= LCN_DP_MAX_WORLD && rank >= 0 && rank < world, "rank %d / world %d (max %d)", rank, world,
-              LCN_DP_MAX_WORLD);
+  LCN_REQUIRE(world == m->dp->world && rank >= 0 && rank < world, "rank %d / world %d (exported for world %d)", rank, world,
+              m->dp->world);
   LcnDp* dp = m->dp;
   dp->rank = rank;
-  dp->world = world;
   for (int p = 0; p < world; ++p) {
     if (p == rank) {
       dp->peer[p] = dp->base;
@@ -196,17 +190,19 @@ int lcn_dp_exchange(const lcn_model* m, float* graw, cudaStream_t st) {
   memset(&f, 0, sizeof(f));
   f.rank = dp->rank;
   f.world = dp->world;
-  float* buckets[LCN_DP_MAX_WORLD];
-  unsigned long long* done_at[LCN_DP_MAX_WORLD];
+  float *buckets[LCN_DP_MAX_WORLD], *stage_at[LCN_DP_MAX_WORLD], *stage_local[LCN_DP_MAX_WORLD];
+  unsigned long long *pushed_at[LCN_DP_MAX_WORLD], *done_at[LCN_DP_MAX_WORLD];
   for (int p = 0; p < dp->world; ++p) {
     f.flags[p] = reinterpret_cast<LcnDpFlags*>(dp->peer[p]);
     buckets[p] = reinterpret_cast<float*>(dp->peer[p] + LCN_DP_FLAG_BYTES);
+    stage_at[p] = reinterpret_cast<float*>(dp->peer[p] + dp->stage_off + (size_t)dp->rank * dp->slot_bytes);   // my slot at rank p
+    stage_local[p] = reinterpret_cast<float*>(dp->base + dp->stage_off + (size_t)p * dp->slot_bytes);          // sender p's slot here
+    pushed_at[p] = &f.flags[p]->ready[dp->rank];
     done_at[p] = &f.flags[p]->done[dp->rank];
   }
   LcnDpFlags* mine = f.flags[dp->rank];
-  lcn_launch(k_dp_publish, dim3(1), dim3(32), 0, st, f);
-  LCN_CHECK_LAUNCH();
-  int rc = lcn_launch_dp_reduce(m, buckets, mine->ready, done_at, &mine->epoch, &mine->ticket, dp->rank, dp->world, st);
+  int rc = lcn_launch_dp_exchange(m, buckets, stage_at, stage_local, mine->ready, pushed_at, done_at, &mine->epoch, &mine->ticket,
+                                  dp->rank, dp->world, st);
   if (rc) return rc;
   lcn_launch(k_dp_wait, dim3(1), dim3(32), 0, st, f);
   LCN_CHECK_LAUNCH();

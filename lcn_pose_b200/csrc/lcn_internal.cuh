@@ -276,9 +276,10 @@ int lcn_launch_adam(const lcn_model* m, float* params, float* mm, float* vv, cha
                     const lcn_step_scalars* dyn, cudaStream_t st);
 int64_t lcn_grad_compact_count(const lcn_model* m);
 int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, bool unpack, cudaStream_t st);
-int lcn_launch_dp_reduce(const lcn_model* m, float* const* buckets, unsigned long long* ready_local,
-                         unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
-                         int world, cudaStream_t st);
+int lcn_launch_dp_exchange(const lcn_model* m, float* const* buckets, float* const* stage_at, float* const* stage_local,
+                           unsigned long long* pushed_local, unsigned long long* const* pushed_at,
+                           unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
+                           int world, cudaStream_t st);
 int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
                           int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,

@@ -1373,126 +1373,177 @@ __global__ void __launch_bounds__(256) k_grad_compact(float* __restrict__ graw, 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// data-parallel exchange (lcn_dp.cu): two-shot all-reduce of the gradient bucket over NVLink peer memory, IN PLACE in the
-// parameter-layout bucket of every rank.  The unit of work is the unit of k_grad_compact -- one Fi x Fo joint-pair
-// block of one weight matrix inside the mask support, or one small tensor -- so the masked-out 40 % of the bucket is
-// never read, never sent; units are dealt round-robin to the ranks.  For its units a rank loads the block from ALL
-// `world` buckets (its own and, over NVLink, the peers'), takes the mean in a fixed order (every rank ends up with
-// bit-identical gradients) and stores it into ALL `world` buckets: reduce-scatter by peer loads, all-gather by peer
-// stores, no staging copy, no pack / unpack pass.  Unit sets of different ranks are disjoint, so in-place is race free.
-// Flags (system-scope release / acquire, epoch numbers that only grow): ready[p] -- rank p's bucket is complete;
-// done[p] -- rank p has stored its units everywhere and finished reading everybody's bucket.
-// ------------------------------------------------------------------------------------------------
-struct DpArgs {
-  float* g[8];                            // the `world` gradient buckets (g[rank] is local)
-  unsigned long long* ready_local;        // [8] local flags written by the peers
-  unsigned long long* done_at[8];         // peer p's done[rank] slot
-  unsigned long long* epoch;              // local
-  unsigned int* ticket;                   // local
-  int rank, world;
-};
-__device__ __forceinline__ float4 dp_ld16(const float* p) {   // L2-coherent 16-byte load (peer data: never from L1)
-  float4 r;
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-template <int W>
-__device__ __forceinline__ void dp_mean16(const DpArgs& d, size_t off, float inv) {
-  float4 v[W];
-#pragma unroll
-  for (int p = 0; p < W; ++p) v[p] = dp_ld16(d.g[p] + off);           // all loads in flight before the first add
-  float4 a = v[0];
-#pragma unroll
-  for (int p = 1; p < W; ++p) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
-  a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
-#pragma unroll
-  for (int p = 0; p < W; ++p) *reinterpret_cast<float4*>(d.g[p] + off) = a;
-}
-__device__ __forceinline__ void dp_mean1(const DpArgs& d, size_t off, float inv) {
-  float a = 0.f;
-  for (int p = 0; p < d.world; ++p) a += __ldcg(d.g[p] + off);
-  a *= inv;
-  for (int p = 0; p < d.world; ++p) d.g[p][off] = a;
-}
-template <int W>
-__global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin) {
-  lcn_pdl_prologue();
-  const unsigned long long e = *d.epoch;
-  if ((int)threadIdx.x < d.world) {
-    unsigned long long v, spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(d.ready_local + threadIdx.x) : "memory");
-      if (v < e && ++spins > (1ull << 28)) { printf("lcn_dp: wait for a peer's ready flag timed out\n"); __trap(); }
-    } while (v < e);
-  }
-  __syncthreads();
-  const float inv = 1.f / (float)d.world;
-  const int n_units = nnz * n_lin + ct.n_other;
-  for (int b = blockIdx.x * d.world + d.rank; b < n_units; b += gridDim.x * d.world) {
-    if (b < nnz * n_lin) {
-      const int l = b / nnz, p = b - l * nnz;
-      const int Fi = lt.Fi[l], Fo = lt.Fo[l], Kout = LCN_J * Fo;
-      const size_t base = lt.w_off[l] + (size_t)(pt.pi[p] * Fi) * Kout + pt.pj[p] * Fo;
-      if ((Fo & 3) == 0) {
-        const int q = Fo >> 2;
-        for (int t = threadIdx.x; t < Fi * q; t += 256) {
-          const int fi = t / q, c4 = (t - fi * q) * 4;
-          dp_mean16<W>(d, base + (size_t)fi * Kout + c4, inv);
-        }
-      } else {
-        for (int t = threadIdx.x; t < Fi * Fo; t += 256) {
-          const int fi = t / Fo, fo = t - fi * Fo;
-          dp_mean1(d, base + (size_t)fi * Kout + fo, inv);
-        }
-      }
-    } else {
-      const int k = b - nnz * n_lin;
-      const size_t base = ct.o_off[k];
-      const int64_t n = ct.o_size[k], n4 = (base & 3) == 0 ? n / 4 : 0;
-      for (int64_t t = threadIdx.x; t < n4; t += 256) dp_mean16<W>(d, base + 4 * t, inv);
-      for (int64_t t = 4 * n4 + threadIdx.x; t < n; t += 256) dp_mean1(d, base + t, inv);
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(d.ticket, 1u) == gridDim.x - 1) {     // last block of this rank
-    *d.ticket = 0u;
-    __threadfence_system();
-    for (int p = 0; p < d.world; ++p)
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.done_at[p]), "l"(e) : "memory");
-  }
-}
-int lcn_launch_dp_reduce(const lcn_model* m, float* const* buckets, unsigned long long* ready_local,
-                         unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
-                         int world, cudaStream_t st) {
-  const CompactTable ct = make_compact(m);
-  DpArgs d;
-  memset(&d, 0, sizeof(d));
-  for (int p = 0; p < world; ++p) { d.g[p] = buckets[p]; d.done_at[p] = done_at[p]; }
-  d.ready_local = ready_local;
-  d.epoch = epoch;
-  d.ticket = ticket;
-  d.rank = rank;
-  d.world = world;
-  const int n_units = m->nnz * m->n_lin + ct.n_other;
-  const dim3 grid(std::max(1, std::min((n_units + world - 1) / world, 4 * m->sm_count)));
-  switch (world) {
-    case 2: lcn_launch(k_dp_reduce<2>, grid, dim3(256), 0, st, d, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
-    case 4: lcn_launch(k_dp_reduce<4>, grid, dim3(256), 0, st, d, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
-    case 8: lcn_launch(k_dp_reduce<8>, grid, dim3(256), 0, st, d, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
-    default: lcn_set_error("data-parallel exchange: world size %d not in {2, 4, 8}", world); return LCN_EINVAL;
-  }
-  LCN_CHECK_LAUNCH();
-  return LCN_OK;
-}
-
 int64_t lcn_grad_compact_count(const lcn_model* m) { return make_compact(m).total; }
 int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, bool unpack, cudaStream_t st) {
   const CompactTable ct = make_compact(m);
   const dim3 grid(m->nnz * m->n_lin + ct.n_other);
   if (unpack) lcn_launch(k_grad_compact<true>, grid, dim3(256), 0, st, graw, compact, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
   else lcn_launch(k_grad_compact<false>, grid, dim3(256), 0, st, graw, compact, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
+  LCN_CHECK_LAUNCH();
+  return LCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// data-parallel exchange (lcn_dp.cu): two-shot all-reduce of the gradient bucket over NVLink peer memory with STORES only.
+// The unit of work is the unit of k_grad_compact -- one Fi x Fo joint-pair block of one weight matrix inside the mask
+// support, or one small tensor -- so the masked-out 40 % of the bucket is never read, never sent.  Units are dealt
+// round-robin to the ranks (owner = unit % world).
+//   k_dp_push    every rank copies its local copy of the units it does NOT own into the owner's staging area (slot
+//                [sender], packed at the unit's k_grad_compact offset): 16-byte peer stores, posted, no round trip;
+//                the last CTA publishes pushed[me] = epoch at every peer
+//   k_dp_reduce  the owner waits for pushed[p] >= epoch from every peer, then for each of its units adds its own block and
+//                the world-1 staged copies (all LOCAL reads) in a fixed order -- every rank ends up with bit-identical
+//                gradients -- and stores the mean into ALL `world` parameter-layout buckets (peer stores again); the
+//                last CTA publishes done[me] = epoch at every peer
+// The pull variant (reduce-scatter by peer LOADS straight out of the peers' buckets, no staging slots) was built and
+// measured first: 0.632 ms per step at 2 GPUs and 0.682 ms at 8, against 0.631 / 0.676 ms for this one -- the same within
+// run-to-run noise; both move 2 (world-1)/world of the bucket per GPU at ~340 GB/s of NVLink egress.  Stores are kept
+// because they are posted writes whose completion does not depend on a round trip through a busy peer.
+// Unit sets of different ranks are disjoint, so writing the mean in place into every bucket is race free: a rank reads a
+// peer-owned unit of its own bucket only in k_dp_push, and the owner overwrites it only after pushed[] from everybody.
+// ------------------------------------------------------------------------------------------------
+struct DpArgs {
+  float* g[8];                            // the `world` parameter-layout gradient buckets (g[rank] is local)
+  float* stage[8];                        // push: stage[q] = rank q's staging slot for THIS rank; reduce: local slot of sender p
+  unsigned long long* wait_local;         // [8] local flags to wait for (reduce: pushed[]; unused in push)
+  unsigned long long* signal_at[8];       // the flag this kernel publishes at every rank (push: pushed[me]; reduce: done[me])
+  unsigned long long* epoch;              // local epoch counter (push increments it)
+  unsigned int* ticket;                   // local CTA counter
+  int rank, world;
+};
+__device__ __forceinline__ void dp_publish(const DpArgs& d, unsigned long long e) {
+  // all blocks have fenced and taken a ticket; the caller is thread 0 of the last one
+  *d.ticket = 0u;
+  __threadfence_system();
+  for (int p = 0; p < d.world; ++p)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.signal_at[p]), "l"(e) : "memory");
+}
+// geometry of unit b: dense offset of its first element, rows x cols, dense row pitch, offset in the packed order
+struct DpUnit {
+  size_t dense, packed;
+  int rows, cols, pitch;
+};
+__device__ __forceinline__ DpUnit dp_unit(int b, const LinTable& lt, const PairTable& pt, const CompactTable& ct, int nnz, int n_lin) {
+  DpUnit u;
+  if (b < nnz * n_lin) {
+    const int l = b / nnz, p = b - l * nnz;
+    const int Fi = lt.Fi[l], Fo = lt.Fo[l];
+    u.rows = Fi; u.cols = Fo; u.pitch = LCN_J * Fo;
+    u.dense = lt.w_off[l] + (size_t)(pt.pi[p] * Fi) * u.pitch + pt.pj[p] * Fo;
+    u.packed = ct.w_coff[l] + (size_t)p * Fi * Fo;
+  } else {
+    const int k = b - nnz * n_lin;
+    u.rows = 1; u.cols = (int)ct.o_size[k]; u.pitch = u.cols;
+    u.dense = ct.o_off[k];
+    u.packed = ct.o_coff[k];
+  }
+  return u;
+}
+__global__ void __launch_bounds__(256) k_dp_push(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin) {
+  lcn_pdl_prologue();
+  const unsigned long long e = *d.epoch + 1;          // (every block reads the old value: the last block stores the new one)
+  const float* mine = d.g[d.rank];
+  const int n_units = nnz * n_lin + ct.n_other;
+  for (int b = blockIdx.x; b < n_units; b += gridDim.x) {
+    const int owner = b % d.world;
+    if (owner == d.rank) continue;
+    const DpUnit u = dp_unit(b, lt, pt, ct, nnz, n_lin);
+    float* dst = d.stage[owner] + u.packed;
+    if ((u.cols & 3) == 0 && (u.dense & 3) == 0 && (u.packed & 3) == 0) {
+      const int q = u.cols >> 2;
+      for (int t = threadIdx.x; t < u.rows * q; t += 256) {
+        const int r = t / q, c4 = (t - r * q) * 4;
+        *reinterpret_cast<float4*>(dst + r * u.cols + c4) = *reinterpret_cast<const float4*>(mine + u.dense + (size_t)r * u.pitch + c4);
+      }
+    } else {
+      for (int t = threadIdx.x; t < u.rows * u.cols; t += 256) {
+        const int r = t / u.cols, c = t - r * u.cols;
+        dst[t] = mine[u.dense + (size_t)r * u.pitch + c];
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(d.ticket, 1u) == gridDim.x - 1) {
+    *d.epoch = e;
+    dp_publish(d, e);
+  }
+}
+template <int W>
+__global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin) {
+  lcn_pdl_prologue();
+  const unsigned long long e = *d.epoch;
+  if ((int)threadIdx.x < W && (int)threadIdx.x != d.rank) {
+    unsigned long long v, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(d.wait_local + threadIdx.x) : "memory");
+      if (v < e && ++spins > (1ull << 28)) { printf("lcn_dp: wait for a peer's pushed flag timed out\n"); __trap(); }
+    } while (v < e);
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)W;
+  float* mine = d.g[d.rank];
+  const int n_units = nnz * n_lin + ct.n_other;
+  for (int b = blockIdx.x * W + d.rank; b < n_units; b += gridDim.x * W) {
+    const DpUnit u = dp_unit(b, lt, pt, ct, nnz, n_lin);
+    if ((u.cols & 3) == 0 && (u.dense & 3) == 0 && (u.packed & 3) == 0) {
+      const int q = u.cols >> 2;
+      for (int t = threadIdx.x; t < u.rows * q; t += 256) {
+        const int r = t / q, c4 = (t - r * q) * 4;
+        const size_t off = u.dense + (size_t)r * u.pitch + c4;
+        float4 v[W];
+#pragma unroll
+        for (int p = 0; p < W; ++p)                    // rank order, the same on every rank: bit-identical means
+          v[p] = p == d.rank ? *reinterpret_cast<const float4*>(mine + off)
+                             : __ldcg(reinterpret_cast<const float4*>(d.stage[p] + u.packed + r * u.cols + c4));
+        float4 a = v[0];
+#pragma unroll
+        for (int p = 1; p < W; ++p) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+#pragma unroll
+        for (int p = 0; p < W; ++p) *reinterpret_cast<float4*>(d.g[p] + off) = a;
+      }
+    } else {
+      for (int t = threadIdx.x; t < u.rows * u.cols; t += 256) {
+        const int r = t / u.cols, c = t - r * u.cols;
+        const size_t off = u.dense + (size_t)r * u.pitch + c;
+        float a = 0.f;
+        for (int p = 0; p < W; ++p) a += p == d.rank ? mine[off] : __ldcg(d.stage[p] + u.packed + t);
+        a *= inv;
+        for (int p = 0; p < W; ++p) d.g[p][off] = a;
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(d.ticket, 1u) == gridDim.x - 1) dp_publish(d, e);
+}
+// buckets[p], stage_at[q] (rank q's slot for this rank), stage_local[p] (this rank's slot for sender p)
+int lcn_launch_dp_exchange(const lcn_model* m, float* const* buckets, float* const* stage_at, float* const* stage_local,
+                           unsigned long long* pushed_local, unsigned long long* const* pushed_at,
+                           unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
+                           int world, cudaStream_t st) {
+  const CompactTable ct = make_compact(m);
+  DpArgs a, r;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < world; ++p) { a.g[p] = buckets[p]; a.stage[p] = stage_at[p]; a.signal_at[p] = pushed_at[p]; }
+  a.epoch = epoch;
+  a.ticket = ticket;
+  a.rank = rank;
+  a.world = world;
+  r = a;
+  for (int p = 0; p < world; ++p) { r.stage[p] = stage_local[p]; r.signal_at[p] = done_at[p]; }
+  r.wait_local = pushed_local;
+  const int n_units = m->nnz * m->n_lin + ct.n_other;
+  const dim3 gpush(std::max(1, std::min(n_units, 4 * m->sm_count)));
+  const dim3 gred(std::max(1, std::min((n_units + world - 1) / world, 4 * m->sm_count)));
+  lcn_launch(k_dp_push, gpush, dim3(256), 0, st, a, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
+  switch (world) {
+    case 2: lcn_launch(k_dp_reduce<2>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    case 4: lcn_launch(k_dp_reduce<4>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    case 8: lcn_launch(k_dp_reduce<8>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    default: lcn_set_error("data-parallel exchange: world size %d not in {2, 4, 8}", world); return LCN_EINVAL;
+  }
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }

@@ -70,7 +70,7 @@ def init_native_dp(engine, group=None):
         return False
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     handles = [None] * world
-    dist.all_gather_object(handles, engine.dp_export(), group=group)
+    dist.all_gather_object(handles, engine.dp_export(world), group=group)
     engine.dp_connect(handles, rank, world)
     dist.barrier(group)                    # nobody starts exchanging before everybody has mapped everybody
     return True

@@ -266,10 +266,10 @@ class LcnEngine:
         return self.loss_dev
 
     # ---- data-parallel exchange inside the backward pass (csrc/lcn_dp.cu) ---------------------------------
-    def dp_export(self):
+    def dp_export(self, world):
         """Allocate this rank's exchange buffer and return its 64-byte CUDA IPC handle (lcn_dp_export)."""
         buf = (C.c_uint8 * 64)()
-        L.check(self.lib.lcn_dp_export(self.h, C.byref(buf)))
+        L.check(self.lib.lcn_dp_export(self.h, int(world), C.byref(buf)))
         return bytes(buf)
 
     def dp_connect(self, handles, rank, world):
