@@ -1,5 +1,6 @@
-// bf16 tensor-core kernels of the LCN layers for sm_100a: tcgen05.mma with TMEM accumulators, operands staged by
-// 1-D bulk TMA (cp.async.bulk) through mbarrier pipelines.
+// Tensor-core kernels of the LCN layers for sm_100a: tcgen05.mma with TMEM accumulators, operands staged by
+// 1-D bulk TMA (cp.async.bulk) through mbarrier pipelines.  Two instantiations each: bf16 operands (LCN_PATH_BF16), and
+// split-bf16 operands -- (hi, lo) planes, three products per block -- for the fp32-parity path (LCN_PATH_FP32, X3).
 //
 //   k_tc_gemm  : Y[128-row tile, group of <=6 output chunks] = sum over the input chunks that have a nonzero 64x64
 //                block into the group of  A[tile, chunk] (128x64, K-major SW128)  x  Wp(panel of present blocks) --

@@ -1,7 +1,8 @@
 // CUDA-core kernels of the LCN hot path: weight preparation (clip_by_norm + mask + pack), the edge
-// layers (17*in_F -> 17*F and 17*F -> 51), BatchNorm statistics / apply, the fp32 block-sparse GEMMs
-// of the 1e-4 parity path, the whole backward pass and the fused masked TF1-Adam step.
-// The bf16 tensor-core (tcgen05) mid-layer GEMMs live in lcn_gemm_tc.cu.
+// layers (17*in_F -> 17*F and 17*F -> 51), BatchNorm statistics / apply, the elementwise half of the backward
+// pass, the fused masked TF1-Adam step, the pack / exchange kernels of data-parallel training, and the
+// orchestration of the forward / backward passes of both arithmetic paths.
+// The tensor-core (tcgen05) mid-layer GEMMs of both paths live in lcn_gemm_tc.cu.
 //
 // Reference semantics implemented here (paths relative to the reference root):
 //   network/models_att.py:534-586 (mask, mask_weights), :588-612 (BN), :630-775 (layers, head),
