@@ -274,8 +274,9 @@ def run_train(args, rank, world, local_rank, dev):
     fwd_flop = fwd_flop_per_pose(nnz, LAYERS, F)
     eng = make_engine(cfg_id, args.path, local_rank)
     mode = args.dp_mode
-    if world > 1 and mode == "p2p":
+    if world > 1 and mode in ("p2p", "p2p-end"):
         lcn_dist.init_native_dp(eng)
+        eng.dp_enable(1 if mode == "p2p" else 2)
     x, y = synth_xy(BATCH, seed=1234 + rank)
     xd, yd = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
     x_pin, y_pin = torch.as_tensor(x).pin_memory(), torch.as_tensor(y).pin_memory()
@@ -401,8 +402,10 @@ def run_train(args, rank, world, local_rank, dev):
             "data": "synthetic", "config": workload_config(cfg_id, args.dropout),
             "detail": {"path": args.path, "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per step)",
                        "parallelism": (f"dp{world}: per-GPU BatchNorm statistics; gradient exchange: " +
-                                       ("two-shot all-reduce of the packed bucket over NVLink peer memory inside lcn_model_backward (csrc/lcn_dp.cu), one graph per step"
-                                        if mode == "p2p" else "one torch.distributed all-reduce of the packed bucket between two graphs"))
+                                       {"p2p": "two-shot all-reduce over NVLink peer memory inside lcn_model_backward (csrc/lcn_dp.cu), streamed per layer behind the weight-gradient GEMMs, one graph per step",
+                                        "p2p-end": "two-shot all-reduce of the whole bucket over NVLink peer memory at the end of lcn_model_backward (csrc/lcn_dp.cu), one graph per step",
+                                        "packed": "one torch.distributed all-reduce of the packed bucket between two graphs",
+                                        "none": "none (replicas diverge: measurement floor only)"}[mode])
                        if world > 1 else "single GPU"},
             "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "poses/s",
                     "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4},
@@ -676,7 +679,7 @@ def main():
     ap.add_argument("--path", default=os.environ.get("LCN_BENCH_PATH", "bf16"), choices=["bf16", "x3", "fp32"],
                     help="bf16: 1e-2 parity path; x3 (= fp32): fp32-parity path on the tensor cores (split-bf16 operands)")
     ap.add_argument("--dropout", type=float, default=0.25)     # params_help.py:166 training default
-    ap.add_argument("--dp-mode", default=os.environ.get("LCN_DP_MODE", "p2p"), choices=["p2p", "packed", "none"],
+    ap.add_argument("--dp-mode", default=os.environ.get("LCN_DP_MODE", "p2p"), choices=["p2p", "p2p-end", "packed", "none"],
                     help="gradient exchange: p2p (library kernel over NVLink peer memory), packed (torch / NCCL all-reduce of the packed "
                          "bucket), none (NO exchange -- calibration of the multi-process overhead only, replicas diverge)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -188,13 +188,16 @@ int lcn_model_unpack_grads(lcn_model* m, const float* d_compact, float* d_grads_
  * kernel (in stream order; capturable into the caller's CUDA graph like every other call), so
  * lcn_model_adam_step needs no change and a data-parallel step is one graph.  Every rank must issue the same sequence of
  * lcn_model_backward calls.  BatchNorm statistics stay per GPU (== the reference at batch B per GPU).
- * lcn_dp_enable(m, 0) switches the exchange off for calls that want the local gradient (tests, the host-side
- * packed-bucket path above). */
+ * The exchange is STREAMED: the joint-pair blocks of every mid-layer weight gradient travel on a third stream of the
+ * model as soon as that layer's weight-gradient GEMM has finished, under the rest of the backward pass; only the first /
+ * last layer and the small tensors (< 2 % of the bucket) are exchanged after it.
+ * lcn_dp_enable(m, mode): 1 (default) streamed; 2 one exchange of the whole bucket at the end of the backward pass;
+ * 0 no exchange, for calls that want the local gradient (tests, the host-side packed-bucket path above). */
 int lcn_dp_export(lcn_model* m, int world, void* h_handle64);
 float* lcn_dp_bucket(const lcn_model* m);   /* the rank's peer-mapped gradient bucket: pass it as d_grads_raw */
 int lcn_dp_connect(lcn_model* m, const void* h_handles /* world x 64 bytes, rank order */, int rank, int world);
 int lcn_dp_world(const lcn_model* m);
-int lcn_dp_enable(lcn_model* m, int on);
+int lcn_dp_enable(lcn_model* m, int mode);
 
 /* (a10) ... or applies TF1 Adam directly from the raw gradients in one fused pass (models_att.py:404-409):
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (host scalar); theta -= lr_t*m/(sqrt(v)+eps).

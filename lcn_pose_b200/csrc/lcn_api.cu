@@ -229,6 +229,9 @@ extern "C" void lcn_model_destroy(lcn_model* m) {
   lcn_dp_destroy(m);
   if (m->aux.ready) {
     cudaStreamDestroy(m->aux.st);
+    cudaStreamDestroy(m->aux.xst);
+    cudaEventDestroy(m->aux.ev_x);
+    cudaEventDestroy(m->aux.ev_xdone);
     cudaEventDestroy(m->aux.ev_go);
     cudaEventDestroy(m->aux.ev_done);
     cudaEventDestroy(m->aux.ev_ms);

@@ -41,6 +41,8 @@
 
 #define LCN_DP_MAX_WORLD 8
 #define LCN_DP_FLAG_BYTES 4096
+#define LCN_DP_STREAMED 1
+#define LCN_DP_AT_END 2
 
 struct LcnDpFlags {                       // lives at the start of every rank's exchange allocation
   unsigned long long epoch;               // local: exchanges started by this rank
@@ -54,7 +56,8 @@ struct LcnDpFlags {                       // lives at the start of every rank's 
 
 struct LcnDp {
   int rank = 0, world = 1;
-  bool enabled = true, connected = false;
+  int mode = LCN_DP_STREAMED;             // lcn_dp_enable: 0 off, 1 streamed behind the weight-gradient GEMMs, 2 one exchange at the end
+  bool connected = false;
   int64_t count = 0;                      // floats in the bucket (= lcn_model_param_count)
   int64_t packed = 0;                     // floats in one staging slot (= lcn_model_grad_compact_count, 16-byte rounded)
   size_t stage_off = 0, slot_bytes = 0;   // staging: `world` slots behind the bucket
@@ -163,7 +166,8 @@ extern "C" int lcn_dp_world(const lcn_model* m) { return (m && m->dp && m->dp->c
 extern "C" int lcn_dp_enable(lcn_model* m, int on) {
   LCN_REQUIRE(m != nullptr, "null model");
   LCN_REQUIRE((m->dp != nullptr && m->dp->connected) || !on, "lcn_dp_enable: the model is not connected (lcn_dp_export / lcn_dp_connect)");
-  if (m->dp) m->dp->enabled = on != 0;
+  LCN_REQUIRE(on >= 0 && on <= 2, "lcn_dp_enable: mode %d not in {0, 1, 2}", on);
+  if (m->dp) m->dp->mode = on;
   return LCN_OK;
 }
 
@@ -179,21 +183,30 @@ void lcn_dp_destroy(lcn_model* m) {
   m->dp = nullptr;
 }
 
-bool lcn_dp_active(const lcn_model* m) { return m->dp != nullptr && m->dp->connected && m->dp->enabled && m->dp->world > 1; }
+int lcn_dp_mode(const lcn_model* m) {
+  return (m->dp != nullptr && m->dp->connected && m->dp->world > 1) ? m->dp->mode : 0;
+}
 
-// Average the raw-gradient bucket over the ranks, in place, on `st` (called at the end of lcn_model_backward).
-int lcn_dp_exchange(const lcn_model* m, float* graw, cudaStream_t st) {
-  LcnDp* dp = m->dp;
-  LCN_REQUIRE(graw == reinterpret_cast<float*>(dp->base + LCN_DP_FLAG_BYTES),
-              "data-parallel model: d_grads_raw must be the peer-mapped bucket returned by lcn_dp_bucket()");
+static DpFlagPtrs dp_flag_ptrs(const LcnDp* dp) {
   DpFlagPtrs f;
   memset(&f, 0, sizeof(f));
   f.rank = dp->rank;
   f.world = dp->world;
+  for (int p = 0; p < dp->world; ++p) f.flags[p] = reinterpret_cast<LcnDpFlags*>(dp->peer[p]);
+  return f;
+}
+
+// Average the units [u0, u1) minus [s0, s1) of the raw-gradient bucket over the ranks, in place, on `st` (u1 < 0: to the
+// end of the bucket).  Every rank makes the same sequence of calls.  The means have landed in this rank's bucket only after a
+// following lcn_dp_wait in stream order.
+int lcn_dp_exchange_units(const lcn_model* m, float* graw, int u0, int u1, int s0, int s1, int max_ctas, cudaStream_t st) {
+  LcnDp* dp = m->dp;
+  LCN_REQUIRE(graw == reinterpret_cast<float*>(dp->base + LCN_DP_FLAG_BYTES),
+              "data-parallel model: d_grads_raw must be the peer-mapped bucket returned by lcn_dp_bucket()");
+  DpFlagPtrs f = dp_flag_ptrs(dp);
   float *buckets[LCN_DP_MAX_WORLD], *stage_at[LCN_DP_MAX_WORLD], *stage_local[LCN_DP_MAX_WORLD];
   unsigned long long *pushed_at[LCN_DP_MAX_WORLD], *done_at[LCN_DP_MAX_WORLD];
   for (int p = 0; p < dp->world; ++p) {
-    f.flags[p] = reinterpret_cast<LcnDpFlags*>(dp->peer[p]);
     buckets[p] = reinterpret_cast<float*>(dp->peer[p] + LCN_DP_FLAG_BYTES);
     stage_at[p] = reinterpret_cast<float*>(dp->peer[p] + dp->stage_off + (size_t)dp->rank * dp->slot_bytes);   // my slot at rank p
     stage_local[p] = reinterpret_cast<float*>(dp->base + dp->stage_off + (size_t)p * dp->slot_bytes);          // sender p's slot here
@@ -201,10 +214,13 @@ int lcn_dp_exchange(const lcn_model* m, float* graw, cudaStream_t st) {
     done_at[p] = &f.flags[p]->done[dp->rank];
   }
   LcnDpFlags* mine = f.flags[dp->rank];
-  int rc = lcn_launch_dp_exchange(m, buckets, stage_at, stage_local, mine->ready, pushed_at, done_at, &mine->epoch, &mine->ticket,
-                                  dp->rank, dp->world, st);
-  if (rc) return rc;
-  lcn_launch(k_dp_wait, dim3(1), dim3(32), 0, st, f);
+  return lcn_launch_dp_exchange(m, buckets, stage_at, stage_local, mine->ready, pushed_at, done_at, &mine->epoch, &mine->ticket,
+                                dp->rank, dp->world, u0, u1, s0, s1, max_ctas, st);
+}
+
+// Every exchange enqueued before this call (on streams `st` is ordered after) is complete when this kernel ends.
+int lcn_dp_wait(const lcn_model* m, cudaStream_t st) {
+  lcn_launch(k_dp_wait, dim3(1), dim3(32), 0, st, dp_flag_ptrs(m->dp));
   LCN_CHECK_LAUNCH();
   return LCN_OK;
 }

@@ -71,6 +71,8 @@ struct LcnAux {
   std::mutex mu;
   bool ready = false, failed = false;
   cudaStream_t st = nullptr;
+  cudaStream_t xst = nullptr;        // data-parallel exchange of finished weight gradients (lcn_dp.cu), forked from `st`
+  cudaEvent_t ev_x = nullptr, ev_xdone = nullptr;
   cudaEvent_t ev_go = nullptr, ev_done = nullptr, ev_ms = nullptr, ev_loss = nullptr;
   cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
 };
@@ -244,8 +246,9 @@ static inline void lcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   } while (0)
 
 // ---- data-parallel exchange (lcn_dp.cu) ----
-bool lcn_dp_active(const lcn_model* m);
-int lcn_dp_exchange(const lcn_model* m, float* graw, cudaStream_t st);   // mean of the bucket over the ranks, in place
+int lcn_dp_mode(const lcn_model* m);      // 0: no exchange; 1: streamed behind the weight-gradient GEMMs; 2: one exchange at the end
+int lcn_dp_exchange_units(const lcn_model* m, float* graw, int u0, int u1, int s0, int s1, int max_ctas, cudaStream_t st);
+int lcn_dp_wait(const lcn_model* m, cudaStream_t st);
 void lcn_dp_destroy(lcn_model* m);
 
 // ---- launch wrappers implemented in the kernel translation units ----
@@ -279,7 +282,7 @@ int lcn_launch_grad_compact(const lcn_model* m, float* graw, float* compact, boo
 int lcn_launch_dp_exchange(const lcn_model* m, float* const* buckets, float* const* stage_at, float* const* stage_local,
                            unsigned long long* pushed_local, unsigned long long* const* pushed_at,
                            unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
-                           int world, cudaStream_t st);
+                           int world, int u0, int u1, int s0, int s1, int max_ctas, cudaStream_t st);
 int lcn_launch_layer_gemm(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, int layer,
                           int transposed, cudaStream_t st);
 int lcn_launch_read_tensor(const lcn_model* m, char* ws, const WsLayout& lay, int kind, int layer,

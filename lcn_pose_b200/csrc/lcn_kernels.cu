@@ -240,8 +240,9 @@ static LcnAux* lcn_aux_get(const lcn_model* m) {
   if (a.failed) return nullptr;
   if (!a.ready) {
     bool ok = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[8] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1], &a.ev_ms, &a.ev_loss};
-    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&a.xst, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[10] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1], &a.ev_ms, &a.ev_loss, &a.ev_x, &a.ev_xdone};
+    for (int i = 0; i < 10 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       (void)cudaGetLastError();
       a.failed = true;
@@ -1440,14 +1441,16 @@ __device__ __forceinline__ DpUnit dp_unit(int b, const LinTable& lt, const PairT
   }
   return u;
 }
-__global__ void __launch_bounds__(256) k_dp_push(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin) {
+// Both kernels work on the unit range [u0, u1) minus [s0, s1): the whole bucket, the units of one weight matrix when the
+// exchange is streamed behind the weight-gradient GEMMs (lcn_dp.cu), or what is left after those.
+__global__ void __launch_bounds__(256) k_dp_push(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin,
+                                                 int u0, int u1, int s0, int s1) {
   lcn_pdl_prologue();
   const unsigned long long e = *d.epoch + 1;          // (every block reads the old value: the last block stores the new one)
   const float* mine = d.g[d.rank];
-  const int n_units = nnz * n_lin + ct.n_other;
-  for (int b = blockIdx.x; b < n_units; b += gridDim.x) {
+  for (int b = u0 + blockIdx.x; b < u1; b += gridDim.x) {
     const int owner = b % d.world;
-    if (owner == d.rank) continue;
+    if (owner == d.rank || (b >= s0 && b < s1)) continue;
     const DpUnit u = dp_unit(b, lt, pt, ct, nnz, n_lin);
     float* dst = d.stage[owner] + u.packed;
     if ((u.cols & 3) == 0 && (u.dense & 3) == 0 && (u.packed & 3) == 0) {
@@ -1471,7 +1474,8 @@ __global__ void __launch_bounds__(256) k_dp_push(DpArgs d, LinTable lt, PairTabl
   }
 }
 template <int W>
-__global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin) {
+__global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTable pt, CompactTable ct, int nnz, int n_lin,
+                                                   int u0, int u1, int s0, int s1) {
   lcn_pdl_prologue();
   const unsigned long long e = *d.epoch;
   if ((int)threadIdx.x < W && (int)threadIdx.x != d.rank) {
@@ -1484,8 +1488,9 @@ __global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTa
   __syncthreads();
   const float inv = 1.f / (float)W;
   float* mine = d.g[d.rank];
-  const int n_units = nnz * n_lin + ct.n_other;
-  for (int b = blockIdx.x * W + d.rank; b < n_units; b += gridDim.x * W) {
+  const int first = u0 + ((d.rank - u0 % W) + W) % W;          // first unit >= u0 this rank owns (owner = unit % W)
+  for (int b = first + blockIdx.x * W; b < u1; b += gridDim.x * W) {
+    if (b >= s0 && b < s1) continue;
     const DpUnit u = dp_unit(b, lt, pt, ct, nnz, n_lin);
     if ((u.cols & 3) == 0 && (u.dense & 3) == 0 && (u.packed & 3) == 0) {
       const int q = u.cols >> 2;
@@ -1523,7 +1528,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce(DpArgs d, LinTable lt, PairTa
 int lcn_launch_dp_exchange(const lcn_model* m, float* const* buckets, float* const* stage_at, float* const* stage_local,
                            unsigned long long* pushed_local, unsigned long long* const* pushed_at,
                            unsigned long long* const* done_at, unsigned long long* epoch, unsigned int* ticket, int rank,
-                           int world, cudaStream_t st) {
+                           int world, int u0, int u1, int s0, int s1, int max_ctas, cudaStream_t st) {
   const CompactTable ct = make_compact(m);
   DpArgs a, r;
   memset(&a, 0, sizeof(a));
@@ -1535,14 +1540,17 @@ int lcn_launch_dp_exchange(const lcn_model* m, float* const* buckets, float* con
   r = a;
   for (int p = 0; p < world; ++p) { r.stage[p] = stage_local[p]; r.signal_at[p] = done_at[p]; }
   r.wait_local = pushed_local;
-  const int n_units = m->nnz * m->n_lin + ct.n_other;
-  const dim3 gpush(std::max(1, std::min(n_units, 4 * m->sm_count)));
-  const dim3 gred(std::max(1, std::min((n_units + world - 1) / world, 4 * m->sm_count)));
-  lcn_launch(k_dp_push, gpush, dim3(256), 0, st, a, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin);
+  const int n_all = m->nnz * m->n_lin + ct.n_other;
+  if (u1 < 0 || u1 > n_all) u1 = n_all;
+  const int n_units = u1 - u0 - std::max(0, std::min(s1, u1) - std::max(s0, u0));
+  if (max_ctas <= 0) max_ctas = 4 * m->sm_count;
+  const dim3 gpush(std::max(1, std::min(n_units, max_ctas)));
+  const dim3 gred(std::max(1, std::min((n_units + world - 1) / world, max_ctas)));
+  lcn_launch(k_dp_push, gpush, dim3(256), 0, st, a, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin, u0, u1, s0, s1);
   switch (world) {
-    case 2: lcn_launch(k_dp_reduce<2>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
-    case 4: lcn_launch(k_dp_reduce<4>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
-    case 8: lcn_launch(k_dp_reduce<8>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin); break;
+    case 2: lcn_launch(k_dp_reduce<2>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin, u0, u1, s0, s1); break;
+    case 4: lcn_launch(k_dp_reduce<4>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin, u0, u1, s0, s1); break;
+    case 8: lcn_launch(k_dp_reduce<8>, gred, dim3(256), 0, st, r, make_lin(m), make_pairs(m), ct, m->nnz, m->n_lin, u0, u1, s0, s1); break;
     default: lcn_set_error("data-parallel exchange: world size %d not in {2, 4, 8}", world); return LCN_EINVAL;
   }
   LCN_CHECK_LAUNCH();
@@ -1717,6 +1725,12 @@ int lcn_launch_forward(const FwdArgs& a) {
   return a.m->d.path == LCN_PATH_BF16 ? forward_impl<__nv_bfloat16>(a) : forward_impl<lcn_sp16>(a);
 }
 
+// Streamed data-parallel exchange, measured at 2 GPUs (profiles/r2/dp_streamed_variants.txt): layers >= LCN_DP_STREAM_FROM
+// are exchanged behind their weight-gradient GEMM with one CTA per SM -- 8 CTAs: 0.973 ms/step, 24: 0.656, 64: 0.623,
+// >= 128: 0.618 (the exchange has to keep up with one weight gradient every ~43 us; its CTAs are short-lived and do not
+// slow the backward pass measurably); layer 1, whose gradient is the last to finish, goes with the first / last layer and
+// the small tensors in one full-width exchange at the end (streaming it as well: 0.621).
+#define LCN_DP_STREAM_FROM 2
 template <typename T>
 static int backward_impl(const lcn_model* m, const float* params, char* ws, const WsLayout& lay, const float* x,
                          const float* labels, float rate, uint64_t seed, uint64_t step, float* loss,
@@ -1728,7 +1742,12 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
   LcnAux* ax = lcn_aux_get(m);
   if (ax == nullptr) aux_lock.unlock();
   cudaStream_t wst = ax ? ax->st : st;
-  const bool dp = lcn_dp_active(m);
+  // data parallel (lcn_dp.cu): with a side stream the mean of every mid-layer weight gradient is exchanged over NVLink on a
+  // third stream as soon as its GEMM has finished, under the rest of the backward pass; what is left for the end is the
+  // first and last layer and the small tensors (< 2 % of the bucket)
+  const int dp_mode = lcn_dp_mode(m);
+  const bool dp_stream = dp_mode == 1 && ax != nullptr;
+  bool dp_forked = false;
   bool wg_pending[2] = {false, false};
   const int64_t blast = m->L[m->n_lin - 1].b_off;     // last-layer bias gradient: accumulated by k_loss_dout (caller's stream)
   if (ax) {
@@ -1850,6 +1869,12 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
         LCN_CHECK_CUDA(cudaEventRecord(ax->ev_wg[l & 1], wst));
         wg_pending[l & 1] = true;
       }
+      if (dp_stream && l >= LCN_DP_STREAM_FROM) {   // dW_l is final on the side stream: average its joint-pair blocks over the ranks
+        LCN_CHECK_CUDA(cudaStreamWaitEvent(ax->xst, ax->ev_wg[l & 1], 0));
+        rc = lcn_dp_exchange_units(m, graw, l * m->nnz, (l + 1) * m->nnz, 0, 0, m->sm_count, ax->xst);
+        if (rc) return rc;
+        dp_forked = true;
+      }
       const size_t wofs = (size_t)(l - 1) * m->nnz * FC * FC * 4096 * 2;
       rc = lcn_tc_gemm(m, lay, l - 1, 1, reinterpret_cast<const __nv_bfloat16*>(dZ), ws + lay.off_wp16b + wofs, nullptr,
                        reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(D(nxt)),
@@ -1872,10 +1897,19 @@ static int backward_impl(const lcn_model* m, const float* params, char* ws, cons
     LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, wst));
     LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   }
-  if (dp) {
-    // data parallel: the bucket is complete on this stream -> two-shot all-reduce over NVLink peer memory (lcn_dp.cu);
-    // on return (in stream order) it holds the mean over the ranks
-    int rc2 = lcn_dp_exchange(m, graw, st);
+  if (dp_mode) {
+    // the bucket is complete on this stream -> two-shot all-reduce over NVLink peer memory of whatever has not been
+    // exchanged yet; after the wait (in stream order) the bucket holds the mean over the ranks
+    if (dp_forked) {
+      LCN_CHECK_CUDA(cudaEventRecord(ax->ev_xdone, ax->xst));
+      LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_xdone, 0));
+      int rc2 = lcn_dp_exchange_units(m, graw, 0, -1, LCN_DP_STREAM_FROM * m->nnz, (m->n_lin - 1) * m->nnz, 0, st);   // all but the streamed layers
+      if (rc2) return rc2;
+    } else {
+      int rc2 = lcn_dp_exchange_units(m, graw, 0, -1, 0, 0, 0, st);
+      if (rc2) return rc2;
+    }
+    int rc2 = lcn_dp_wait(m, st);
     if (rc2) return rc2;
   }
   return LCN_OK;

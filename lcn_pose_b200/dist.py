@@ -78,15 +78,17 @@ def init_native_dp(engine, group=None):
 
 def dp_train_step(engine, x, labels, dropout=0.0, mode="p2p", group=None, graph=True):
     """One data-parallel train step on this rank's shard of the global batch; returns (loss, lr) like train_step.
-    mode "p2p": exchange inside lcn_model_backward (init_native_dp is run on first use); "packed": torch all-reduce of the
-    packed bucket between backward and Adam."""
+    mode "p2p": exchange inside lcn_model_backward, streamed behind the weight-gradient GEMMs (init_native_dp is run on
+    first use); "p2p-end": the same kernels, one exchange at the end of the backward pass; "packed": torch all-reduce of
+    the packed bucket between backward and Adam."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if mode == "p2p":
+    if mode in ("p2p", "p2p-end"):
         if multi and getattr(engine, "dp_world", 1) == 1:
             init_native_dp(engine, group)
+            engine.dp_enable(1 if mode == "p2p" else 2)
         return engine.train_step_graph(x, labels, dropout) if graph else engine.train_step(x, labels, dropout)
     if mode != "packed":
-        raise ValueError("mode must be 'p2p' or 'packed'")
+        raise ValueError("mode must be 'p2p', 'p2p-end' or 'packed'")
     if getattr(engine, "dp_world", 1) > 1:
         engine.dp_enable(False)          # the torch-level exchange below replaces the one inside backward
         engine.dp_world = -engine.dp_world

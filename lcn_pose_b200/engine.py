@@ -291,8 +291,10 @@ class LcnEngine:
         self.grads_raw = torch.as_tensor(self._dp_bucket_owner, device=self.device)
         assert self.grads_raw.data_ptr() == ptr
 
-    def dp_enable(self, on):
-        L.check(self.lib.lcn_dp_enable(self.h, int(bool(on))))
+    def dp_enable(self, mode):
+        """lcn_dp_enable: 1 / True streamed behind the weight-gradient GEMMs (default), 2 one exchange at the end of the
+        backward pass, 0 / False none (backward leaves the local gradient)."""
+        L.check(self.lib.lcn_dp_enable(self.h, int(mode)))
         self._graphs.clear()
 
     # ---- data-parallel exchange: only what backward produces travels (lcn_model_pack_grads) ----

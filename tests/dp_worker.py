@@ -62,11 +62,12 @@ def main():
     eng.adam()
     stage('torch-level bucket mean ok')
     err_native = None
-    if mode == "p2p":
-        # the exchange inside lcn_model_backward (per-layer all-reduces behind the weight-gradient GEMMs + the grouped
-        # tail) leaves the same mean in the bucket
+    if mode in ("p2p", "p2p-end"):
+        # the exchange inside lcn_model_backward (streamed per layer behind the weight-gradient GEMMs, or one exchange at
+        # the end) leaves the same mean in the bucket
         eng4 = engine()
         lcn_dist.init_native_dp(eng4)
+        eng4.dp_enable(1 if mode == "p2p" else 2)
         stage('native communicator created')
         eng4.forward(xd, bn_group=n, training=True, dropout=0.25)
         eng4.backward(xd, yd, 0.25)
@@ -106,7 +107,7 @@ def main():
     assert outliers <= 16 and float(d.max()) < 2e-4, (outliers, float(d.max()))
     print(json.dumps({"rank": rank, "world": world, "mode": mode, "bucket_mean_rel_err": err, "native_bucket_mean_rel_err": err_native, "replicas_identical": identical,
                       "losses": losses, "manual_avg_max_param_diff": float(d.max()), "outliers": outliers}), flush=True)
-    for e in (eng, eng2, eng3):
+    for e in (eng, eng2, eng3) + ((eng4,) if err_native is not None else ()):
         e.close()
     dist.barrier()
     dist.destroy_process_group()

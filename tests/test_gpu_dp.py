@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["p2p", "packed"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-end", "packed"])
 def test_replicas_stay_identical_and_bucket_is_the_mean(mode):
     n = torch.cuda.device_count()
     if n < 2:
