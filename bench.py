@@ -208,10 +208,10 @@ def launches_per_step(n_bn, path, gather=False):
     layer) + bn_act per BN layer (the BatchNorm statistics are accumulated by the GEMM itself on the bf16 path; the
     split-bf16 path adds k_bn_finalize), head; backward: loss, head dgrad, last-layer wgrad, BN backward (reduce + apply)
     per BN layer, dgrad + wgrad per mid layer, first-layer wgrad, bias-gradient reduce; optimizer: pairdot, mask gradient,
-    Adam, mask scalars, 5 weight packs."""
+    Adam, 2 weight packs (mid layers; both edge layers)."""
     fwd = 2 * n_bn + 1 + (n_bn if path != "bf16" else 0)
     bwd = 3 + 2 * n_bn + 2 * (n_bn - 1) + 2
-    opt = 9
+    opt = 5
     return fwd + bwd + opt + (1 if gather else 0)
 
 

@@ -94,33 +94,42 @@ __global__ void k_sumsq(const float* __restrict__ params, LinTable lt, LayerScal
   if (threadIdx.x == 0) atomicAdd(&sc[l].norm2, s);
 }
 
-// mask = softmax(var, axis=0) * support (models_att.py:569-571) or the constant; per-layer clip scale
+// mask = softmax(var, axis=0) * support (models_att.py:569-571) or the constant; per-layer clip scale.
+// The weight-pack kernels evaluate these two helpers themselves (one thread per block), so that k_mask_scalars is not a
+// launch of its own in front of them on the tail of every train step; it remains for models without mid layers.
+__device__ __forceinline__ float lcn_mask_value(const float* __restrict__ params, int64_t mask_off, const ConstMask& cmask,
+                                                const SupportBits& sup, int i, int j) {
+  if (!((sup.row[i] >> j) & 1u)) return 0.f;
+  if (mask_off < 0) return cmask.v[i * LCN_J + j];
+  const float* var = params + mask_off;
+  float mx = -INFINITY;
+  for (int k = 0; k < LCN_J; ++k) mx = fmaxf(mx, var[k * LCN_J + j]);
+  float den = 0.f;
+  for (int k = 0; k < LCN_J; ++k) den += expf(var[k * LCN_J + j] - mx);
+  return expf(var[i * LCN_J + j] - mx) / den;
+}
+__device__ __forceinline__ float lcn_inv_norm(const LayerScalars* sc, int l, int max_norm, bool* clipped) {
+  const double nrm = sqrt(sc[l].norm2);
+  const bool clip = max_norm && nrm > 1.0;
+  if (clipped) *clipped = clip;
+  return clip ? (float)(1.0 / nrm) : 1.0f;
+}
+__device__ __forceinline__ void lcn_write_mask_scalars(const float* __restrict__ params, int64_t mask_off,
+                                                       const ConstMask& cmask, const SupportBits& sup, int n_lin,
+                                                       int max_norm, LayerScalars* sc, float* mask_out, int t) {
+  if (t < LCN_J * LCN_J) mask_out[t] = lcn_mask_value(params, mask_off, cmask, sup, t / LCN_J, t % LCN_J);
+  if (t < n_lin) {
+    bool clip;
+    const float inv = lcn_inv_norm(sc, t, max_norm, &clip);
+    sc[t].inv_norm = inv;
+    sc[t].clipped = clip ? 1.f : 0.f;
+  }
+}
 __global__ void k_mask_scalars(const float* __restrict__ params, int64_t mask_off, SupportBits sup,
                                ConstMask cmask, int n_lin, int max_norm,
                                LayerScalars* sc, float* mask_out) {
   lcn_pdl_prologue();
-  int t = threadIdx.x;
-  if (t < LCN_J * LCN_J) {
-    int i = t / LCN_J, j = t % LCN_J;
-    float mval;
-    if (mask_off >= 0) {
-      const float* var = params + mask_off;
-      float mx = -INFINITY;
-      for (int k = 0; k < LCN_J; ++k) mx = fmaxf(mx, var[k * LCN_J + j]);
-      float den = 0.f;
-      for (int k = 0; k < LCN_J; ++k) den += expf(var[k * LCN_J + j] - mx);
-      mval = expf(var[t] - mx) / den;
-    } else {
-      mval = cmask.v[t];
-    }
-    mask_out[t] = ((sup.row[i] >> j) & 1u) ? mval : 0.f;
-  }
-  if (t < n_lin) {
-    double nrm = sqrt(sc[t].norm2);
-    bool clip = max_norm && nrm > 1.0;
-    sc[t].inv_norm = clip ? (float)(1.0 / nrm) : 1.0f;
-    sc[t].clipped = clip ? 1.f : 0.f;
-  }
+  lcn_write_mask_scalars(params, mask_off, cmask, sup, n_lin, max_norm, sc, mask_out, (int)threadIdx.x);
 }
 
 // dense masked effective weight of an edge layer: Wm = W * inv_norm * mask[i,j]
@@ -145,15 +154,27 @@ __global__ void __launch_bounds__(256) k_pack_mid(const float* __restrict__ para
                                                   const float* __restrict__ mask, int F, int FC, int nnz,
                                                   float* __restrict__ wp32, __nv_bfloat16* __restrict__ wp16f,
                                                   __nv_bfloat16* __restrict__ wp16b, __nv_bfloat16* __restrict__ wp16f_lo,
-                                                  __nv_bfloat16* __restrict__ wp16b_lo, int write32, int write16) {
+                                                  __nv_bfloat16* __restrict__ wp16b_lo, int write32, int write16,
+                                                  int64_t mask_off, ConstMask cmask, int n_lin, int max_norm,
+                                                  LayerScalars* sc_out, float* mask_out) {
   lcn_pdl_prologue();
   __shared__ float tile[64][65];     // tile[fi][fo], scaled
+  __shared__ float s_scale;
   int mid = blockIdx.y, l = mid + 1;
   int sb = blockIdx.x;
   int p = sb / (FC * FC), hi = (sb / FC) % FC, ho = sb % FC;
   int i = pt.pi[p], j = pt.pj[p];
   int P = LCN_J * F;
-  float scale = sc[l].inv_norm * mask[i * LCN_J + j];
+  // mask_out != nullptr: this launch stands in for k_mask_scalars -- every block derives its own scale from ||W||^2 and
+  // the mask variable, block (0, 0) also stores the 289 mask values and the per-layer scalars for the kernels that follow
+  if (threadIdx.x == 0)
+    s_scale = mask_out != nullptr ? lcn_inv_norm(sc, l, max_norm, nullptr) * lcn_mask_value(params, mask_off, cmask, sup, i, j)
+                                  : sc[l].inv_norm * mask[i * LCN_J + j];
+  __syncthreads();
+  const float scale = s_scale;
+  if (mask_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
+    for (int t = threadIdx.x; t < LCN_J * LCN_J; t += blockDim.x)
+      lcn_write_mask_scalars(params, mask_off, cmask, sup, n_lin, max_norm, sc_out, mask_out, t);
   const float* w = params + lt.w_off[l] + (size_t)(i * F + hi * 64) * P + j * F + ho * 64;
   size_t mid_sb = (size_t)nnz * FC * FC;
   float* d32 = wp32 + ((size_t)mid * mid_sb + sb) * 4096;
@@ -233,6 +254,61 @@ __global__ void k_pack_first16(const float* __restrict__ wm_first, int Kin, int 
   }
 }
 
+// Both edge layers in ONE launch (replaces k_pack_edge x 2 + k_pack_first16 + k_pack_last16 when 17*in_F <= 64): the
+// dense masked weights Wm = W * inv_norm * mask[i,j] in fp32 (CUDA-core first layer / head of the fp32-parity path, parity
+// taps) and, when the bf16 pointers are given, their tensor-core tiles.  grid (17*FC, 4, 2): z = 0 first layer (x = output
+// chunk), z = 1 last layer (x = channel chunk); y = 16 of the 64 rows of the tile.  Scales from ||W||^2 and the mask
+// variable directly (see lcn_mask_value), so the launch does not wait for k_mask_scalars.
+__global__ void __launch_bounds__(256) k_pack_edges(const float* __restrict__ params, int64_t w_first, int64_t w_last,
+                                                    int in_F, int F, int P, int last, const LayerScalars* sc,
+                                                    int64_t mask_off, ConstMask cmask, SupportBits sup, int max_norm,
+                                                    float* __restrict__ wm_first, float* __restrict__ wm_last,
+                                                    __nv_bfloat16* __restrict__ wf16, __nv_bfloat16* __restrict__ wl16f,
+                                                    __nv_bfloat16* __restrict__ wl16b) {
+  lcn_pdl_prologue();
+  __shared__ float s_m[LCN_J];       // mask column / row of this tile, times inv_norm
+  const int x = blockIdx.x;
+  if (blockIdx.z == 0) {
+    // first layer: rows k = input feature (joint i = k / in_F), columns of output chunk x (joint j = x*64 / F)
+    const int Kin = LCN_J * in_F, j = (x * 64) / F;
+    if ((int)threadIdx.x < LCN_J)
+      s_m[threadIdx.x] = lcn_inv_norm(sc, 0, max_norm, nullptr) * lcn_mask_value(params, mask_off, cmask, sup, threadIdx.x, j);
+    __syncthreads();
+    const float* w = params + w_first;
+    for (int e = blockIdx.y * 1024 + threadIdx.x; e < (int)(blockIdx.y + 1) * 1024; e += blockDim.x) {
+      const int k = e >> 6, n = e & 63;
+      float v = 0.f;
+      if (k < Kin) {
+        const size_t o = (size_t)k * P + x * 64 + n;
+        v = w[o] * s_m[k / in_F];
+        wm_first[o] = v;
+      }
+      if (wf16 != nullptr) wf16[(size_t)x * 4096 + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
+    }
+  } else {
+    // last layer: rows = channels of chunk x (joint i = x*64 / F), columns n = 3*j + c < 51
+    const int i = (x * 64) / F;
+    if ((int)threadIdx.x < LCN_J)
+      s_m[threadIdx.x] = lcn_inv_norm(sc, last, max_norm, nullptr) * lcn_mask_value(params, mask_off, cmask, sup, i, threadIdx.x);
+    __syncthreads();
+    const float* w = params + w_last;
+    for (int e = blockIdx.y * 1024 + threadIdx.x; e < (int)(blockIdx.y + 1) * 1024; e += blockDim.x) {
+      const int k = e >> 6, n = e & 63;
+      float v = 0.f;
+      if (n < 51) {
+        const size_t o = (size_t)(x * 64 + k) * 51 + n;
+        v = w[o] * s_m[n / 3];
+        wm_last[o] = v;
+      }
+      if (wl16f != nullptr) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        wl16f[(size_t)x * 4096 + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = h;
+        wl16b[(size_t)x * 4096 + k * 64 + ((((n >> 3) ^ (k & 7)) << 3) | (n & 7))] = h;
+      }
+    }
+  }
+}
+
 // side stream + events of the model (LcnAux), created on first use under aux.mu (held by the caller); nullptr when
 // the creation failed -- the callers then enqueue everything on the caller's stream
 static LcnAux* lcn_aux_get(const lcn_model* m) {
@@ -265,16 +341,22 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
   }
   ConstMask cmask;
   memcpy(cmask.v, m->d.const_mask, sizeof(cmask.v));
-  lcn_launch(k_mask_scalars, dim3(1), dim3(320), 0, st, params, m->mask_off, m->sup, cmask, m->n_lin, m->d.max_norm, sc, mask);
-  LCN_CHECK_LAUNCH();
   int last = m->n_lin - 1;
   int n_mid = m->n_lin - 2;
-  const bool use_tc = true;                          // both paths run the mid layers on the tensor cores
   const bool x3 = m->d.path == LCN_PATH_FP32;
-  // the edge-layer packs (four small dependent launches) run on the model's side stream next to the mid-layer pack
+  const bool bf = m->d.path == LCN_PATH_BF16;
+  // With mid layers and a first layer of <= 64 input features (every configuration of the reference) the weight
+  // preparation is two concurrent launches: k_pack_mid on the caller's stream (it also stores the mask values and the
+  // per-layer scalars for the kernels that follow) and k_pack_edges on the model's side stream.  Otherwise the general
+  // sequence k_mask_scalars -> k_pack_edge (-> bf16 tiles) per edge layer.
+  const bool fused_prep = n_mid > 0 && m->L[0].Kin <= 64;
+  if (!fused_prep) {
+    lcn_launch(k_mask_scalars, dim3(1), dim3(320), 0, st, params, m->mask_off, m->sup, cmask, m->n_lin, m->d.max_norm, sc, mask);
+    LCN_CHECK_LAUNCH();
+  }
   std::unique_lock<std::mutex> aux_lock;
   LcnAux* ax = nullptr;
-  if (use_tc && n_mid > 0) {
+  if (n_mid > 0) {
     aux_lock = std::unique_lock<std::mutex>(m->aux.mu);
     ax = lcn_aux_get(m);
     if (ax == nullptr) aux_lock.unlock();
@@ -284,13 +366,20 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
     LCN_CHECK_CUDA(cudaEventRecord(ax->ev_go, st));
     LCN_CHECK_CUDA(cudaStreamWaitEvent(est, ax->ev_go, 0));
   }
-  // two dependent pairs of small launches (dense masked weights, then their bf16 tiles): the first layer's pair on the
-  // side stream, the last layer's pair behind the mid-layer pack on the caller's stream -- the tail is one pair long
-  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
-                                  reinterpret_cast<float*>(ws + lay.off_wm_first));
-  if (m->d.path == LCN_PATH_BF16 && m->L[0].Kin <= 64)
-    lcn_launch(k_pack_first16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
-                                                  m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
+  if (fused_prep) {
+    lcn_launch(k_pack_edges, dim3(LCN_J * m->FC, 4, 2), dim3(256), 0, est, params, m->L[0].w_off, m->L[last].w_off, m->d.in_F,
+               m->d.F, m->P, last, static_cast<const LayerScalars*>(sc), m->mask_off, cmask, m->sup, m->d.max_norm,
+               reinterpret_cast<float*>(ws + lay.off_wm_first), reinterpret_cast<float*>(ws + lay.off_wm_last),
+               bf ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16) : nullptr,
+               bf ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f) : nullptr,
+               bf ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b) : nullptr);
+  } else {
+    lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, est, params + m->L[0].w_off, m->L[0].Fi, m->L[0].Fo, sc, 0, mask,
+                                    reinterpret_cast<float*>(ws + lay.off_wm_first));
+    if (bf && m->L[0].Kin <= 64)
+      lcn_launch(k_pack_first16, dim3(LCN_J * m->FC, 4), dim3(256), 0, est, reinterpret_cast<const float*>(ws + lay.off_wm_first), m->L[0].Kin,
+                                                    m->P, reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wf16));
+  }
   if (ax) LCN_CHECK_CUDA(cudaEventRecord(ax->ev_done, est));
   if (n_mid > 0) {
     lcn_launch(k_pack_mid, dim3(dim3(m->nnz * m->FC * m->FC, n_mid)), dim3(256), 0, st, 
@@ -299,14 +388,17 @@ int lcn_launch_prepare(const lcn_model* m, const float* params, char* ws, const 
         reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b),
         x3 ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16f_lo) : nullptr,
         x3 ? reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wp16b_lo) : nullptr,
-        x3 ? 1 : 0 /* fp32 copy: the parity tap of the fp32-parity path (lcn_model_read_tensor kind 2) */, 1);
+        x3 ? 1 : 0 /* fp32 copy: the parity tap of the fp32-parity path (lcn_model_read_tensor kind 2) */, 1,
+        m->mask_off, cmask, m->n_lin, m->d.max_norm, fused_prep ? sc : nullptr, fused_prep ? mask : nullptr);
   }
-  lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
-                                  reinterpret_cast<float*>(ws + lay.off_wm_last));
-  if (m->d.path == LCN_PATH_BF16)
-    lcn_launch(k_pack_last16, dim3(LCN_J * m->FC, 4), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_last),
-                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
-                                                 reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
+  if (!fused_prep) {
+    lcn_launch(k_pack_edge, dim3(64), dim3(256), 0, st, params + m->L[last].w_off, m->L[last].Fi, m->L[last].Fo, sc, last, mask,
+                                    reinterpret_cast<float*>(ws + lay.off_wm_last));
+    if (bf)
+      lcn_launch(k_pack_last16, dim3(LCN_J * m->FC, 4), dim3(256), 0, st, reinterpret_cast<const float*>(ws + lay.off_wm_last),
+                                                   reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16f),
+                                                   reinterpret_cast<__nv_bfloat16*>(ws + lay.off_wl16b));
+  }
   LCN_CHECK_LAUNCH();
   if (ax) LCN_CHECK_CUDA(cudaStreamWaitEvent(st, ax->ev_done, 0));
   return LCN_OK;
