@@ -1172,17 +1172,39 @@ __global__ void __launch_bounds__(EW_MAXT, 2) k_bn_bwd_apply(const T* __restrict
 // db[l][col] = sum over the per-block partial rows written by k_bn_bwd_apply.  grid (ceil(P/64), n_bn), 256 threads
 __global__ void __launch_bounds__(256) k_db_reduce(const float* __restrict__ dbpart, int nblocks, int P,
                                                    float* __restrict__ graw, LinTable lt_b /* w_off holds b_off */) {
+  // grid (P/64, n_bn): 16 row lanes x 16 column quads; a thread adds every 16th partial row of its 4 columns with four
+  // independent accumulators (all of its <= 19 loads in flight), then the lanes are combined in a fixed order
   lcn_pdl_prologue();
-  __shared__ float sh[4][64];
-  int l = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
-  float a = 0.f;
+  __shared__ float4 sh[16][16];
+  const int l = blockIdx.y, q = threadIdx.x & 15, lane = threadIdx.x >> 4;
+  const int c = blockIdx.x * 64 + q * 4;
+  float4 a[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < P) {
     const float* src = dbpart + (size_t)l * nblocks * P + c;
-    for (int b = sl; b < nblocks; b += 4) a += src[(size_t)b * P];
+    int b = lane;
+    for (; b + 48 < nblocks; b += 64) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(b + 16 * k) * P);
+        a[k].x += v.x; a[k].y += v.y; a[k].z += v.z; a[k].w += v.w;
+      }
+    }
+    for (int k = 0; b < nblocks; b += 16, ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)b * P);
+      a[k & 3].x += v.x; a[k & 3].y += v.y; a[k & 3].z += v.z; a[k & 3].w += v.w;
+    }
   }
-  sh[sl][threadIdx.x & 63] = a;
+  sh[lane][q] = make_float4((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
+                            (a[0].z + a[1].z) + (a[2].z + a[3].z), (a[0].w + a[1].w) + (a[2].w + a[3].w));
   __syncthreads();
-  if (sl == 0 && c < P) graw[lt_b.w_off[l] + c] = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+  if (lane == 0 && c < P) {
+    float4 r = sh[0][q];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) { r.x += sh[k][q].x; r.y += sh[k][q].y; r.z += sh[k][q].z; r.w += sh[k][q].w; }
+    *reinterpret_cast<float4*>(graw + lt_b.w_off[l] + c) = r;
+  }
 }
 
 // first layer weight gradient: dWm1[k][c] = sum_rows X[row][k] dZ0[row][c]  (dense 17*in_F x P)
@@ -1224,20 +1246,44 @@ __global__ void __launch_bounds__(256) k_first_wgrad(const float* __restrict__ x
 // chain rule through mask_weights / clip_by_norm / mask softmax, and the fused masked Adam
 // ------------------------------------------------------------------------------------------------
 // pairdot[l][p] = <dWm_l(block p), W_l(block p)>      grid (nnz, n_lin), 256 threads
-__global__ void k_pairdot(const float* __restrict__ params, const float* __restrict__ graw, LinTable lt,
-                          PairTable pt, float* __restrict__ pairdot) {
+__global__ void __launch_bounds__(256) k_pairdot(const float* __restrict__ params, const float* __restrict__ graw, LinTable lt,
+                                                 PairTable pt, float* __restrict__ pairdot) {
   lcn_pdl_prologue();
   __shared__ double sh[32];
   int p = blockIdx.x, l = blockIdx.y;
   int Fi = lt.Fi[l], Fo = lt.Fo[l], Kout = LCN_J * Fo;
   int i = pt.pi[p], j = pt.pj[p];
-  const float* w = params + lt.w_off[l];
-  const float* g = graw + lt.w_off[l];
+  const size_t base = (size_t)lt.w_off[l] + (size_t)(i * Fi) * Kout + j * Fo;
+  const float* w = params + base;
+  const float* g = graw + base;
   double s = 0.0;
-  for (int e = threadIdx.x; e < Fi * Fo; e += blockDim.x) {
-    int fi = e / Fo, fo = e - fi * Fo;
-    size_t o = (size_t)(i * Fi + fi) * Kout + j * Fo + fo;
-    s += (double)g[o] * (double)w[o];
+  if ((Fo & 3) == 0 && (base & 3) == 0) {
+    // 16-byte loads, four rows of the block in flight per thread
+    const int q = Fo >> 2, n4 = Fi * q;
+    for (int t0 = threadIdx.x; t0 < n4; t0 += 4 * 256) {
+      float4 wv[4], gv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = t0 + k * 256;
+        wv[k] = gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < n4) {
+          const int fi = t / q, c4 = (t - fi * q) * 4;
+          const size_t o = (size_t)fi * Kout + c4;
+          wv[k] = *reinterpret_cast<const float4*>(w + o);
+          gv[k] = *reinterpret_cast<const float4*>(g + o);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        s += (double)gv[k].x * (double)wv[k].x + (double)gv[k].y * (double)wv[k].y + (double)gv[k].z * (double)wv[k].z +
+             (double)gv[k].w * (double)wv[k].w;
+    }
+  } else {
+    for (int e = threadIdx.x; e < Fi * Fo; e += blockDim.x) {
+      int fi = e / Fo, fo = e - fi * Fo;
+      size_t o = (size_t)fi * Kout + fo;
+      s += (double)g[o] * (double)w[o];
+    }
   }
   s = block_reduce_sum_d(s, sh);
   if (threadIdx.x == 0) pairdot[l * LCN_J * LCN_J + p] = (float)s;
