@@ -230,7 +230,6 @@ extern "C" void lcn_model_destroy(lcn_model* m) {
   if (m->aux.ready) {
     cudaStreamDestroy(m->aux.st);
     cudaStreamDestroy(m->aux.xst);
-    cudaEventDestroy(m->aux.ev_x);
     cudaEventDestroy(m->aux.ev_xdone);
     cudaEventDestroy(m->aux.ev_go);
     cudaEventDestroy(m->aux.ev_done);

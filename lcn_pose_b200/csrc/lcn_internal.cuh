@@ -72,7 +72,7 @@ struct LcnAux {
   bool ready = false, failed = false;
   cudaStream_t st = nullptr;
   cudaStream_t xst = nullptr;        // data-parallel exchange of finished weight gradients (lcn_dp.cu), forked from `st`
-  cudaEvent_t ev_x = nullptr, ev_xdone = nullptr;
+  cudaEvent_t ev_xdone = nullptr;
   cudaEvent_t ev_go = nullptr, ev_done = nullptr, ev_ms = nullptr, ev_loss = nullptr;
   cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
 };

@@ -317,8 +317,8 @@ static LcnAux* lcn_aux_get(const lcn_model* m) {
   if (!a.ready) {
     bool ok = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&a.xst, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[10] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1], &a.ev_ms, &a.ev_loss, &a.ev_x, &a.ev_xdone};
-    for (int i = 0; i < 10 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
+    cudaEvent_t* evs[9] = {&a.ev_go, &a.ev_done, &a.ev_dz[0], &a.ev_dz[1], &a.ev_wg[0], &a.ev_wg[1], &a.ev_ms, &a.ev_loss, &a.ev_xdone};
+    for (int i = 0; i < 9 && ok; ++i) ok = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       (void)cudaGetLastError();
       a.failed = true;
