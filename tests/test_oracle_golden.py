@@ -134,3 +134,19 @@ def test_datareader_normalise_denormalise_pinned_to_reference(golden):
     den = O.denormalize(golden["dr_y_test"], res[:, 0], res[:, 1])
     np.testing.assert_allclose(den, golden["dr_denorm"], rtol=0, atol=1e-10)
     np.testing.assert_allclose(den, golden["dr_test_j3d"], rtol=0, atol=1e-9)     # denormalize inverts read_3d
+
+
+@pytest.mark.parametrize("k", [3, 2])
+def test_rotate_180_known_answer_of_the_reference_tests(k):
+    """The two cases of the reference's own tools/tests.py (TestRotateData): a 180-degree rotation about joint 0 maps
+    xy -> -(xy - pivot) + pivot and leaves the third coordinate alone.  (Those tests also expect the batch to double,
+    which tools/data.py:289-322 no longer does; the arithmetic they pin is what is checked here.)"""
+    data = np.zeros((1, 17, k))
+    for i in range(17):
+        data[0, i] = [i, i + 1, 1][:k]
+    rot = O.rotate_data(data, angle=180)
+    assert rot.shape == data.shape
+    pivot = data[0, 0, :2]
+    np.testing.assert_allclose(rot[0, :, :2], -(data[0, :, :2] - pivot) + pivot, atol=1e-6)
+    if k == 3:
+        np.testing.assert_allclose(rot[0, :, 2], data[0, :, 2])
